@@ -1,0 +1,116 @@
+/* ssp_b200 -- C ABI of the B200-native homography-warp correspondence path of Semantic-SuperPoint.
+ *
+ * The reference (Gabriel-SGama/Semantic-SuperPoint) has no FFI: its boundary for this path is a set of
+ * Python callables in utils/utils.py, Train_model_heatmap_all.py and export.py.  Every entry point below
+ * names the reference callable (file:line) it serves; the Python host side (semantic-superpoint_b200/*.py)
+ * re-exports those callables with unchanged signatures and binds them to this library through ctypes.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; tensors are contiguous fp32 NCHW
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or freed here
+ *   - `stream` is a cudaStream_t; calls are stream-ordered and never synchronise, except ssp_nms_fast /
+ *     ssp_box_nms whose reference API returns host data (they sync the stream to read counters)
+ *   - return value: 0 = ok, < 0 = argument error, > 0 = cudaError_t; ssp_last_error() gives the text
+ */
+#ifndef SSP_B200_H
+#define SSP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ssp_version(void);
+const char* ssp_last_error(void);
+int ssp_sm_count(void);
+
+/* ---- a1 / a10: warp_points (utils/utils.py:315-343), filter_points (:303-311),
+ *      warp_keypoints / keep_true_keypoints (evaluations/detector_evaluation.py:139-191) ---- */
+int ssp_warp_points(const float* pts /*[P,2] x,y*/, int P, const float* H /*[B,3,3]*/, int B,
+                    float* out /*[B,P,2]*/, void* stream);
+int ssp_warp_points_mask(const float* pts, int P, const float* H, int B, float shape_x, float shape_y,
+                         float* out /*[B,P,2]*/, uint8_t* keep /*[B,P] 0<=p<=shape-1*/, void* stream);
+int ssp_warp_keypoints_f64(const double* kp /*[K,2] x,y pixels*/, int K, const double* H /*[3,3]*/, double W,
+                           double Hh, double* out /*[K,2]*/, uint8_t* keep /*[K] 0<=x<W,0<=y<H*/, void* stream);
+
+/* ---- a2: inv_warp_image_batch / inv_warp_image (utils/utils.py:347-405).
+ *      xs[W], ys[H] = the normalised sampling grid (torch.linspace(-1,1,n) of the reference, :375).
+ *      mode 0 = bilinear, 1 = nearest; zeros padding, align_corners=True. ---- */
+int ssp_inv_warp_image(const float* img /*[B,C,H,W]*/, int B, int C, int H, int W, const float* Hinv /*[B,3,3]*/,
+                       const float* xs, const float* ys, int mode, float* out /*[B,C,H,W]*/, void* stream);
+
+/* ---- a3: compute_valid_mask (utils/utils.py:715-742): nearest warp of ones + erosion by an explicit
+ *      structuring element kern[kh,kw] (device, uint8) with anchor (ax,ay); kh == kw == 0 -> no erosion ---- */
+int ssp_valid_mask(int B, int H, int W, const float* Hinv, const float* xs, const float* ys, const uint8_t* kern,
+                   int kh, int kw, int ax, int ay, float* out /*[B,H,W]*/, void* stream);
+
+/* ---- a4: labels2Dto3D (utils/utils.py:408-440), getMasks (Train_model_frontend_all.py:373-386),
+ *      detector_loss (Train_model_heatmap_all.py:155-179) forward / backward.
+ *      fused2d = 0: target [B,65,Hc,Wc], mask [B,Hc,Wc] (the reference call signature)
+ *      fused2d = 1: target = labels_2D [B,1,H,W], mask = mask_2D [B,1,H,W] (labels2Dto3D+getMasks fused in)
+ *      out3 = { loss, numerator, sum(mask)+1e-5 } ---- */
+int ssp_labels2d_to_3d(const float* labels /*[B,1,H,W]*/, int B, int H, int W, int add_dustbin,
+                       float* out /*[B,64|65,H/8,W/8]*/, void* stream);
+int ssp_cell_mask(const float* mask2d /*[B,1,H,W]*/, int B, int H, int W, float* out /*[B,H/8,W/8]*/, void* stream);
+size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc);
+int ssp_detector_loss_fwd(const float* semi /*[B,65,Hc,Wc]*/, const float* target, const float* mask, int B, int Hc,
+                          int Wc, int fused2d, float* out3, void* ws, size_t ws_bytes, void* stream);
+int ssp_detector_loss_bwd(const float* semi, const float* target, const float* mask, int B, int Hc, int Wc,
+                          int fused2d, const float* fwd_out3, const float* gout /*[1]*/, float* dsemi, void* stream);
+
+/* ---- a6: flattenDetection (utils/utils.py:515-560) ---- */
+int ssp_flatten_detection(const float* semi /*[N,65,Hc,Wc]*/, int N, int Hc, int Wc, float* heat /*[N,1,8Hc,8Wc]*/,
+                          void* stream);
+
+/* ---- a7: combine_heatmap (export.py:49-60), batched over I source images ---- */
+int ssp_combine_heatmap(const float* heat /*[I,N,H,W]*/, const float* mask /*[I,N,H,W]*/,
+                        const float* Hinv /*[I,N,3,3]*/, int I, int N, int H, int W, const float* xs, const float* ys,
+                        float* out /*[I,H,W]*/, void* stream);
+
+/* ---- a8 / a9: getPtsFromHeatmap + nms_fast (utils/utils.py:581-609, 653-712), box_nms (:612-650).
+ *      stencil: device (2R+1)^2 bytes, 1 = suppressed offset.  pts: [I,3,capacity] float64 rows x,y,conf,
+ *      confidence-descending.  counts_host: HOST int[I]. ---- */
+size_t ssp_nms_ws_bytes(int I, int H, int W, int capacity);
+int ssp_nms_fast(const float* heat /*[I,H,W]*/, int I, int H, int W, float conf_thresh, int R, const uint8_t* stencil,
+                 int border, int capacity, double* pts, int* counts_host, void* ws, size_t ws_bytes, void* stream);
+int ssp_box_nms(const float* prob /*[I,H,W]*/, int I, int H, int W, float min_prob, int R, const uint8_t* stencil,
+                float* out /*[I,H,W]*/, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a5: descriptor_loss (utils/utils.py:779-893), forward and backward, split into stages.
+ *      Nc = Hc*Wc, Nc_pad = ceil(Nc/128)*128.  wpts [B,Nc_pad,2], mv_pad [B,Nc_pad],
+ *      bitsR/bitsC [B,Nc_pad/32,Nc_pad] u32 indicator bit-matrices, partials = per-CTA (unweighted, weighted)
+ *      double pairs.  out8 = { loss, pos_sum, neg_sum, norm, num_loss, num_pos, num_neg, sum(mask_valid) } ---- */
+int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/, int B, int Hc, int Wc,
+                      int cell, float* wpts, float* mv_pad, void* stream);
+int ssp_desc_pos_nblocks(int B, int Nc);
+int ssp_desc_pos_fwd(const float* D /*[B,Dch,Hc,Wc]*/, const float* Dw, const float* wpts, const float* mv_pad, int B,
+                     int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos, double* partials,
+                     void* stream);
+int ssp_desc_dense_simt_nblocks(int B, int Nc);
+int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* wpts, const float* mv_pad, int B, int Hc,
+                            int Wc, int Dch, int cell, float dist, float mneg, double* partials, uint32_t* bitsR,
+                            uint32_t* bitsC, float* dbgS /*[B,Nc,Nc] or NULL*/, void* stream);
+int ssp_desc_pack(const float* src /*[B,Dch,Nc]*/, const float* scale /*[B,Nc_pad] or NULL*/, int B, int Dch, int Nc,
+                  void* hi /*bf16 [B,Nc_pad,Dch]*/, void* lo /*or NULL*/, void* stream);
+int ssp_desc_dense_tc_nblocks(int B, int Nc);
+int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* wpts,
+                          const float* mv_pad, int B, int Hc, int Wc, int cell, float dist, float mneg,
+                          double* partials, uint32_t* bitsR, uint32_t* bitsC, float* dbgS, void* stream);
+int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const float* mv_pad, int B,
+                      int Hc, int Wc, float* out8, void* stream);
+int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,
+                       void* stream);
+int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)*/, const float* out8, int B,
+                   int Nc_pad, float* alpha /*[B,Nc_pad]*/, void* stream);
+int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src /*[B,Dch,Nc]*/, const float* colscale,
+                            const float* rowscale, int B, int Dch, int Nc, float* out /*[B,Dch,Nc]*/, void* stream);
+int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale, int B, int Nc,
+                          float* out /*[B,256,Nc]*/, void* stream);
+int ssp_desc_pos_bwd(const float* D, const float* Dw, const float* wpts, const float* mv_pad, const float* g3,
+                     const float* out8, int B, int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos,
+                     float* dD, float* dDw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSP_B200_H */

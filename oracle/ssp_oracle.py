@@ -1,0 +1,391 @@
+"""CPU ORACLE for the homography-warp correspondence path -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+A numpy restatement of the reference algorithms (Gabriel-SGama/Semantic-SuperPoint), each function citing
+the reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product package (semantic-superpoint_b200/) never does.
+
+Pinning: the reference ships no golden vectors or assertions for this path, so this oracle is
+pinned against outputs of the LIVE reference functions, generated in the authoring container by
+tests/golden/make_golden.py (which imports /root/reference) and committed as tests/golden/*.npz;
+tests/test_oracle_golden.py replays them.  Third-party arithmetic on the path that is restated here:
+torch 2.11 (F.grid_sample bilinear/nearest zeros-padding align_corners=True, softmax, BCELoss with the
+-100 log clamp, torch.norm), torchvision 0.26 ops.nms, opencv 4.13 getStructuringElement(MORPH_ELLIPSE) +
+erode (reference pins opencv-python 3.4.2.16).  The only torch call kept is torch.linspace for the
+sampling-grid table (the reference builds it with a CPU torch.linspace, utils/utils.py:375, whose rounding
+differs by 1 ulp from the textbook formula).
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# warps
+# ------------------------------------------------------------------------------------------------
+def linspace_grid(n):
+    import torch
+    return torch.linspace(-1, 1, n).numpy().copy()
+
+
+def warp_points(points, homographies):
+    """utils/utils.py:315-343.  points [P,2] (x,y); homographies [3,3] or [B,3,3] -> [P,2] or [B,P,2] (fp32)."""
+    H = np.asarray(homographies, dtype=f32)
+    no_batches = H.ndim == 2
+    H = H.reshape(-1, 3, 3)
+    p = np.concatenate([np.asarray(points, dtype=f32), np.ones((len(points), 1), f32)], axis=1)  # [P,3]
+    w = np.einsum("bij,pj->bpi", H, p).astype(f32)
+    out = (w[:, :, :2] / w[:, :, 2:]).astype(f32)
+    return out[0] if no_batches else out
+
+
+def filter_points(points, shape, return_mask=False):
+    """utils/utils.py:303-311.  0 <= p <= shape-1 in every coordinate (inclusive)."""
+    points = np.asarray(points, dtype=f32)
+    shape = np.asarray(shape, dtype=f32)
+    mask = np.all((points >= 0) & (points <= shape - 1), axis=-1)
+    return (points[mask], mask) if return_mask else points[mask]
+
+
+def warp_keypoints_f64(keypoints, H):
+    """evaluations/detector_evaluation.py:139-150: float64 [x,y,1] H^T / z in pixel coordinates."""
+    kp = np.asarray(keypoints, dtype=np.float64)[:, :2]
+    hom = np.concatenate([kp, np.ones((kp.shape[0], 1))], axis=1)
+    w = hom @ np.asarray(H, dtype=np.float64).T
+    return w[:, :2] / w[:, 2:]
+
+
+def keep_in_bounds_f64(points, shape):
+    """evaluations/detector_evaluation.py:160-191: 0 <= x < W and 0 <= y < H (strict upper bound). shape=(H,W)."""
+    return (points[:, 0] >= 0) & (points[:, 0] < shape[1]) & (points[:, 1] >= 0) & (points[:, 1] < shape[0])
+
+
+def _unnormalize(coord, size):
+    # ATen grid_sampler_unnormalize, align_corners=True: ((coord + 1) / 2) * (size - 1)
+    return ((coord + f32(1)) / f32(2)) * f32(size - 1)
+
+
+def grid_sample(img, grid, mode):
+    """torch F.grid_sample(img [B,C,H,W], grid [B,Ho,Wo,2] (x,y), mode, padding zeros, align_corners=True)."""
+    img = np.asarray(img, dtype=f32)
+    B, C, H, W = img.shape
+    ix = _unnormalize(grid[..., 0].astype(f32), W)
+    iy = _unnormalize(grid[..., 1].astype(f32), H)
+    out = np.zeros((B, C) + ix.shape[1:], dtype=f32)
+    bidx = np.arange(B)[:, None, None]
+    if mode == "nearest":
+        rx, ry = np.rint(ix), np.rint(iy)  # std::nearbyint = round half to even
+        ok = (rx >= 0) & (rx < W) & (ry >= 0) & (ry < H)
+        xi = np.where(ok, rx, 0).astype(np.int64)
+        yi = np.where(ok, ry, 0).astype(np.int64)
+        for c in range(C):
+            out[:, c] = np.where(ok, img[bidx, c, yi, xi], f32(0))
+        return out
+    x0, y0 = np.floor(ix), np.floor(iy)
+    x1, y1 = x0 + 1, y0 + 1
+    wts = [((x1 - ix) * (y1 - iy), x0, y0), ((ix - x0) * (y1 - iy), x1, y0),
+           ((x1 - ix) * (iy - y0), x0, y1), ((ix - x0) * (iy - y0), x1, y1)]
+    for wgt, xx, yy in wts:
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        xi = np.where(ok, xx, 0).astype(np.int64)
+        yi = np.where(ok, yy, 0).astype(np.int64)
+        for c in range(C):
+            out[:, c] += np.where(ok, img[bidx, c, yi, xi] * wgt.astype(f32), f32(0))
+    return out
+
+
+def inv_warp_image_batch(img, mat_homo_inv, mode="bilinear"):
+    """utils/utils.py:347-385."""
+    img = np.asarray(img, dtype=f32)
+    if img.ndim in (2, 3):
+        img = img.reshape(1, 1, img.shape[0], img.shape[1])
+    Hm = np.asarray(mat_homo_inv, dtype=f32).reshape(-1, 3, 3)
+    B, C, H, W = img.shape
+    xs, ys = linspace_grid(W), linspace_grid(H)
+    gx, gy = np.meshgrid(xs, ys)  # [H,W] each, (x,y) at pixel (row,col)
+    pts = np.stack([gx.reshape(-1), gy.reshape(-1)], axis=1)
+    src = warp_points(pts, Hm).reshape(B, H, W, 2)
+    return grid_sample(img, src, mode)
+
+
+def ellipse_kernel(radius):
+    """cv2.getStructuringElement(MORPH_ELLIPSE, (2r,2r)) (opencv modules/imgproc/src/morph.dispatch.cpp)."""
+    k = int(radius) * 2
+    r = c = k // 2
+    inv_r2 = 1.0 / (r * r) if r else 0.0
+    ker = np.zeros((k, k), np.uint8)
+    for i in range(k):
+        dy = i - r
+        if abs(dy) <= r:
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+            ker[i, max(c - dx, 0):min(c + dx + 1, k)] = 1
+    return ker
+
+
+def erode(mask, kernel):
+    """cv2.erode(mask, kernel): min over the kernel footprint, anchor (kw//2, kh//2), out-of-image taps ignored."""
+    H, W = mask.shape
+    kh, kw = kernel.shape
+    ay, ax = kh // 2, kw // 2
+    out = np.ones_like(mask)
+    for ky in range(kh):
+        for kx in range(kw):
+            if not kernel[ky, kx]:
+                continue
+            dy, dx = ky - ay, kx - ax
+            sh = np.ones_like(mask)
+            ys0, ys1 = max(0, -dy), min(H, H - dy)
+            xs0, xs1 = max(0, -dx), min(W, W - dx)
+            sh[ys0:ys1, xs0:xs1] = mask[ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx]
+            out = np.minimum(out, sh)
+    return out
+
+
+def compute_valid_mask(image_shape, inv_homography, erosion_radius=0):
+    """utils/utils.py:715-742."""
+    Hm = np.asarray(inv_homography, dtype=f32).reshape(-1, 3, 3)
+    B = Hm.shape[0]
+    H, W = int(image_shape[0]), int(image_shape[1])
+    mask = inv_warp_image_batch(np.ones((B, 1, H, W), f32), Hm, mode="nearest").reshape(B, H, W)
+    if erosion_radius > 0:
+        ker = ellipse_kernel(erosion_radius)
+        for i in range(B):
+            mask[i] = erode(mask[i], ker)
+    return mask
+
+
+# ------------------------------------------------------------------------------------------------
+# detector labels / loss / heatmap
+# ------------------------------------------------------------------------------------------------
+def space_to_depth(x, bs=8):
+    """utils/d2s.py:27-44 == pixel_unshuffle: channel = dy*bs + dx."""
+    B, C, H, W = x.shape
+    assert C == 1
+    y = x.reshape(B, H // bs, bs, W // bs, bs).transpose(0, 2, 4, 1, 3)
+    return y.reshape(B, bs * bs, H // bs, W // bs)
+
+
+def depth_to_space(x, bs=8):
+    """utils/d2s.py:8-25 == pixel_shuffle."""
+    B, C, Hc, Wc = x.shape
+    y = x.reshape(B, bs, bs, Hc, Wc).transpose(0, 3, 1, 4, 2)
+    return y.reshape(B, 1, Hc * bs, Wc * bs)
+
+
+def labels2Dto3D(labels, cell_size=8, add_dustbin=True):
+    """utils/utils.py:408-440."""
+    lab = space_to_depth(np.asarray(labels, dtype=f32), cell_size)
+    if add_dustbin:
+        dust = f32(1) - lab.sum(axis=1, dtype=f32)
+        dust[dust < 1.0] = 0
+        lab = np.concatenate([lab, dust[:, None]], axis=1)
+        dn = lab.sum(axis=1, dtype=f32)
+        lab = lab / dn[:, None]
+    return lab.astype(f32)
+
+
+def getMasks(mask_2D, cell_size=8):
+    """Train_model_frontend_all.py:373-386."""
+    return np.prod(space_to_depth(np.asarray(mask_2D, dtype=f32), cell_size), axis=1, dtype=f32)
+
+
+def softmax(x, axis):
+    m = x.max(axis=axis, keepdims=True)
+    e = np.exp(x - m)
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def detector_loss(semi, target, mask, grad=False):
+    """Train_model_heatmap_all.py:155-179 (softmax branch): BCE over softmax probabilities, masked mean.
+    Computed in float64 from the fp32 inputs; with grad=True also returns dLoss/dsemi (BCELoss backward uses
+    (p - t) / max(p (1 - p), 1e-12), softmax backward p * (g - sum p g))."""
+    x = np.asarray(semi, dtype=np.float64)
+    t = np.asarray(target, dtype=np.float64)
+    m = np.asarray(mask, dtype=np.float64)
+    p = softmax(x, 1)
+    with np.errstate(divide="ignore"):
+        bce = -(t * np.maximum(np.log(p), -100) + (1 - t) * np.maximum(np.log(1 - p), -100))
+    den = m.sum() + 1e-5
+    loss = (bce.sum(axis=1) * m).sum() / den
+    if not grad:
+        return f32(loss)
+    dp = (m / den)[:, None] * (p - t) / np.maximum(p * (1 - p), 1e-12)
+    dx = p * (dp - (p * dp).sum(axis=1, keepdims=True))
+    return f32(loss), dx.astype(f32)
+
+
+def flattenDetection(semi):
+    """utils/utils.py:515-560: softmax(65) -> drop dustbin -> depth_to_space(8).  [B,65,Hc,Wc] -> [B,1,H,W]."""
+    semi = np.asarray(semi, dtype=f32)
+    batch = semi.ndim == 4
+    if not batch:
+        semi = semi[None]
+    dense = softmax(semi, 1).astype(f32)
+    heat = depth_to_space(dense[:, :-1])
+    return heat if batch else heat[0]
+
+
+def combine_heatmap(heatmap, inv_homographies, mask_2D):
+    """export.py:49-60.  heatmap/mask [N,1,H,W], inv_homographies [1,N,3,3] -> [1,H,W]."""
+    heatmap = np.asarray(heatmap, dtype=f32) * np.asarray(mask_2D, dtype=f32)
+    Hm = np.asarray(inv_homographies, dtype=f32)[0]
+    h = inv_warp_image_batch(heatmap, Hm, mode="bilinear").sum(axis=0, dtype=f32)
+    m = inv_warp_image_batch(mask_2D, Hm, mode="bilinear").sum(axis=0, dtype=f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return h / m
+
+
+# ------------------------------------------------------------------------------------------------
+# keypoints
+# ------------------------------------------------------------------------------------------------
+def nms_fast(in_corners, H, W, dist_thresh):
+    """utils/utils.py:653-712, with numpy's unstable default argsort replaced by kind='stable' so that ties
+    have a defined order (the reference leaves it undefined)."""
+    grid = np.zeros((H, W), dtype=int)
+    inds = np.zeros((H, W), dtype=int)
+    inds1 = np.argsort(-in_corners[2, :], kind="stable")
+    corners = in_corners[:, inds1]
+    rcorners = corners[:2, :].round().astype(int)
+    if rcorners.shape[1] == 0:
+        return np.zeros((3, 0)).astype(int), np.zeros(0).astype(int)
+    if rcorners.shape[1] == 1:
+        return np.vstack((rcorners, in_corners[2])).reshape(3, 1), np.zeros((1)).astype(int)
+    grid[rcorners[1], rcorners[0]] = 1
+    inds[rcorners[1], rcorners[0]] = np.arange(rcorners.shape[1])
+    pad = dist_thresh
+    grid = np.pad(grid, ((pad, pad), (pad, pad)), mode="constant")
+    for i in range(rcorners.shape[1]):
+        x, y = rcorners[0, i] + pad, rcorners[1, i] + pad
+        if grid[y, x] == 1:
+            grid[y - pad:y + pad + 1, x - pad:x + pad + 1] = 0
+            grid[y, x] = -1
+    keepy, keepx = np.where(grid == -1)
+    keepy, keepx = keepy - pad, keepx - pad
+    inds_keep = inds[keepy, keepx]
+    out = corners[:, inds_keep]
+    inds2 = np.argsort(-out[-1, :], kind="stable")
+    return out[:, inds2], inds1[inds_keep[inds2]]
+
+
+def getPtsFromHeatmap(heatmap, conf_thresh, nms_dist, border_remove=4):
+    """utils/utils.py:581-609 (stable sorts).  Returns float64 [3,K]: x, y, conf, confidence-descending."""
+    H, W = heatmap.shape
+    ys, xs = np.where(heatmap >= conf_thresh)
+    if len(ys) == 0:
+        return np.zeros((3, 0))
+    pts = np.zeros((3, len(ys)))
+    pts[0, :], pts[1, :], pts[2, :] = xs, ys, heatmap[ys, xs]
+    pts, _ = nms_fast(pts, H, W, dist_thresh=nms_dist)
+    inds = np.argsort(pts[2, :], kind="stable")
+    pts = pts[:, inds[::-1]]
+    b = border_remove
+    rm = (pts[0, :] < b) | (pts[0, :] >= (W - b)) | (pts[1, :] < b) | (pts[1, :] >= (H - b))
+    return pts[:, ~rm]
+
+
+def box_nms(prob, size, iou=0.1, min_prob=0.01):
+    """utils/utils.py:612-650 with torchvision.ops.nms restated: greedy in descending score (stable), a box is
+    dropped when its IoU with an already kept box exceeds `iou` (fp32 arithmetic like torchvision)."""
+    prob = np.asarray(prob, dtype=f32)
+    ys, xs = np.nonzero(prob > f32(min_prob))
+    out = np.zeros_like(prob)
+    if len(ys) == 0:
+        return out
+    half = f32(size / 2.0)
+    pts = np.stack([ys, xs], axis=1).astype(f32)
+    boxes = np.concatenate([pts - half, pts + half], axis=1)
+    scores = prob[ys, xs]
+    order = np.argsort(-scores, kind="stable")
+    area = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+    alive = np.ones(len(order), bool)
+    for ii, i in enumerate(order):
+        if not alive[i]:
+            continue
+        rest = order[ii + 1:]
+        rest = rest[alive[rest]]
+        if len(rest) == 0:
+            break
+        w = np.maximum(f32(0), np.minimum(boxes[i, 2], boxes[rest, 2]) - np.maximum(boxes[i, 0], boxes[rest, 0]))
+        h = np.maximum(f32(0), np.minimum(boxes[i, 3], boxes[rest, 3]) - np.maximum(boxes[i, 1], boxes[rest, 1]))
+        inter = (w * h).astype(f32)
+        ovr = inter / (area[i] + area[rest] - inter)
+        alive[rest[ovr > f32(iou)]] = False
+    keep = np.array([i for i in order if alive[i]], dtype=int)
+    out[ys[keep], xs[keep]] = scores[keep]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# descriptor loss
+# ------------------------------------------------------------------------------------------------
+def descriptor_pair_mask(homographies, Hc, Wc, cell_size=8, descriptor_dist=4):
+    """utils/utils.py:824-860: warped cell centres and the [B,Nc,Nc] correspondence mask (fp32 op order)."""
+    Hm = np.asarray(homographies, dtype=f32).reshape(-1, 3, 3)
+    Hpx, Wpx = f32(Hc * cell_size), f32(Wc * cell_size)
+    kk, ll = np.meshgrid(np.arange(Hc), np.arange(Wc), indexing="ij")
+    cy = (kk.reshape(-1) * cell_size + cell_size // 2).astype(f32)
+    cx = (ll.reshape(-1) * cell_size + cell_size // 2).astype(f32)
+    ny = cy / Hpx * f32(2) - f32(1)  # normPts divides by H, W
+    nx = cx / Wpx * f32(2) - f32(1)
+    w = warp_points(np.stack([nx, ny], 1), Hm)  # [B,Nc,2] (x,y)
+    wx = (w[..., 0] + f32(1)) * Wpx / f32(2)
+    wy = (w[..., 1] + f32(1)) * Hpx / f32(2)
+    dy = cy[None, None, :] - wy[:, :, None]
+    dx = cx[None, None, :] - wx[:, :, None]
+    dist = np.sqrt((dy * dy + dx * dx).astype(f32)).astype(f32)
+    return (dist <= f32(descriptor_dist)).astype(f32), np.stack([wx, wy], -1)
+
+
+def descriptor_loss(descriptors, descriptors_warped, homographies, mask_valid=None, cell_size=8, lamda_d=250,
+                    descriptor_dist=4, grad=None, return_mask=False, chunk=1024):
+    """utils/utils.py:779-893 restated with a chunked matmul for the all-pairs dot product (the reference
+    materialises [B,Hc,Wc,Hc,Wc,256]).  Sums in float64.  grad = (g_loss, g_pos, g_neg) additionally returns
+    d/d descriptors and d/d descriptors_warped of  g_loss*loss + g_pos*pos_sum + g_neg*neg_sum."""
+    D = np.asarray(descriptors, dtype=f32)
+    Dw = np.asarray(descriptors_warped, dtype=f32)
+    B, Dch, Hc, Wc = D.shape
+    Nc = Hc * Wc
+    mask, _ = descriptor_pair_mask(homographies, Hc, Wc, cell_size, descriptor_dist)
+    mv = np.ones((B, Nc), f32) if mask_valid is None else np.asarray(mask_valid, dtype=f32).reshape(B, Nc)
+    norm = f32(B) * (mv.sum(dtype=f32) + f32(1)) * f32(Hc) * f32(Wc)
+    A = D.reshape(B, Dch, Nc).transpose(0, 2, 1)  # [B,Nc,D]
+    Bm = Dw.reshape(B, Dch, Nc)                   # [B,D,Nc]
+    s_loss = s_pos = s_neg = 0.0
+    if grad is not None:
+        gl, gp, gn = [float(g) for g in grad]
+        dD = np.zeros((B, Nc, Dch), np.float64)
+        dDw = np.zeros((B, Dch, Nc), np.float64)
+    for b in range(B):
+        for r0 in range(0, Nc, chunk):
+            r1 = min(Nc, r0 + chunk)
+            dot = A[b, r0:r1] @ Bm[b]  # [r,Nc]
+            m = mask[b, r0:r1]
+            pos = np.maximum(f32(1.0) - dot, f32(0))
+            neg = np.maximum(dot - f32(0.2), f32(0))
+            lp = f32(lamda_d) * m * pos
+            ln = (f32(1) - m) * neg
+            s_loss += float(((lp + ln) * mv[b][None, :]).sum(dtype=np.float64))
+            s_pos += float(lp.sum(dtype=np.float64))
+            s_neg += float(ln.sum(dtype=np.float64))
+            if grad is not None:
+                x_p, x_n = f32(1.0) - dot, dot - f32(0.2)
+                ip = np.where(x_p > 0, 1.0, np.where(x_p == 0, 0.5, 0.0))  # torch.max(a, 0-tensor) ties split
+                inn = np.where(x_n > 0, 1.0, np.where(x_n == 0, 0.5, 0.0))
+                wl = gl * mv[b][None, :].astype(np.float64)
+                G = (-(lamda_d * m) * ip * (wl + gp) + (1.0 - m) * inn * (wl + gn)) / float(norm)
+                dD[b, r0:r1] += G @ Bm[b].T.astype(np.float64)
+                dDw[b] += A[b, r0:r1].T.astype(np.float64) @ G
+    out = [f32(s_loss / float(norm)), f32(s_pos / float(norm)), f32(s_neg / float(norm))]
+    res = (out[0], mask.reshape(B, Hc, Wc, Hc, Wc) if return_mask else None, out[1], out[2])
+    if grad is not None:
+        gD = dD.transpose(0, 2, 1).reshape(B, Dch, Hc, Wc).astype(f32)
+        gDw = dDw.reshape(B, Dch, Hc, Wc).astype(f32)
+        return res + (gD, gDw)
+    return res
+
+
+def descriptor_dots(descriptors, descriptors_warped):
+    """float64 all-pairs dot products [B,Nc,Nc] (used by tests to locate hinge kinks)."""
+    D = np.asarray(descriptors, dtype=np.float64)
+    Dw = np.asarray(descriptors_warped, dtype=np.float64)
+    B, Dch = D.shape[:2]
+    return np.einsum("bdi,bdj->bij", D.reshape(B, Dch, -1), Dw.reshape(B, Dch, -1))

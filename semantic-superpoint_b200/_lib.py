@@ -1,0 +1,125 @@
+"""ctypes binding of lib/libssp_b200.so (include/ssp_b200.h).
+
+The product path has no fallback: if the library is missing it is built with nvcc, and if that fails (or a
+tensor is not on a CUDA device) the call raises.  Nothing here imports oracle/.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_F = _c.c_float
+_D = _c.c_double
+_Z = _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ssp_b200.h one to one (tests/test_abi.py checks this)
+SIGNATURES = {
+    "ssp_version": (_I, []),
+    "ssp_last_error": (_c.c_char_p, []),
+    "ssp_sm_count": (_I, []),
+    "ssp_warp_points": (_I, [_P, _I, _P, _I, _P, _P]),
+    "ssp_warp_points_mask": (_I, [_P, _I, _P, _I, _F, _F, _P, _P, _P]),
+    "ssp_warp_keypoints_f64": (_I, [_P, _I, _P, _D, _D, _P, _P, _P]),
+    "ssp_inv_warp_image": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "ssp_valid_mask": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "ssp_labels2d_to_3d": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "ssp_cell_mask": (_I, [_P, _I, _I, _I, _P, _P]),
+    "ssp_detector_loss_ws_bytes": (_Z, [_I, _I, _I]),
+    "ssp_detector_loss_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "ssp_detector_loss_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ssp_flatten_detection": (_I, [_P, _I, _I, _I, _P, _P]),
+    "ssp_combine_heatmap": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ssp_nms_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "ssp_nms_fast": (_I, [_P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _Z, _P]),
+    "ssp_box_nms": (_I, [_P, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
+    "ssp_desc_geometry": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "ssp_desc_pos_nblocks": (_I, [_I, _I]),
+    "ssp_desc_pos_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
+    "ssp_desc_dense_simt_nblocks": (_I, [_I, _I]),
+    "ssp_desc_dense_fwd_simt": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "ssp_desc_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
+    "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P]),
+    "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
+    "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "ssp_desc_pos_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # kernels-launching C-ABI calls made through this module (bench.py reports it)
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) the shared library and declare every prototype."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RuntimeError("libssp_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+            _build.build_library()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = header / library mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ssp_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise RuntimeError(ssp_last_error()) on failure."""
+    global launch_count
+    launch_count += 1
+    check(getattr(load(), name)(*args), name)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else _c.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    return _c.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "ssp_b200 has no CPU path: got a %s tensor; move inputs to a CUDA device (sm_100a)" % t.device
+            )
+
+
+def f32c(t, device=None):
+    """fp32, contiguous, 16-byte aligned view/copy of t (optionally moved to `device`)."""
+    if device is not None and t.device != torch.device(device):
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t

@@ -1,0 +1,45 @@
+// Shared definitions for the dense descriptor hinge loss (reference: utils/utils.py:779-893).
+//
+// Decomposition used by every engine (SIMT fp32 and tcgen05):
+//   loss terms split into the sparse POSITIVE pairs (mask == 1, <= a handful per row; evaluated in
+//   exact fp32 by the pos kernels, weight lamda_d) and the dense NEGATIVE part over all other pairs
+//   (hinge max(dot - margin_neg, 0), evaluated by the GEMM kernel with the positive pairs zeroed).
+//   The GEMM kernel also emits the indicator bit-matrix I[r,c] = (1 - mask) * 1[dot > margin_neg] in two
+//   orientations so that the backward is two pure indicator-GEMMs and never recomputes S.
+//
+// Layouts:
+//   wpts   [B, Nc_pad] float2  warped cell centres (x, y) in pixels; padded rows hold SSP_FAR
+//   mv_pad [B, Nc_pad] float   mask_valid per warped-image cell, zero padded
+//   bitsR  [B, Nc_pad/32, Nc_pad] u32   word (cw, r): columns 32cw..32cw+31 of row r
+//   bitsC  [B, Nc_pad/32, Nc_pad] u32   word (rw, c): rows 32rw..32rw+31 of column c
+//   Nc_pad = ceil(Nc / 128) * 128
+#pragma once
+#include "common.cuh"
+
+#define SSP_FAR 1.0e30f
+#define DESC_PAD 128
+
+struct DescGeom {
+  int B, Hc, Wc, Nc, Nc_pad, Dch;
+  int cell;          // cell size (8)
+  float dist;        // descriptor_dist
+  float lamda;       // lamda_d
+  float mpos, mneg;  // margins 1.0 / 0.2
+};
+
+static inline int desc_nc_pad(int Nc) { return (Nc + DESC_PAD - 1) / DESC_PAD * DESC_PAD; }
+
+// centre of cell index c in pixels, (x, y)   [utils/utils.py:829-831]
+__device__ __forceinline__ void cell_center(int c, int Wc, int cell, float& cx, float& cy) {
+  int k = c / Wc, l = c - k * Wc;
+  cy = (float)(k * cell + cell / 2);
+  cx = (float)(l * cell + cell / 2);
+}
+
+// mask = ||centre - warped|| <= dist, evaluated in fp32 exactly in this order everywhere
+// [utils/utils.py:854-857]
+__device__ __forceinline__ bool pair_positive(float wx, float wy, float cx, float cy, float dist) {
+  float dy = cy - wy, dx = cx - wx;
+  float d2 = __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
+  return __fsqrt_rn(d2) <= dist;
+}

@@ -1,0 +1,495 @@
+// tcgen05 / TMEM / TMA engine for the dense descriptor loss (sm_100a).
+// Reference semantics: utils/utils.py:863-890 (all-pairs dot product + hinge + masks + reductions).
+//
+// Operands are bf16 K-major planes [B, Nc_pad, 256] produced by desc_pack_kernel: plane "hi" alone
+// (mode bf16) or hi + lo with three MMA chains hi*hi + lo*hi + hi*lo (mode bf16x3, ~2^-16 relative
+// product error = fp32-grade dot products on the tensor pipe).
+//
+// Forward kernel, one CTA per (pair b, 128-row tile):
+//   warp 8      TMA producer: A rows (all 256 channels, resident) once, then the B ring of 16 KB
+//               K-chunks (64 channels x 128 cells, SWIZZLE_128B) for every 128-column tile
+//   warp 9      MMA issuer: tcgen05.mma kind::f16 M=128 N=128 K=16 into a double-buffered TMEM
+//               accumulator (2 x 128 columns); tcgen05.commit frees ring slots / publishes tiles
+//   warps 0-7   epilogue: tcgen05.ld 32x32b (one row per thread, 64 columns per warp), hinge,
+//               positive-pair masking on the few warps that can contain one, mask_valid weighting,
+//               running sums, indicator bit-matrix in both orientations.  The pair matrix never
+//               reaches HBM.
+//
+// Backward kernel = indicator GEMM  out[b, d, r] = rowscale[r] * sum_k bit(r,k) * Bp[b, k, d]:
+//   warps 0-3   expand 64 indicator bits per row into bf16 {0,1} and tcgen05.st them as the A
+//               operand into TMEM (A never touches shared memory); later the epilogue
+//   warp 4      TMA producer of B tiles [64 cells x 256 channels] (MN-major, SWIZZLE_128B)
+//   warp 5      MMA issuer, M=128 N=256 K=16, A from TMEM, fp32 accumulator of 256 TMEM columns
+#include "desc_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128;        // rows per CTA
+constexpr int BN = 128;        // columns per accumulator tile
+constexpr int KD = 256;        // descriptor channels (GEMM K of the forward)
+constexpr int KC = 64;         // channels per smem chunk = 128 B of bf16 = one swizzle row
+constexpr int NKC = KD / KC;   // 4
+constexpr int CHUNK_BYTES = BM * KC * 2;  // 16 KB
+constexpr int FWD_THREADS = 320;
+constexpr int BAR_BYTES = 1024;
+
+template <int P> struct FwdCfg {
+  static constexpr int NSTAGE = (P == 1) ? 8 : 5;
+  static constexpr int A_BYTES = P * NKC * CHUNK_BYTES;
+  static constexpr int B_BYTES = NSTAGE * CHUNK_BYTES;
+  static constexpr int SMEM = A_BYTES + B_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// One 32-column slice of the accumulator row owned by this thread.
+template <bool SLOW, bool BITS>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ mvp, int cbase, float wx,
+                                          float wy, const DescGeom& g, float& su, float& sw, uint32_t& rowword,
+                                          uint32_t& colword, int lane) {
+  rowword = 0;
+  colword = 0;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 m4 = __ldg(reinterpret_cast<const float4*>(mvp) + j4);
+    float mvv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j4 * 4 + jj;
+      float s = __uint_as_float(v[j]);
+      float neg = fmaxf(s - g.mneg, 0.f);
+      if (SLOW) {
+        float cx, cy;
+        cell_center(cbase + j, g.Wc, g.cell, cx, cy);
+        if (pair_positive(wx, wy, cx, cy, g.dist)) neg = 0.f;
+      }
+      su += neg;
+      sw = fmaf(neg, mvv[jj], sw);
+      if (BITS) {
+        bool p = neg > 0.f;
+        rowword |= p ? (1u << j) : 0u;
+        uint32_t bal = __ballot_sync(0xffffffffu, p);
+        if (lane == j) colword = bal;
+      }
+    }
+  }
+}
+
+template <int P, bool BITS>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const float2* __restrict__ wpts, const float* __restrict__ mv_pad, DescGeom g,
+                         double* __restrict__ partials, uint32_t* __restrict__ bitsR, uint32_t* __restrict__ bitsC,
+                         float* __restrict__ dbgS) {
+  using Cfg = FwdCfg<P>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::B_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = b_full + NSTAGE;
+  uint64_t* t_full = b_empty + NSTAGE;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+  double* red = reinterpret_cast<double*>(tmem_ptr + 2);  // 8 warps x 2
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int MT = g.Nc_pad / BM, NT = g.Nc_pad / BN;
+  const int b = blockIdx.x / MT, m0 = (blockIdx.x % MT) * BM;
+  const int row_base = b * g.Nc_pad;  // first packed row of this pair
+
+  if (warp == 8 && lane == 0) {
+    tc::prefetch_tmap(&tmA_hi);
+    tc::prefetch_tmap(&tmB_hi);
+    if (P == 2) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      tc::mbar_init(a_full, 1);
+      for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
+      for (int s = 0; s < 2; ++s) { tc::mbar_init(t_full + s, 1); tc::mbar_init(t_empty + s, 8); }
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_ptr, 256);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tc::mbar_expect_tx(a_full, Cfg::A_BYTES);
+      for (int p = 0; p < P; ++p)
+        for (int kc = 0; kc < NKC; ++kc)
+          tc::tma_load_2d(p == 0 ? &tmA_hi : &tmA_lo, a_full, sA + (p * NKC + kc) * CHUNK_BYTES, kc * KC, row_base + m0);
+      int it = 0;
+      for (int nt = 0; nt < NT; ++nt)
+        for (int kc = 0; kc < NKC; ++kc)
+          for (int p = 0; p < P; ++p, ++it) {
+            int s = it % NSTAGE;
+            uint32_t ph = (it / NSTAGE) & 1;
+            tc::mbar_wait(b_empty + s, ph ^ 1);
+            tc::mbar_expect_tx(b_full + s, CHUNK_BYTES);
+            tc::tma_load_2d(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * CHUNK_BYTES, kc * KC, row_base + nt * BN);
+          }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BN, 0, 0);
+      tc::mbar_wait(a_full, 0);
+      const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+      int it = 0;
+      for (int nt = 0; nt < NT; ++nt) {
+        int as = nt & 1;
+        uint32_t aph = (nt >> 1) & 1;
+        tc::mbar_wait(t_empty + as, aph ^ 1);
+        tc::fence_after_sync();
+        uint32_t d_tmem = tmem_base + as * BN;
+        uint32_t first = 1;
+        for (int kc = 0; kc < NKC; ++kc)
+          for (int p = 0; p < P; ++p, ++it) {
+            int s = it % NSTAGE;
+            uint32_t ph = (it / NSTAGE) & 1;
+            tc::mbar_wait(b_full + s, ph);
+            tc::fence_after_sync();
+            // B plane p (0 = hi, 1 = lo) meets A hi; B hi additionally meets A lo (lo*lo is dropped)
+            const int n_a = (P == 2 && p == 0) ? 2 : 1;
+            for (int pa = 0; pa < n_a; ++pa) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                uint64_t da = tc::smem_desc_sw128(sA_u + (pa * NKC + kc) * CHUNK_BYTES + k * 32, 16, 1024);
+                uint64_t db = tc::smem_desc_sw128(sB_u + s * CHUNK_BYTES + k * 32, 16, 1024);
+                tc::mma_ss(d_tmem, da, db, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            tc::mma_commit(b_empty + s);  // slot reusable once these MMAs have read it
+          }
+        tc::mma_commit(t_full + as);  // accumulator tile complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue warps 0..7 ------------------------------
+    const int q = warp & 3, half = warp >> 2;
+    const int row = m0 + q * 32 + lane;  // row inside the padded pair
+    const float2 w = wpts[(size_t)row_base + row];
+    const int NW = g.Nc_pad / 32;
+    double su_d = 0.0, sw_d = 0.0;
+    for (int nt = 0; nt < NT; ++nt) {
+      int as = nt & 1;
+      uint32_t aph = (nt >> 1) & 1;
+      tc::mbar_wait(t_full + as, aph);
+      tc::fence_after_sync();
+      float su = 0.f, sw = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int cbase = nt * BN + half * 64 + ch * 32;
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * 64 + ch * 32, v);
+        // can any row of this warp have a positive pair among these 32 columns? (conservative, y only)
+        int kA = cbase / g.Wc, kB = (cbase + 31) / g.Wc;
+        float ylo = (float)(kA * g.cell + g.cell / 2) - g.dist - 1.f;
+        float yhi = (float)(kB * g.cell + g.cell / 2) + g.dist + 1.f;
+        bool slow = __any_sync(0xffffffffu, w.y >= ylo && w.y <= yhi) && cbase < g.Nc;
+        tc::tmem_ld_wait();
+        const float* mvp = mv_pad + (size_t)row_base + cbase;
+        uint32_t rowword, colword;
+        if (slow) epi_chunk<true, BITS>(v, mvp, cbase, w.x, w.y, g, su, sw, rowword, colword, lane);
+        else epi_chunk<false, BITS>(v, mvp, cbase, w.x, w.y, g, su, sw, rowword, colword, lane);
+        if (BITS) {
+          bitsR[((size_t)b * NW + cbase / 32) * g.Nc_pad + row] = rowword;
+          bitsC[((size_t)b * NW + (m0 + q * 32) / 32) * g.Nc_pad + cbase + lane] = colword;
+        }
+        if (dbgS && row < g.Nc) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cbase + j < g.Nc) dbgS[((size_t)b * g.Nc + row) * g.Nc + cbase + j] = __uint_as_float(v[j]);
+        }
+      }
+      // all TMEM reads of this stage are complete (wait::ld above): hand the stage back
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(t_empty + as);
+      su_d += (double)su;
+      sw_d += (double)sw;
+    }
+    su_d = warp_sum_d(su_d);
+    sw_d = warp_sum_d(sw_d);
+    if (lane == 0) { red[warp * 2] = su_d; red[warp * 2 + 1] = sw_d; }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[2 * i]; c += red[2 * i + 1]; }
+    partials[2 * (size_t)blockIdx.x] = a;
+    partials[2 * (size_t)blockIdx.x + 1] = c;
+  }
+  if (warp == 9) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// indicator GEMM (backward)
+// ------------------------------------------------------------------------------------------------
+constexpr int KT = 64;                       // cells (GEMM K) per stage
+constexpr int BG_BOX_BYTES = KT * 128;       // one [64 cells x 64 channels] box = 8 KB
+constexpr int BG_THREADS = 192;
+
+template <int P> struct BgCfg {
+  static constexpr int NS = (P == 1) ? 4 : 3;
+  static constexpr int STAGE_BYTES = P * 4 * BG_BOX_BYTES;  // 32 KB per plane
+  static constexpr int SMEM = NS * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+template <int P>
+__global__ void __launch_bounds__(BG_THREADS, 1)
+desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale, int Nc, int Nc_pad,
+                         float* __restrict__ out) {
+  using Cfg = BgCfg<P>;
+  constexpr int NS = Cfg::NS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
+  uint64_t* b_full = bars;
+  uint64_t* a_full = b_full + NS;
+  uint64_t* s_free = a_full + NS;
+  uint64_t* d_full = s_free + NS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int MT = Nc_pad / BM, NK = Nc_pad / KT, NW = Nc_pad / 32;
+  const int b = blockIdx.x / MT, m0 = (blockIdx.x % MT) * BM;
+  const int row_base = b * Nc_pad;
+  constexpr uint32_t A_COL0 = 256;  // TMEM columns [0,256) accumulator, then NS x 32 columns of A
+
+  if (warp == 4 && lane == 0) {
+    tc::prefetch_tmap(&tmB_hi);
+    if (P == 2) tc::prefetch_tmap(&tmB_lo);
+  }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int s = 0; s < NS; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(a_full + s, 128); tc::mbar_init(s_free + s, 1); }
+      tc::mbar_init(d_full, 1);
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_ptr, 512);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int kc = 0; kc < NK; ++kc) {
+        int s = kc % NS;
+        uint32_t ph = (kc / NS) & 1;
+        tc::mbar_wait(s_free + s, ph ^ 1);
+        tc::mbar_expect_tx(b_full + s, Cfg::STAGE_BYTES);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        for (int p = 0; p < P; ++p)
+          for (int dc = 0; dc < 4; ++dc)
+            tc::tma_load_2d(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, st + (p * 4 + dc) * BG_BOX_BYTES, dc * 64, row_base + kc * KT);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, 256, 0, 1);  // A K-major (TMEM), B MN-major
+      const uint32_t smem_u = tc::smem_u32(smem);
+      uint32_t first = 1;
+      for (int kc = 0; kc < NK; ++kc) {
+        int s = kc % NS;
+        uint32_t ph = (kc / NS) & 1;
+        tc::mbar_wait(b_full + s, ph);
+        tc::mbar_wait(a_full + s, ph);
+        tc::fence_after_sync();
+        for (int p = 0; p < P; ++p) {
+#pragma unroll
+          for (int k = 0; k < KT / 16; ++k) {
+            // 16 cells = two 8-row groups (SBO 1024 B); 256 channels = four 64-wide blocks (LBO 8 KB)
+            uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * 4 * BG_BOX_BYTES + k * 2048, BG_BOX_BYTES, 1024);
+            uint32_t a_tmem = tmem_base + A_COL0 + s * 32 + k * 8;
+            tc::mma_ts(tmem_base, a_tmem, db, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+        }
+        tc::mma_commit(s_free + s);
+      }
+      tc::mma_commit(d_full);
+    }
+    __syncwarp();
+  } else {
+    // warps 0..3: expand indicator bits -> bf16 A operand in TMEM
+    const int q = warp;
+    const int row = m0 + q * 32 + lane;
+    for (int kc = 0; kc < NK; ++kc) {
+      int s = kc % NS;
+      uint32_t ph = (kc / NS) & 1;
+      uint32_t w0 = __ldg(bits + ((size_t)b * NW + kc * 2) * Nc_pad + row);
+      uint32_t w1 = __ldg(bits + ((size_t)b * NW + kc * 2 + 1) * Nc_pad + row);
+      tc::mbar_wait(s_free + s, ph ^ 1);
+      tc::fence_after_sync();
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        r[i] = ((w0 >> (2 * i)) & 1u) * 0x3F80u + ((w0 >> (2 * i + 1)) & 1u) * 0x3F800000u;
+        r[16 + i] = ((w1 >> (2 * i)) & 1u) * 0x3F80u + ((w1 >> (2 * i + 1)) & 1u) * 0x3F800000u;
+      }
+      tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(a_full + s);
+    }
+    // epilogue: accumulator row of this thread -> out[b, d, row] (coalesced over rows)
+    tc::mbar_wait(d_full, 0);
+    tc::fence_after_sync();
+    float rs = 1.f;
+    if (rowscale && row < Nc) rs = rowscale[(size_t)row_base + row];
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, v);
+      tc::tmem_ld_wait();
+      if (row < Nc) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[((size_t)b * KD + ch * 32 + j) * Nc + row] = __uint_as_float(v[j]) * rs;
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// packed plane [rows, 256] bf16 -> 2-D map with a [box_rows x 64] SWIZZLE_128B box
+int make_plane_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { ssp_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return SSP_EUNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)KD, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)KD * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KC, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ssp_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SSP_EARG; }
+  return SSP_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { ssp_set_error("cudaFuncSetAttribute(%d B smem) failed: %s", bytes, cudaGetErrorString(e)); return (int)e; }
+  return SSP_OK;
+}
+
+}  // namespace
+
+extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / BM); }
+
+// Ahi/Alo: packed planes of `descriptors`, Bhi/Blo: packed planes of `descriptors_warped`
+// ([B, Nc_pad, 256] bf16).  Alo == Blo == NULL selects single-pass bf16; otherwise bf16x3.
+extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
+                                     const float* wpts, const float* mv_pad, int B, int Hc, int Wc, int cell,
+                                     float dist, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
+                                     float* dbgS, void* stream) {
+  SSP_REQUIRE(Ahi && Bhi && wpts && mv_pad && partials, "ssp_desc_dense_fwd_tc: null pointer");
+  SSP_REQUIRE((Alo == nullptr) == (Blo == nullptr), "ssp_desc_dense_fwd_tc: lo planes must both be given or both null");
+  SSP_REQUIRE((bitsR == nullptr) == (bitsC == nullptr), "ssp_desc_dense_fwd_tc: bitsR/bitsC must both be given or both null");
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0 && cell > 0, "ssp_desc_dense_fwd_tc: bad sizes");
+  SSP_REQUIRE(mneg > 0.f, "ssp_desc_dense_fwd_tc: margin_neg must be > 0 (zero padding relies on it)");
+  SSP_REQUIRE((((uintptr_t)Ahi | (uintptr_t)Bhi | (uintptr_t)Alo | (uintptr_t)Blo | (uintptr_t)mv_pad) & 15) == 0,
+              "ssp_desc_dense_fwd_tc: operands must be 16-byte aligned");
+  DescGeom g;
+  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = KD; g.cell = cell;
+  g.dist = dist; g.lamda = 0.f; g.mpos = 0.f; g.mneg = mneg;
+  uint64_t rows = (uint64_t)B * g.Nc_pad;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = make_plane_map(&mAh, Ahi, rows, BM))) return rc;
+  if ((rc = make_plane_map(&mBh, Bhi, rows, BN))) return rc;
+  if ((rc = make_plane_map(&mAl, Alo ? Alo : Ahi, rows, BM))) return rc;
+  if ((rc = make_plane_map(&mBl, Blo ? Blo : Bhi, rows, BN))) return rc;
+  int grid = ssp_desc_dense_tc_nblocks(B, g.Nc);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float2* wp = reinterpret_cast<const float2*>(wpts);
+#define LAUNCH_FWD(PP, BB)                                                                                   \
+  do {                                                                                                       \
+    if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB>, FwdCfg<PP>::SMEM))) return rc;                      \
+    desc_dense_fwd_tc_kernel<PP, BB><<<grid, FWD_THREADS, FwdCfg<PP>::SMEM, st>>>(mAh, mAl, mBh, mBl, wp, mv_pad, g, \
+                                                                                   partials, bitsR, bitsC, dbgS);  \
+  } while (0)
+  if (Alo) { if (bitsR) LAUNCH_FWD(2, true); else LAUNCH_FWD(2, false); }
+  else     { if (bitsR) LAUNCH_FWD(1, true); else LAUNCH_FWD(1, false); }
+#undef LAUNCH_FWD
+  SSP_CUDA_CHECK_LAUNCH("desc_dense_fwd_tc_kernel");
+  return SSP_OK;
+}
+
+// out[b, d, r] = rowscale[b, r] * sum_k bit(r, k) * (Bhi + Blo)[b, k, d]      (out is [B, 256, Nc] fp32)
+extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
+                                     int B, int Nc, float* out, void* stream) {
+  SSP_REQUIRE(bits && Bhi && out, "ssp_desc_bits_gemm_tc: null pointer");
+  SSP_REQUIRE(B > 0 && Nc > 0, "ssp_desc_bits_gemm_tc: bad sizes");
+  SSP_REQUIRE((((uintptr_t)Bhi | (uintptr_t)Blo) & 15) == 0, "ssp_desc_bits_gemm_tc: operands must be 16-byte aligned");
+  int Nc_pad = desc_nc_pad(Nc);
+  uint64_t rows = (uint64_t)B * Nc_pad;
+  CUtensorMap mh, ml;
+  int rc;
+  if ((rc = make_plane_map(&mh, Bhi, rows, KT))) return rc;
+  if ((rc = make_plane_map(&ml, Blo ? Blo : Bhi, rows, KT))) return rc;
+  int grid = B * (Nc_pad / BM);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Blo) {
+    if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
+    desc_bits_gemm_tc_kernel<2><<<grid, BG_THREADS, BgCfg<2>::SMEM, st>>>(mh, ml, bits, rowscale, Nc, Nc_pad, out);
+  } else {
+    if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
+    desc_bits_gemm_tc_kernel<1><<<grid, BG_THREADS, BgCfg<1>::SMEM, st>>>(mh, ml, bits, rowscale, Nc, Nc_pad, out);
+  }
+  SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
+  return SSP_OK;
+}

@@ -1,0 +1,317 @@
+// Detector label / loss path and heatmap flattening.
+// Reference semantics (Gabriel-SGama/Semantic-SuperPoint):
+//   labels2Dto3D            utils/utils.py:408-440   (+ SpaceToDepth utils/d2s.py:27-44)
+//   getMasks                Train_model_frontend_all.py:373-386
+//   detector_loss (softmax) Train_model_heatmap_all.py:155-179  -> BCE over softmax probabilities
+//   flattenDetection        utils/utils.py:515-560   (+ DepthToSpace utils/d2s.py:8-25)
+// Layout: one thread per 8x8 cell; the 65 channel values of a cell are Nc floats apart (NCHW), so a
+// warp reads 32 consecutive cells of one channel = one 128 B line; the 8x8 pixel block of a cell is
+// 8 rows of 32 B, read/written as 2 x float4 per row.  All kernels are HBM-bound.
+#include "common.cuh"
+
+#define CELL 8
+#define NCH 65
+
+// ---- deterministic two-level reduction: per-block partials -> last block sums in index order ----
+template <int NV>
+__device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double* __restrict__ partials,
+                                                     unsigned int* __restrict__ counter, double (&total)[NV]) {
+  __shared__ double sh[32];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double r = block_sum_d(v[i], sh);
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * NV + i] = r;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double a = 0.0;
+    for (unsigned int j = threadIdx.x; j < gridDim.x; j += blockDim.x) a += partials[(size_t)j * NV + i];
+    total[i] = block_sum_d(a, sh);
+  }
+  return threadIdx.x == 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// labels2Dto3D: pixel-unshuffle(8) (+ dustbin + normalisation)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_cell(const float* __restrict__ img, int W, int y0, int x0, float (&v)[64]) {
+#pragma unroll
+  for (int dy = 0; dy < CELL; ++dy) {
+    const float4* r = reinterpret_cast<const float4*>(img + (size_t)(y0 + dy) * W + x0);
+    float4 a = __ldg(r), b = __ldg(r + 1);
+    v[dy * 8 + 0] = a.x; v[dy * 8 + 1] = a.y; v[dy * 8 + 2] = a.z; v[dy * 8 + 3] = a.w;
+    v[dy * 8 + 4] = b.x; v[dy * 8 + 5] = b.y; v[dy * 8 + 6] = b.z; v[dy * 8 + 7] = b.w;
+  }
+}
+
+// dustbin + normaliser exactly as the reference: d = 1 - sum; d < 1 -> 0; divide all 65 by their sum
+__device__ __forceinline__ void dustbin_norm(float (&v)[64], float& dust) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; ++c) s += v[c];
+  dust = 1.f - s;
+  if (dust < 1.f) dust = 0.f;
+  float dn = s + dust;
+#pragma unroll
+  for (int c = 0; c < 64; ++c) v[c] = v[c] / dn;
+  dust = dust / dn;
+}
+
+__global__ void __launch_bounds__(128)
+labels2d_to_3d_kernel(const float* __restrict__ labels, int B, int H, int W, int add_dustbin,
+                      float* __restrict__ out) {
+  int Hc = H / CELL, Wc = W / CELL, Nc = Hc * Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= B * Nc) return;
+  int b = cell / Nc, ij = cell % Nc;
+  int k = ij / Wc, l = ij % Wc;
+  float v[64];
+  load_cell(labels + (size_t)b * H * W, W, k * CELL, l * CELL, v);
+  int nch = add_dustbin ? 65 : 64;
+  float dust = 0.f;
+  if (add_dustbin) dustbin_norm(v, dust);
+  float* o = out + (size_t)b * nch * Nc + ij;
+#pragma unroll
+  for (int c = 0; c < 64; ++c) o[(size_t)c * Nc] = v[c];
+  if (add_dustbin) o[(size_t)64 * Nc] = dust;
+}
+
+extern "C" int ssp_labels2d_to_3d(const float* labels, int B, int H, int W, int add_dustbin, float* out,
+                                  void* stream) {
+  SSP_REQUIRE(labels && out, "ssp_labels2d_to_3d: null pointer");
+  SSP_REQUIRE(B > 0 && H >= CELL && W >= CELL && H % CELL == 0 && W % CELL == 0,
+              "ssp_labels2d_to_3d: H=%d W=%d must be positive multiples of 8 (B=%d)", H, W, B);
+  int cells = B * (H / CELL) * (W / CELL);
+  labels2d_to_3d_kernel<<<ssp_ceil_div(cells, 128), 128, 0, (cudaStream_t)stream>>>(labels, B, H, W, add_dustbin, out);
+  SSP_CUDA_CHECK_LAUNCH("labels2d_to_3d_kernel");
+  return SSP_OK;
+}
+
+// getMasks: product of the 64 sub-pixels of every cell
+__global__ void __launch_bounds__(128)
+cell_mask_kernel(const float* __restrict__ mask2d, int B, int H, int W, float* __restrict__ out) {
+  int Hc = H / CELL, Wc = W / CELL, Nc = Hc * Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= B * Nc) return;
+  int b = cell / Nc, ij = cell % Nc;
+  float v[64];
+  load_cell(mask2d + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
+  float p = v[0];
+#pragma unroll
+  for (int c = 1; c < 64; ++c) p *= v[c];
+  out[cell] = p;
+}
+
+extern "C" int ssp_cell_mask(const float* mask2d, int B, int H, int W, float* out, void* stream) {
+  SSP_REQUIRE(mask2d && out, "ssp_cell_mask: null pointer");
+  SSP_REQUIRE(B > 0 && H >= CELL && W >= CELL && H % CELL == 0 && W % CELL == 0,
+              "ssp_cell_mask: H=%d W=%d must be positive multiples of 8 (B=%d)", H, W, B);
+  int cells = B * (H / CELL) * (W / CELL);
+  cell_mask_kernel<<<ssp_ceil_div(cells, 128), 128, 0, (cudaStream_t)stream>>>(mask2d, B, H, W, out);
+  SSP_CUDA_CHECK_LAUNCH("cell_mask_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// detector loss: sum_cells mask * sum_c BCE(softmax(semi)_c, target_c) / (sum mask + 1e-5)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax65(const float* __restrict__ semi_cell, size_t Nc, float (&p)[NCH]) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    p[c] = __ldg(semi_cell + (size_t)c * Nc);
+    m = fmaxf(m, p[c]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    p[c] = expf(p[c] - m);
+    s += p[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) p[c] = p[c] / s;
+}
+
+__device__ __forceinline__ float bce_term(float p, float t) {
+  // nn.BCELoss: log terms clamped at -100
+  float lp = fmaxf(logf(p), -100.f);
+  float lq = fmaxf(logf(1.f - p), -100.f);
+  return -(t * lp + (1.f - t) * lq);
+}
+
+// FUSED2D = 0: target [B,65,Hc,Wc] and mask [B,Hc,Wc] are given (reference call signature).
+// FUSED2D = 1: target/mask are built on the fly from labels_2D / mask_2D [B,1,H,W].
+template <int FUSED2D>
+__global__ void __launch_bounds__(128)
+detector_loss_fwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
+                         const float* __restrict__ mask, int B, int Hc, int Wc, double* __restrict__ partials,
+                         unsigned int* __restrict__ counter, float* __restrict__ out) {
+  int Nc = Hc * Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[2] = {0.0, 0.0};
+  if (cell < B * Nc) {
+    int b = cell / Nc, ij = cell % Nc;
+    float p[NCH];
+    softmax65(semi + (size_t)b * NCH * Nc + ij, Nc, p);
+    float mk, bce = 0.f;
+    if (FUSED2D) {
+      int H = Hc * CELL, W = Wc * CELL;
+      float v[64], dust;
+      load_cell(mask + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
+      mk = v[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) mk *= v[c];
+      load_cell(target + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
+      dustbin_norm(v, dust);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) bce += bce_term(p[c], v[c]);
+      bce += bce_term(p[64], dust);
+    } else {
+      mk = __ldg(mask + cell);
+      const float* t = target + (size_t)b * NCH * Nc + ij;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) bce += bce_term(p[c], __ldg(t + (size_t)c * Nc));
+    }
+    acc[0] = (double)(bce * mk);
+    acc[1] = (double)mk;
+  }
+  double tot[2];
+  if (block_reduce_publish<2>(acc, partials, counter, tot)) {
+    float num = (float)tot[0];
+    float den = (float)tot[1] + 1e-5f;
+    out[0] = num / den;  // loss
+    out[1] = num;
+    out[2] = den;
+    *counter = 0;
+  }
+}
+
+// d semi = gout * mask/den * softmax_bwd( (p - t) / max(p (1-p), 1e-12) )
+template <int FUSED2D>
+__global__ void __launch_bounds__(128)
+detector_loss_bwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
+                         const float* __restrict__ mask, int B, int Hc, int Wc, const float* __restrict__ fwd_out,
+                         const float* __restrict__ gout, float* __restrict__ dsemi) {
+  int Nc = Hc * Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= B * Nc) return;
+  int b = cell / Nc, ij = cell % Nc;
+  float p[NCH], t[NCH];
+  softmax65(semi + (size_t)b * NCH * Nc + ij, Nc, p);
+  float mk;
+  if (FUSED2D) {
+    int H = Hc * CELL, W = Wc * CELL;
+    float v[64], dust;
+    load_cell(mask + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
+    mk = v[0];
+#pragma unroll
+    for (int c = 1; c < 64; ++c) mk *= v[c];
+    load_cell(target + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
+    dustbin_norm(v, dust);
+#pragma unroll
+    for (int c = 0; c < 64; ++c) t[c] = v[c];
+    t[64] = dust;
+  } else {
+    mk = __ldg(mask + cell);
+    const float* tp = target + (size_t)b * NCH * Nc + ij;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) t[c] = __ldg(tp + (size_t)c * Nc);
+  }
+  float scale = __ldg(gout) * mk / __ldg(fwd_out + 2);
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float dp = scale * (p[c] - t[c]) / fmaxf((1.f - p[c]) * p[c], 1e-12f);
+    t[c] = dp;
+    dot += p[c] * dp;
+  }
+  float* o = dsemi + (size_t)b * NCH * Nc + ij;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) o[(size_t)c * Nc] = p[c] * (t[c] - dot);
+}
+
+extern "C" size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc) {
+  size_t nblk = (size_t)ssp_ceil_div(B * Hc * Wc, 128);
+  return 16 + nblk * 2 * sizeof(double);
+}
+
+extern "C" int ssp_detector_loss_fwd(const float* semi, const float* target, const float* mask, int B, int Hc,
+                                     int Wc, int fused2d, float* out3, void* ws, size_t ws_bytes, void* stream) {
+  SSP_REQUIRE(semi && target && mask && out3 && ws, "ssp_detector_loss_fwd: null pointer");
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_fwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
+  SSP_REQUIRE(ws_bytes >= ssp_detector_loss_ws_bytes(B, Hc, Wc), "ssp_detector_loss_fwd: workspace too small");
+  SSP_REQUIRE(((uintptr_t)ws & 15) == 0, "ssp_detector_loss_fwd: workspace must be 16-byte aligned");
+  if (fused2d)
+    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
+                "ssp_detector_loss_fwd: 2-D label/mask pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* counter = (unsigned int*)ws;
+  double* partials = (double*)((char*)ws + 16);
+  SSP_CUDA_CALL(cudaMemsetAsync(counter, 0, 16, st));
+  int nblk = ssp_ceil_div(B * Hc * Wc, 128);
+  if (fused2d)
+    detector_loss_fwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
+  else
+    detector_loss_fwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_fwd_kernel");
+  return SSP_OK;
+}
+
+extern "C" int ssp_detector_loss_bwd(const float* semi, const float* target, const float* mask, int B, int Hc,
+                                     int Wc, int fused2d, const float* fwd_out3, const float* gout, float* dsemi,
+                                     void* stream) {
+  SSP_REQUIRE(semi && target && mask && fwd_out3 && gout && dsemi, "ssp_detector_loss_bwd: null pointer");
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_bwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
+  if (fused2d)
+    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
+                "ssp_detector_loss_bwd: 2-D label/mask pointers must be 16-byte aligned");
+  int nblk = ssp_ceil_div(B * Hc * Wc, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fused2d)
+    detector_loss_bwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
+  else
+    detector_loss_bwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_bwd_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// flattenDetection: softmax(65) -> drop dustbin -> pixel-shuffle(8)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+flatten_detection_kernel(const float* __restrict__ semi, int N, int Hc, int Wc, float* __restrict__ heat) {
+  int Nc = Hc * Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= N * Nc) return;
+  int b = cell / Nc, ij = cell % Nc;
+  int k = ij / Wc, l = ij % Wc;
+  float p[NCH];
+  softmax65(semi + (size_t)b * NCH * Nc + ij, Nc, p);
+  int W = Wc * CELL;
+  float* o = heat + (size_t)b * Nc * 64 + (size_t)(k * CELL) * W + l * CELL;
+#pragma unroll
+  for (int dy = 0; dy < CELL; ++dy) {
+    float4* r = reinterpret_cast<float4*>(o + (size_t)dy * W);
+    r[0] = make_float4(p[dy * 8 + 0], p[dy * 8 + 1], p[dy * 8 + 2], p[dy * 8 + 3]);
+    r[1] = make_float4(p[dy * 8 + 4], p[dy * 8 + 5], p[dy * 8 + 6], p[dy * 8 + 7]);
+  }
+}
+
+extern "C" int ssp_flatten_detection(const float* semi, int N, int Hc, int Wc, float* heat, void* stream) {
+  SSP_REQUIRE(semi && heat, "ssp_flatten_detection: null pointer");
+  SSP_REQUIRE(N > 0 && Hc > 0 && Wc > 0, "ssp_flatten_detection: bad sizes N=%d Hc=%d Wc=%d", N, Hc, Wc);
+  SSP_REQUIRE(((uintptr_t)heat & 15) == 0, "ssp_flatten_detection: output must be 16-byte aligned");
+  int cells = N * Hc * Wc;
+  flatten_detection_kernel<<<ssp_ceil_div(cells, 128), 128, 0, (cudaStream_t)stream>>>(semi, N, Hc, Wc, heat);
+  SSP_CUDA_CHECK_LAUNCH("flatten_detection_kernel");
+  return SSP_OK;
+}

@@ -1,0 +1,304 @@
+// Keypoint extraction: getPtsFromHeatmap / nms_fast and box_nms on the GPU.
+// Reference: utils/utils.py:581-609 (getPtsFromHeatmap), :653-712 (nms_fast), :612-650 (box_nms)
+//            twins in models/model_wrap.py:129-192,266-293   -- Gabriel-SGama/Semantic-SuperPoint
+//
+// The reference walks the candidates in descending-confidence order and keeps a point iff no
+// already-kept point lies in its suppression window.  For a strict total order this greedy result is
+// unique and equals the fixed point of parallel rounds:
+//   undecided p:  a kept point in window(p)                     -> suppressed
+//                 no undecided point of higher priority in window(p) -> kept
+// State transitions are monotone (undecided -> kept | suppressed) and each pixel has one writer, so
+// rounds may read stale neighbour state without changing the result (a stale "undecided" only delays
+// a decision).  Priority = (confidence desc, linear index asc) = numpy stable argsort(-conf).
+// The window is a (2R+1)^2 boolean stencil in shared memory: all ones for nms_fast (Chebyshev
+// radius R), the IoU > thr footprint for box_nms.  Tiles are 32x32 with an R halo; each launch runs
+// NMS_LOCAL_ITERS rounds on its tile snapshot before publishing.
+#include "common.cuh"
+
+#define NT 32
+#define NMS_LOCAL_ITERS 4
+#define ST_NONE 0
+#define ST_UNDECIDED 1
+#define ST_KEPT 2
+
+__global__ void nms_init_kernel(const float* __restrict__ heat, size_t n, float thr, int strict,
+                                uint8_t* __restrict__ state) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = heat[i];
+  bool c = strict ? (v > thr) : (v >= thr);
+  state[i] = c ? ST_UNDECIDED : ST_NONE;
+}
+
+__global__ void __launch_bounds__(256)
+nms_round_kernel(const float* __restrict__ heat, uint8_t* __restrict__ state, int H, int W, int R,
+                 const uint8_t* __restrict__ stencil, unsigned int* __restrict__ remaining) {
+  extern __shared__ unsigned char smem_raw[];
+  int TW = NT + 2 * R;
+  float* sv = reinterpret_cast<float*>(smem_raw);                 // TW*TW values
+  uint8_t* ss = reinterpret_cast<uint8_t*>(sv + TW * TW);         // TW*TW states
+  uint8_t* sk = ss + TW * TW;                                     // (2R+1)^2 stencil
+  __shared__ int any_undecided;
+  int tid = threadIdx.x;
+  size_t img = (size_t)blockIdx.z * H * W;
+  heat += img;
+  state += img;
+  int ty0 = blockIdx.y * NT, tx0 = blockIdx.x * NT;
+  if (tid == 0) any_undecided = 0;
+  __syncthreads();
+  // interior first: skip the tile when nothing is undecided
+  int found = 0;
+  for (int i = tid; i < NT * NT; i += 256) {
+    int y = ty0 + i / NT, x = tx0 + i % NT;
+    if (y < H && x < W && state[(size_t)y * W + x] == ST_UNDECIDED) found = 1;
+  }
+  if (found) any_undecided = 1;
+  __syncthreads();
+  if (!any_undecided) return;
+  int S = 2 * R + 1;
+  for (int i = tid; i < S * S; i += 256) sk[i] = stencil[i];
+  for (int i = tid; i < TW * TW; i += 256) {
+    int y = ty0 - R + i / TW, x = tx0 - R + i % TW;
+    uint8_t s = ST_NONE;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      s = state[(size_t)y * W + x];
+      if (s != ST_NONE) v = heat[(size_t)y * W + x];
+    }
+    ss[i] = s;
+    sv[i] = v;
+  }
+  __syncthreads();
+  int left = 0;
+  for (int it = 0; it < NMS_LOCAL_ITERS; ++it) {
+    uint8_t ns[4];
+    left = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int i = tid + q * 256;
+      int ly = i / NT, lx = i % NT;
+      int c = (ly + R) * TW + (lx + R);
+      uint8_t s = ss[c];
+      ns[q] = s;
+      if (s != ST_UNDECIDED) continue;
+      float v = sv[c];
+      bool kept_near = false, higher_near = false;
+      for (int dy = -R; dy <= R; ++dy) {
+        for (int dx = -R; dx <= R; ++dx) {
+          if (!sk[(dy + R) * S + (dx + R)] || (dx == 0 && dy == 0)) continue;
+          int o = c + dy * TW + dx;
+          uint8_t so = ss[o];
+          if (so == ST_KEPT) kept_near = true;
+          else if (so == ST_UNDECIDED) {
+            float vo = sv[o];
+            // priority: larger value first, then smaller linear index (dy<0 or dy==0&&dx<0)
+            if (vo > v || (vo == v && (dy < 0 || (dy == 0 && dx < 0)))) higher_near = true;
+          }
+        }
+      }
+      if (kept_near) ns[q] = ST_NONE;
+      else if (!higher_near) ns[q] = ST_KEPT;
+      else left++;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int i = tid + q * 256;
+      ss[(i / NT + R) * TW + (i % NT + R)] = ns[q];
+    }
+    __syncthreads();
+  }
+  // publish the interior
+  for (int i = tid; i < NT * NT; i += 256) {
+    int y = ty0 + i / NT, x = tx0 + i % NT;
+    if (y < H && x < W) state[(size_t)y * W + x] = ss[(i / NT + R) * TW + (i % NT + R)];
+  }
+  if (left) atomicAdd(remaining, (unsigned int)left);
+}
+
+// kept points outside the removed border -> unordered list (value, linear index)
+__global__ void nms_compact_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ state, int H, int W,
+                                   int border, int capacity, float* __restrict__ lval, int* __restrict__ lidx,
+                                   unsigned int* __restrict__ count) {
+  int img = blockIdx.y;
+  size_t off = (size_t)img * H * W;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (i < H * W) {
+    int y = i / W, x = i % W;
+    keep = state[off + i] == ST_KEPT && x >= border && x < W - border && y >= border && y < H - border;
+  }
+  unsigned int bal = __ballot_sync(0xffffffffu, keep);
+  int lane = threadIdx.x & 31;
+  unsigned int base = 0;
+  if (lane == 0 && bal) base = atomicAdd(count + img, (unsigned int)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (keep) {
+    unsigned int slot = base + __popc(bal & ((1u << lane) - 1u));
+    if (slot < (unsigned int)capacity) {
+      lval[(size_t)img * capacity + slot] = heat[off + i];
+      lidx[(size_t)img * capacity + slot] = i;
+    }
+  }
+}
+
+// rank-by-counting sort: output order = (confidence desc, linear index desc), i.e. the reference's
+// `argsort(conf)[::-1]` with a stable sort.  pts is [3, capacity] doubles per image: x, y, conf.
+__global__ void __launch_bounds__(256)
+nms_rank_emit_kernel(const float* __restrict__ lval, const int* __restrict__ lidx,
+                     const unsigned int* __restrict__ count, int W, int capacity, double* __restrict__ pts) {
+  __shared__ float tv[256];
+  __shared__ int ti[256];
+  int img = blockIdx.y;
+  int K = min((int)count[img], capacity);
+  lval += (size_t)img * capacity;
+  lidx += (size_t)img * capacity;
+  pts += (size_t)img * 3 * capacity;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= K) return;
+  float v = 0.f;
+  int id = 0;
+  if (i < K) { v = lval[i]; id = lidx[i]; }
+  int rank = 0;
+  for (int base = 0; base < K; base += 256) {
+    int j = base + threadIdx.x;
+    __syncthreads();
+    if (j < K) { tv[threadIdx.x] = lval[j]; ti[threadIdx.x] = lidx[j]; }
+    __syncthreads();
+    int lim = min(256, K - base);
+    for (int q = 0; q < lim; ++q) {
+      float vo = tv[q];
+      int io = ti[q];
+      rank += (vo > v || (vo == v && io > id)) ? 1 : 0;
+    }
+  }
+  if (i < K) {
+    pts[rank] = (double)(id % W);
+    pts[capacity + rank] = (double)(id / W);
+    pts[2 * (size_t)capacity + rank] = (double)v;
+  }
+}
+
+__global__ void nms_dense_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ state, size_t n,
+                                 float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = state[i] == ST_KEPT ? heat[i] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t ssp_nms_ws_bytes(int I, int H, int W, int capacity) {
+  size_t n = (size_t)I * H * W;
+  size_t state = (n + 255) / 256 * 256;
+  size_t ctr = 256 + (((size_t)I * 4 + 255) / 256) * 256;   // [remaining | pad] + per-image counts
+  size_t lists = (size_t)I * capacity * 8;
+  return state + ctr + lists + 256;
+}
+
+struct NmsWs {
+  uint8_t* state;
+  unsigned int* remaining;
+  unsigned int* count;
+  float* lval;
+  int* lidx;
+};
+
+static NmsWs nms_carve(void* ws, int I, int H, int W, int capacity) {
+  NmsWs w;
+  size_t n = (size_t)I * H * W;
+  char* p = (char*)ws;
+  w.state = (uint8_t*)p;
+  p += (n + 255) / 256 * 256;
+  w.remaining = (unsigned int*)p;
+  p += 256;
+  w.count = (unsigned int*)p;
+  p += (((size_t)I * 4 + 255) / 256) * 256;
+  w.lval = (float*)p;
+  p += (size_t)I * capacity * 4;
+  w.lidx = (int*)p;
+  return w;
+}
+
+// Runs the rounds to the fixed point.  Synchronises the stream every `batch` rounds to read the
+// number of still-undecided pixels (the reference API returns host data, so a sync is inherent).
+static int nms_run_rounds(const float* heat, const NmsWs& w, int I, int H, int W, int R, const uint8_t* stencil,
+                          cudaStream_t st, int* rounds_out) {
+  dim3 grid(ssp_ceil_div(W, NT), ssp_ceil_div(H, NT), I);
+  int TW = NT + 2 * R;
+  size_t smem = (size_t)TW * TW * 5 + (size_t)(2 * R + 1) * (2 * R + 1);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ssp_set_error("nms: window radius %d needs %zu B shared memory: %s", R, smem, cudaGetErrorString(e)); return (int)e; }
+  }
+  int rounds = 0;
+  unsigned int remaining = 1;
+  const int batch = 2;
+  while (remaining) {
+    for (int k = 0; k < batch; ++k) {
+      if (k == batch - 1) SSP_CUDA_CALL(cudaMemsetAsync(w.remaining, 0, 4, st));
+      nms_round_kernel<<<grid, 256, smem, st>>>(heat, w.state, H, W, R, stencil, w.remaining);
+      SSP_CUDA_CHECK_LAUNCH("nms_round_kernel");
+      ++rounds;
+    }
+    SSP_CUDA_CALL(cudaMemcpyAsync(&remaining, w.remaining, 4, cudaMemcpyDeviceToHost, st));
+    SSP_CUDA_CALL(cudaStreamSynchronize(st));
+    if (rounds > 4 * (H + W) * I + 64) { ssp_set_error("nms: rounds did not converge"); return SSP_EUNSUPPORTED; }
+  }
+  if (rounds_out) *rounds_out = rounds;
+  return SSP_OK;
+}
+
+// getPtsFromHeatmap for I images of HxW.  pts: [I,3,capacity] float64 (x,y,conf rows, conf-descending),
+// counts_host: [I] ints on the HOST (number of points per image).  stencil: device (2R+1)^2 bytes.
+extern "C" int ssp_nms_fast(const float* heat, int I, int H, int W, float conf_thresh, int R,
+                            const uint8_t* stencil, int border, int capacity, double* pts, int* counts_host,
+                            void* ws, size_t ws_bytes, void* stream) {
+  SSP_REQUIRE(heat && stencil && pts && counts_host && ws, "ssp_nms_fast: null pointer");
+  SSP_REQUIRE(I > 0 && I <= 65535 && H > 0 && W > 0 && R >= 0 && R <= 48 && border >= 0 && capacity > 0,
+              "ssp_nms_fast: bad sizes I=%d H=%d W=%d R=%d border=%d capacity=%d", I, H, W, R, border, capacity);
+  SSP_REQUIRE(ws_bytes >= ssp_nms_ws_bytes(I, H, W, capacity), "ssp_nms_fast: workspace too small");
+  SSP_REQUIRE(((uintptr_t)ws & 255) == 0, "ssp_nms_fast: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  NmsWs w = nms_carve(ws, I, H, W, capacity);
+  size_t n = (size_t)I * H * W;
+  nms_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(heat, n, conf_thresh, 0, w.state);
+  SSP_CUDA_CHECK_LAUNCH("nms_init_kernel");
+  int rc = nms_run_rounds(heat, w, I, H, W, R, stencil, st, nullptr);
+  if (rc) return rc;
+  SSP_CUDA_CALL(cudaMemsetAsync(w.count, 0, (size_t)I * 4, st));
+  dim3 cg(ssp_ceil_div(H * W, 256), I);
+  nms_compact_kernel<<<cg, 256, 0, st>>>(heat, w.state, H, W, border, capacity, w.lval, w.lidx, w.count);
+  SSP_CUDA_CHECK_LAUNCH("nms_compact_kernel");
+  dim3 rg(ssp_ceil_div(capacity, 256), I);
+  nms_rank_emit_kernel<<<rg, 256, 0, st>>>(w.lval, w.lidx, w.count, W, capacity, pts);
+  SSP_CUDA_CHECK_LAUNCH("nms_rank_emit_kernel");
+  SSP_CUDA_CALL(cudaMemcpyAsync(counts_host, w.count, (size_t)I * 4, cudaMemcpyDeviceToHost, st));
+  SSP_CUDA_CALL(cudaStreamSynchronize(st));
+  for (int i = 0; i < I; ++i) {
+    if (counts_host[i] > capacity) {
+      ssp_set_error("ssp_nms_fast: image %d has %d keypoints, capacity %d", i, counts_host[i], capacity);
+      return SSP_EARG;
+    }
+  }
+  return SSP_OK;
+}
+
+// box_nms: candidates prob > min_prob (strict), IoU-footprint stencil, dense output map.
+extern "C" int ssp_box_nms(const float* prob, int I, int H, int W, float min_prob, int R, const uint8_t* stencil,
+                           float* out, void* ws, size_t ws_bytes, void* stream) {
+  SSP_REQUIRE(prob && stencil && out && ws, "ssp_box_nms: null pointer");
+  SSP_REQUIRE(I > 0 && I <= 65535 && H > 0 && W > 0 && R >= 0 && R <= 48, "ssp_box_nms: bad sizes I=%d H=%d W=%d R=%d", I, H, W, R);
+  SSP_REQUIRE(ws_bytes >= ssp_nms_ws_bytes(I, H, W, 1), "ssp_box_nms: workspace too small");
+  SSP_REQUIRE(((uintptr_t)ws & 255) == 0, "ssp_box_nms: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  NmsWs w = nms_carve(ws, I, H, W, 1);
+  size_t n = (size_t)I * H * W;
+  nms_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prob, n, min_prob, 1, w.state);
+  SSP_CUDA_CHECK_LAUNCH("nms_init_kernel");
+  int rc = nms_run_rounds(prob, w, I, H, W, R, stencil, st, nullptr);
+  if (rc) return rc;
+  nms_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prob, w.state, n, out);
+  SSP_CUDA_CHECK_LAUNCH("nms_dense_kernel");
+  return SSP_OK;
+}

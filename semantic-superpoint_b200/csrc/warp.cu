@@ -1,0 +1,231 @@
+// Batched homography warping: warp_points, inv_warp_image_batch, compute_valid_mask, filter masks.
+// Reference semantics: utils/utils.py:303-405, 715-742 and evaluations/detector_evaluation.py:139-191
+// (Gabriel-SGama/Semantic-SuperPoint).  All kernels are HBM-bound streaming kernels; the source
+// image of a warp is gathered through L1/L2 (one image is 0.3-1.2 MB, far below the 126 MB L2).
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------------------------
+// a1: warp_points   out[b,p,:] = (H_b [x,y,1]^T)[:2] / (H_b [x,y,1]^T)[2]
+// ----------------------------------------------------------------------------------------------
+__global__ void warp_points_kernel(const float* __restrict__ pts, int P, const float* __restrict__ Hm,
+                                   float* __restrict__ out) {
+  int b = blockIdx.y;
+  __shared__ float h[9];
+  if (threadIdx.x < 9) h[threadIdx.x] = Hm[b * 9 + threadIdx.x];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    float2 xy = reinterpret_cast<const float2*>(pts)[p];
+    float ox, oy;
+    homography_apply(h, xy.x, xy.y, ox, oy);
+    reinterpret_cast<float2*>(out)[(size_t)b * P + p] = make_float2(ox, oy);
+  }
+}
+
+extern "C" int ssp_warp_points(const float* pts, int P, const float* Hm, int B, float* out, void* stream) {
+  SSP_REQUIRE(pts && Hm && out, "ssp_warp_points: null pointer");
+  SSP_REQUIRE(P >= 0 && B > 0, "ssp_warp_points: bad sizes P=%d B=%d", P, B);
+  if (P == 0) return SSP_OK;
+  dim3 grid(min(ssp_ceil_div(P, 256), 148 * 8), B);
+  warp_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pts, P, Hm, out);
+  SSP_CUDA_CHECK_LAUNCH("warp_points_kernel");
+  return SSP_OK;
+}
+
+// a10: fused warp + in-bounds predicate (filter_points semantics: 0 <= p <= shape-1, inclusive).
+__global__ void warp_points_mask_kernel(const float* __restrict__ pts, int P, const float* __restrict__ Hm,
+                                        float sx, float sy, float* __restrict__ out,
+                                        uint8_t* __restrict__ keep) {
+  int b = blockIdx.y;
+  __shared__ float h[9];
+  if (threadIdx.x < 9) h[threadIdx.x] = Hm[b * 9 + threadIdx.x];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    float2 xy = reinterpret_cast<const float2*>(pts)[p];
+    float ox, oy;
+    homography_apply(h, xy.x, xy.y, ox, oy);
+    reinterpret_cast<float2*>(out)[(size_t)b * P + p] = make_float2(ox, oy);
+    keep[(size_t)b * P + p] = (ox >= 0.f && ox <= sx - 1.f && oy >= 0.f && oy <= sy - 1.f) ? 1 : 0;
+  }
+}
+
+extern "C" int ssp_warp_points_mask(const float* pts, int P, const float* Hm, int B, float shape_x,
+                                    float shape_y, float* out, uint8_t* keep, void* stream) {
+  SSP_REQUIRE(pts && Hm && out && keep, "ssp_warp_points_mask: null pointer");
+  SSP_REQUIRE(P >= 0 && B > 0, "ssp_warp_points_mask: bad sizes P=%d B=%d", P, B);
+  if (P == 0) return SSP_OK;
+  dim3 grid(min(ssp_ceil_div(P, 256), 148 * 8), B);
+  warp_points_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pts, P, Hm, shape_x, shape_y, out, keep);
+  SSP_CUDA_CHECK_LAUNCH("warp_points_mask_kernel");
+  return SSP_OK;
+}
+
+// Evaluation-side twin in float64 pixel coordinates (detector_evaluation.py:139-191):
+// warped = [x,y,1] H^T / z ; keep = 0 <= x < W and 0 <= y < H (strict upper bound).
+__global__ void warp_keypoints_f64_kernel(const double* __restrict__ kp, int K, const double* __restrict__ Hm,
+                                          double W, double Hh, double* __restrict__ out,
+                                          uint8_t* __restrict__ keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  double x = kp[2 * i], y = kp[2 * i + 1];
+  double X = Hm[0] * x + Hm[1] * y + Hm[2];
+  double Y = Hm[3] * x + Hm[4] * y + Hm[5];
+  double Z = Hm[6] * x + Hm[7] * y + Hm[8];
+  double ox = X / Z, oy = Y / Z;
+  out[2 * i] = ox;
+  out[2 * i + 1] = oy;
+  keep[i] = (ox >= 0.0 && ox < W && oy >= 0.0 && oy < Hh) ? 1 : 0;
+}
+
+extern "C" int ssp_warp_keypoints_f64(const double* kp, int K, const double* Hm, double W, double H,
+                                      double* out, uint8_t* keep, void* stream) {
+  SSP_REQUIRE(kp && Hm && out && keep, "ssp_warp_keypoints_f64: null pointer");
+  SSP_REQUIRE(K >= 0, "ssp_warp_keypoints_f64: bad K=%d", K);
+  if (K == 0) return SSP_OK;
+  warp_keypoints_f64_kernel<<<ssp_ceil_div(K, 128), 128, 0, (cudaStream_t)stream>>>(kp, K, Hm, W, H, out, keep);
+  SSP_CUDA_CHECK_LAUNCH("warp_keypoints_f64_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// a2: inv_warp_image_batch = F.grid_sample(img, warp(grid), mode, zeros padding, align_corners=True)
+// The normalised grid values xs[W], ys[H] are passed in as tables (the reference builds them with a
+// CPU torch.linspace, utils/utils.py:375) so that sampling coordinates are reproduced exactly.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bilinear_zero(const float* __restrict__ im, int H, int W, float ix, float iy) {
+  float fx = floorf(ix), fy = floorf(iy);
+  int x0 = (int)fx, y0 = (int)fy;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  // weights exactly as ATen grid_sampler: nw=(x1-ix)(y1-iy) ne=(ix-x0)(y1-iy) sw=(x1-ix)(iy-y0) se=(ix-x0)(iy-y0)
+  float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+  float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  bool xin0 = (x0 >= 0) & (x0 < W), xin1 = (x1 >= 0) & (x1 < W);
+  bool yin0 = (y0 >= 0) & (y0 < H), yin1 = (y1 >= 0) & (y1 < H);
+  float acc = 0.f;
+  if (yin0) {
+    const float* r = im + (size_t)y0 * W;
+    if (xin0) acc += __ldg(r + x0) * (wx0 * wy0);
+    if (xin1) acc += __ldg(r + x1) * (wx1 * wy0);
+  }
+  if (yin1) {
+    const float* r = im + (size_t)y1 * W;
+    if (xin0) acc += __ldg(r + x0) * (wx0 * wy1);
+    if (xin1) acc += __ldg(r + x1) * (wx1 * wy1);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float nearest_zero(const float* __restrict__ im, int H, int W, float ix, float iy) {
+  // std::nearbyint under the default rounding mode = round half to even = rintf
+  float rx = rintf(ix), ry = rintf(iy);
+  if (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H) return __ldg(im + (size_t)(int)ry * W + (int)rx);
+  return 0.f;
+}
+
+// src pixel coordinate of output pixel (x,y): grid_sampler unnormalize with align_corners=True
+__device__ __forceinline__ void src_coord(const float* h, float gx, float gy, int H, int W, float& ix, float& iy) {
+  float nx, ny;
+  homography_apply(h, gx, gy, nx, ny);
+  ix = ((nx + 1.f) / 2.f) * (float)(W - 1);
+  iy = ((ny + 1.f) / 2.f) * (float)(H - 1);
+}
+
+template <int MODE>  // 0 bilinear, 1 nearest
+__global__ void __launch_bounds__(256)
+inv_warp_kernel(const float* __restrict__ img, int C, int H, int W, const float* __restrict__ Hinv,
+                const float* __restrict__ xs, const float* __restrict__ ys, float* __restrict__ out) {
+  int b = blockIdx.z;
+  __shared__ float h[9];
+  if (threadIdx.x < 9 && threadIdx.y == 0) h[threadIdx.x] = Hinv[b * 9 + threadIdx.x];
+  __syncthreads();
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  float ix, iy;
+  src_coord(h, __ldg(xs + x), __ldg(ys + y), H, W, ix, iy);
+  size_t plane = (size_t)H * W;
+  for (int c = 0; c < C; ++c) {
+    const float* im = img + ((size_t)b * C + c) * plane;
+    float v = MODE == 0 ? bilinear_zero(im, H, W, ix, iy) : nearest_zero(im, H, W, ix, iy);
+    out[((size_t)b * C + c) * plane + (size_t)y * W + x] = v;
+  }
+}
+
+extern "C" int ssp_inv_warp_image(const float* img, int B, int C, int H, int W, const float* Hinv,
+                                  const float* xs, const float* ys, int mode, float* out, void* stream) {
+  SSP_REQUIRE(img && Hinv && xs && ys && out, "ssp_inv_warp_image: null pointer");
+  SSP_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "ssp_inv_warp_image: bad sizes B=%d C=%d H=%d W=%d", B, C, H, W);
+  SSP_REQUIRE(mode == 0 || mode == 1, "ssp_inv_warp_image: mode must be 0 (bilinear) or 1 (nearest), got %d", mode);
+  SSP_REQUIRE(B <= 65535, "ssp_inv_warp_image: batch %d exceeds grid.z limit", B);
+  dim3 block(32, 8);
+  dim3 grid(ssp_ceil_div(W, 32), ssp_ceil_div(H, 8), B);
+  if (mode == 0)
+    inv_warp_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(img, C, H, W, Hinv, xs, ys, out);
+  else
+    inv_warp_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(img, C, H, W, Hinv, xs, ys, out);
+  SSP_CUDA_CHECK_LAUNCH("inv_warp_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// a3: compute_valid_mask = nearest-warp of an all-ones image, then cv2.erode with an explicit
+// structuring element (taps that fall outside the image are ignored = cv2's default +inf border).
+// Fused: a 32x32 output tile computes the raw in-bounds predicate for tile+halo into shared memory
+// and takes the min over the kernel taps there; nothing but the final mask touches HBM.
+// ----------------------------------------------------------------------------------------------
+#define VM_TILE 32
+__global__ void __launch_bounds__(256)
+valid_mask_kernel(int H, int W, const float* __restrict__ Hinv, const float* __restrict__ xs,
+                  const float* __restrict__ ys, const uint8_t* __restrict__ kern, int kh, int kw, int ax, int ay,
+                  float* __restrict__ out) {
+  extern __shared__ uint8_t raw[];  // (VM_TILE + kh - 1) x (VM_TILE + kw - 1), 1 = valid or outside image
+  __shared__ float h[9];
+  int b = blockIdx.z;
+  int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < 9) h[tid] = Hinv[b * 9 + tid];
+  __syncthreads();
+  int ph = kh > 0 ? kh - 1 : 0, pw = kw > 0 ? kw - 1 : 0;
+  int th = VM_TILE + ph, tw = VM_TILE + pw;
+  int y0 = blockIdx.y * VM_TILE - (kh > 0 ? ay : 0);
+  int x0 = blockIdx.x * VM_TILE - (kw > 0 ? ax : 0);
+  for (int i = tid; i < th * tw; i += 256) {
+    int yy = y0 + i / tw, xx = x0 + i % tw;
+    uint8_t v = 1;  // outside the image: ignored by the erosion
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      float ix, iy;
+      src_coord(h, __ldg(xs + xx), __ldg(ys + yy), H, W, ix, iy);
+      float rx = rintf(ix), ry = rintf(iy);
+      v = (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H) ? 1 : 0;
+    }
+    raw[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < VM_TILE * VM_TILE; i += 256) {
+    int ly = i / VM_TILE, lx = i % VM_TILE;
+    int y = blockIdx.y * VM_TILE + ly, x = blockIdx.x * VM_TILE + lx;
+    if (y >= H || x >= W) continue;
+    uint8_t m = 1;
+    if (kh > 0 && kw > 0) {
+      for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx)
+          if (kern[ky * kw + kx]) m &= raw[(ly + ky) * tw + (lx + kx)];
+    } else {
+      m = raw[ly * tw + lx];
+    }
+    out[((size_t)b * H + y) * W + x] = (float)m;
+  }
+}
+
+extern "C" int ssp_valid_mask(int B, int H, int W, const float* Hinv, const float* xs, const float* ys,
+                              const uint8_t* kern, int kh, int kw, int ax, int ay, float* out, void* stream) {
+  SSP_REQUIRE(Hinv && xs && ys && out, "ssp_valid_mask: null pointer");
+  SSP_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "ssp_valid_mask: bad sizes B=%d H=%d W=%d", B, H, W);
+  SSP_REQUIRE((kh == 0 && kw == 0) || (kern && kh > 0 && kw > 0 && kh <= 64 && kw <= 64 && ax >= 0 && ax < kw &&
+                                       ay >= 0 && ay < kh),
+              "ssp_valid_mask: bad structuring element kh=%d kw=%d anchor=(%d,%d)", kh, kw, ax, ay);
+  dim3 block(32, 8);
+  dim3 grid(ssp_ceil_div(W, VM_TILE), ssp_ceil_div(H, VM_TILE), B);
+  size_t smem = (size_t)(VM_TILE + (kh > 0 ? kh - 1 : 0)) * (VM_TILE + (kw > 0 ? kw - 1 : 0));
+  valid_mask_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(H, W, Hinv, xs, ys, kern, kh, kw, ax, ay, out);
+  SSP_CUDA_CHECK_LAUNCH("valid_mask_kernel");
+  return SSP_OK;
+}

@@ -1,0 +1,226 @@
+"""autograd.Functions that drive the detector-loss and dense descriptor-loss kernels through the C ABI.
+
+reference: Train_model_heatmap_all.py:155-179 (detector_loss), utils/utils.py:779-893 (descriptor_loss).
+Multi-GPU: both losses use GLOBAL-batch normalisers, so with `dist_group` set the local
+numerators / mask sums are all-reduced (one tiny NCCL call each) before the division, and the backward
+kernels scale by the global normaliser.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import call, f32c, ptr, stream_of
+
+_ENGINES = ("bf16x3", "bf16", "fp32")
+_engine = "bf16x3"
+
+
+def set_descriptor_engine(name):
+    """'bf16x3' (tcgen05, hi/lo split, fp32-grade), 'bf16' (tcgen05 single pass) or 'fp32' (CUDA cores)."""
+    global _engine
+    if name not in _ENGINES:
+        raise ValueError("descriptor engine must be one of %s" % (_ENGINES,))
+    _engine = name
+
+
+def get_descriptor_engine():
+    return _engine
+
+
+def _all_reduce(t, group):
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if group is True else group)
+
+
+# ------------------------------------------------------------------------------------------------
+class DetectorLossFn(torch.autograd.Function):
+    """loss = sum_cells mask * sum_c BCE(softmax(semi)_c, target_c) / (sum mask + 1e-5)
+
+    fused2d=False: target [B,65,Hc,Wc], mask [B,Hc,Wc]  (reference signature)
+    fused2d=True : target = labels_2D [B,1,H,W], mask = mask_2D [B,1,H,W] (labels2Dto3D + getMasks fused)
+    """
+
+    @staticmethod
+    def forward(ctx, semi, target, mask, fused2d, dist_group=None):
+        _lib.require_cuda(semi)
+        dev = semi.device
+        x = f32c(semi.detach(), dev)
+        t = f32c(target.detach(), dev)
+        m = f32c(mask.detach(), dev)
+        B, C, Hc, Wc = x.shape
+        if C != 65:
+            raise RuntimeError("detector_loss: input must have 65 channels, got %d" % C)
+        if fused2d:
+            if t.numel() != B * Hc * Wc * 64 or m.numel() != B * Hc * Wc * 64:
+                raise RuntimeError("detector_loss_2d: labels_2D / mask_2D must be [B,1,8Hc,8Wc]")
+        else:
+            if t.shape != x.shape or m.numel() != B * Hc * Wc:
+                raise RuntimeError("detector_loss: target must be [B,65,Hc,Wc] and mask [B,Hc,Wc]")
+        out3 = torch.empty((3,), dtype=torch.float32, device=dev)
+        nbytes = _lib.load().ssp_detector_loss_ws_bytes(B, Hc, Wc)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        call("ssp_detector_loss_fwd", ptr(x), ptr(t), ptr(m), B, Hc, Wc, 1 if fused2d else 0, ptr(out3), ptr(ws),
+             nbytes, stream_of(x))
+        if dist_group is not None:
+            sums = torch.stack((out3[1], out3[2] - 1e-5))
+            _all_reduce(sums, dist_group)
+            out3[1] = sums[0]
+            out3[2] = sums[1] + 1e-5
+            out3[0] = out3[1] / out3[2]
+        ctx.save_for_backward(x, t, m, out3)
+        ctx.fused2d = fused2d
+        return out3[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        x, t, m, out3 = ctx.saved_tensors
+        B, C, Hc, Wc = x.shape
+        g = f32c(gout.reshape(1), x.device)
+        dsemi = torch.empty_like(x)
+        call("ssp_detector_loss_bwd", ptr(x), ptr(t), ptr(m), B, Hc, Wc, 1 if ctx.fused2d else 0, ptr(out3), ptr(g),
+             ptr(dsemi), stream_of(x))
+        return dsemi, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+def _nc_pad(nc):
+    return (nc + 127) // 128 * 128
+
+
+class DescriptorLossFn(torch.autograd.Function):
+    """Dense descriptor hinge loss.  Returns (loss_desc, pos_sum, neg_sum, wpts); the three scalars are
+    differentiable w.r.t. descriptors and descriptors_warped, wpts (warped cell centres) is not."""
+
+    @staticmethod
+    def forward(ctx, D, Dw, Hm, mv, cell, lamda, dist, engine, dist_group=None, debug_S=None):
+        lib = _lib.load()
+        dev = D.device
+        Dc = f32c(D.detach(), dev)
+        Dwc = f32c(Dw.detach(), dev)
+        if Dc.shape != Dwc.shape:
+            raise RuntimeError("descriptor_loss: descriptor shapes differ")
+        B, Dch, Hc, Wc = Dc.shape
+        Nc = Hc * Wc
+        Ncp = _nc_pad(Nc)
+        st = stream_of(Dc)
+        mpos, mneg = 1.0, 0.2  # hard-coded in the reference (utils/utils.py:817-818)
+        if engine not in _ENGINES:
+            raise ValueError("descriptor engine must be one of %s" % (_ENGINES,))
+        if Dch != 256:
+            engine = "fp32"  # the tcgen05 kernels are specialised for 256 channels
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+
+        wpts = torch.empty((B, Ncp, 2), dtype=torch.float32, device=dev)
+        mv_pad = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
+        call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), st)
+
+        npos = lib.ssp_desc_pos_nblocks(B, Nc)
+        pos_part = torch.empty((npos, 2), dtype=torch.float64, device=dev)
+        call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos,
+             ptr(pos_part), st)
+
+        bitsR = bitsC = None
+        if need_grad:
+            bitsR = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
+            bitsC = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
+        planes = None
+        if engine == "fp32":
+            nneg = lib.ssp_desc_dense_simt_nblocks(B, Nc)
+            neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
+            call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist,
+                 mneg, ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+        else:
+            split = engine == "bf16x3"
+            Ahi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
+            Bhi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
+            Alo = torch.empty_like(Ahi) if split else None
+            Blo = torch.empty_like(Bhi) if split else None
+            call("ssp_desc_pack", ptr(Dc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), st)
+            call("ssp_desc_pack", ptr(Dwc), None, B, Dch, Nc, ptr(Bhi), ptr(Blo), st)
+            nneg = lib.ssp_desc_dense_tc_nblocks(B, Nc)
+            neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
+            call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc,
+                 cell, dist, mneg, ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+            planes = (Ahi, Alo)
+
+        out8 = torch.empty((8,), dtype=torch.float32, device=dev)
+        call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_pad), B, Hc, Wc, ptr(out8), st)
+        if dist_group is not None:
+            import torch.distributed as tdist
+            sums = out8[4:8].clone()
+            _all_reduce(sums, dist_group)
+            world = tdist.get_world_size(None if dist_group is True else dist_group)
+            norm = float(B * world) * (sums[3] + 1.0) * float(Hc * Wc)
+            out8[3] = norm
+            out8[0:3] = sums[0:3] / norm
+
+        if need_grad:
+            ctx.save_for_backward(Dc, Dwc, wpts, mv_pad, out8, bitsR, bitsC,
+                                  *( [planes[0]] + ([planes[1]] if planes[1] is not None else []) if planes else []))
+        ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
+        ctx.mark_non_differentiable(wpts)
+        return out8[0], out8[1], out8[2], wpts
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_loss, g_pos, g_neg, _g_wpts):
+        saved = ctx.saved_tensors
+        Dc, Dwc, wpts, mv_pad, out8, bitsR, bitsC = saved[:7]
+        B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, split = ctx.meta
+        dev = Dc.device
+        Nc = Hc * Wc
+        Ncp = _nc_pad(Nc)
+        st = stream_of(Dc)
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g3 = torch.stack([(g if g is not None else zero).reshape(()).to(torch.float32) for g in (g_loss, g_pos, g_neg)])
+        g3 = g3.contiguous()
+        alpha = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
+        call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), st)
+        dD = torch.empty_like(Dc)
+        dDw = torch.empty_like(Dwc)
+        if engine == "fp32":
+            # dD[b,:,r] = sum_c I[r,c] * alpha[c] * Dw[b,:,c];   dDw[b,:,c] = alpha[c] * sum_r I[r,c] * D[b,:,r]
+            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, B, Dch, Nc, ptr(dD), st)
+            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), B, Dch, Nc, ptr(dDw), st)
+        else:
+            Ahi = saved[7]
+            Alo = saved[8] if split else None
+            Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
+            Slo = torch.empty_like(Shi) if split else None
+            call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, B, Nc, ptr(dD), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), B, Nc, ptr(dDw), st)
+        call("ssp_desc_pos_bwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), ptr(g3), ptr(out8), B, Hc, Wc, Dch, cell,
+             dist, lamda, mpos, ptr(dD), ptr(dDw), st)
+        return dD, dDw, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+class LazyPairMask(object):
+    """The [B,Hc,Wc,Hc,Wc] float correspondence mask of descriptor_loss (utils/utils.py:854-860), built only
+    when somebody looks at it: the reference's single caller never does, and at B=32 it is 184 MB."""
+
+    def __init__(self, wpts, B, Hc, Wc, cell, dist):
+        self._wpts, self._geom, self._t = wpts, (B, Hc, Wc, cell, dist), None
+
+    @property
+    def shape(self):
+        B, Hc, Wc, _, _ = self._geom
+        return torch.Size((B, Hc, Wc, Hc, Wc))
+
+    def materialize(self):
+        if self._t is None:
+            B, Hc, Wc, cell, dist = self._geom
+            m = torch.empty((B, Hc * Wc, Hc * Wc), dtype=torch.float32, device=self._wpts.device)
+            call("ssp_desc_pair_mask", ptr(self._wpts), B, Hc, Wc, cell, dist, ptr(m), stream_of(m))
+            self._t = m.view(B, Hc, Wc, Hc, Wc)
+        return self._t
+
+    def __getattr__(self, name):  # anything else behaves like the tensor
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        conv = lambda a: a.materialize() if isinstance(a, LazyPairMask) else a
+        return func(*[conv(a) for a in args], **{k: conv(v) for k, v in (kwargs or {}).items()})

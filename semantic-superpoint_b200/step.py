@@ -1,0 +1,48 @@
+"""The two hot loops of the reference, expressed over the kernels (no backbone: heads' outputs come in).
+
+loss_step          = Train_model_heatmap_all.train_val_sample lines 295-350 (detector loss x2 + descriptor loss)
+adaptation_step    = export.export_detector_homoAdapt_gpu lines 304-323 (flatten -> aggregate -> NMS -> top-k)
+Both are free of host synchronisation except the final keypoint read-back of adaptation_step.
+"""
+import torch
+
+from . import utils as U
+
+
+def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2D, mask_warp_2D, mat_H,
+              lamda_d=250, descriptor_dist=4, lambda_loss=1.0, engine=None, dist_group=None):
+    """Returns dict(loss, loss_det, loss_det_warp, loss_desc, positive_dist, negative_dist).
+
+    loss = loss_det + loss_det_warp + lambda_loss * loss_desc   (uniform weighting, Train_model_heatmap_all.py:361-365)
+    """
+    loss_det = U.detector_loss_2d(semi, labels_2D, mask_2D, dist_group=dist_group)
+    loss_det_warp = U.detector_loss_2d(semi_warp, warped_labels, mask_warp_2D, dist_group=dist_group)
+    mask_desc = U.getMasks(mask_warp_2D, 8, device=semi.device).unsqueeze(1)
+    kw = {"dist_group": dist_group}
+    if engine is not None:
+        kw["engine"] = engine
+    loss_desc, _mask, pos, neg = U.descriptor_loss(desc, desc_warp, mat_H, mask_valid=mask_desc, device=semi.device,
+                                                   lamda_d=lamda_d, descriptor_dist=descriptor_dist, **kw)
+    loss = loss_det + loss_det_warp + lambda_loss * loss_desc
+    return {"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
+            "positive_dist": pos, "negative_dist": neg}
+
+
+@torch.no_grad()
+def adaptation_step(semi, inv_homographies, mask_2D, conf_thresh=0.015, nms_dist=4, top_k=600):
+    """semi [I,N,65,Hc,Wc] (or [N,65,Hc,Wc]), inv_homographies [I,N,3,3], mask_2D [I,N,H,W] -> list of [K,3] arrays
+    (x, y, prob), K <= top_k, per source image."""
+    if semi.dim() == 4:
+        semi, inv_homographies, mask_2D = semi.unsqueeze(0), inv_homographies.reshape(1, -1, 3, 3), mask_2D.reshape(
+            1, semi.shape[0], mask_2D.shape[-2], mask_2D.shape[-1])
+    I, N, C, Hc, Wc = semi.shape
+    heat = U.flattenDetection(semi.reshape(I * N, C, Hc, Wc)).reshape(I, N, Hc * 8, Wc * 8)
+    agg = U.combine_heatmap_batch(heat, inv_homographies, mask_2D)
+    pts = U.heatmap_to_pts_batch(agg, conf_thresh, nms_dist)
+    out = []
+    for p in pts:
+        p = p.transpose()
+        if top_k and p.shape[0] > top_k:
+            p = p[:top_k, :]
+        out.append(p)
+    return out

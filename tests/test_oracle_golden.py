@@ -1,0 +1,117 @@
+"""oracle/ssp_oracle.py against outputs of the live reference (tests/golden/*.npz, made by make_golden.py).
+This is the pin of the oracle: the reference itself has no fixtures for the path."""
+import numpy as np
+
+from oracle import ssp_oracle as O
+from ssp_b200 import synth
+
+TOL = 1e-4  # relative, the north_star tolerance for coordinates / pixels / losses / gradients
+
+
+def close(a, b, rtol=TOL, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def test_warp_points(golden):
+    g = golden("warp_points")
+    close(O.warp_points(g["pts"], g["H"]), g["out_batched"])
+    close(O.warp_points(g["pts"], g["H"][1]), g["out_single"])
+    fp, fm = O.filter_points(g["pix"], [64, 48], return_mask=True)
+    assert np.array_equal(fm, g["filt_mask"]) and np.array_equal(fp, g["filt_pts"])
+
+
+def test_inv_warp(golden):
+    g = golden("inv_warp")
+    close(O.inv_warp_image_batch(g["img"], g["Hinv"], "bilinear"), g["out_bilinear"], atol=2e-6)
+    on = O.inv_warp_image_batch(g["img"], g["Hinv"], "nearest")
+    assert (on != g["out_nearest"]).mean() < 1e-3  # nearest ties at exact half pixels may flip
+    close(O.inv_warp_image_batch(g["img"][0, 0], g["Hinv"][0])[0, 0], g["out_single"], atol=2e-6)
+    close(O.inv_warp_image_batch(g["img"][:1], np.eye(3, dtype=np.float32)), g["out_identity"], atol=2e-6)
+
+
+def test_valid_mask_and_ellipse(golden):
+    g = golden("valid_mask")
+    for r in range(1, 9):
+        assert np.array_equal(O.ellipse_kernel(r), g["ellipse_%d" % r]), r
+    for r in (0, 1, 3):
+        m = O.compute_valid_mask((48, 64), g["Hinv5"], r)
+        assert (m != g["mask_r%d" % r]).sum() <= 2, r
+    m = O.compute_valid_mask((240, 320), g["Hinv2"], 3)
+    assert (m != g["mask_240_r3"]).sum() <= 4
+    assert np.array_equal(O.compute_valid_mask((48, 64), np.eye(3), 3), g["mask_identity_r3"])
+
+
+def test_labels_and_detector_loss(golden):
+    g = golden("detector")
+    close(O.labels2Dto3D(g["lab_bin"]), g["l3_bin"])
+    close(O.labels2Dto3D(g["lab_soft"]), g["l3_soft"])
+    close(O.labels2Dto3D(g["lab_tiny"]), g["l3_tiny"])
+    close(O.labels2Dto3D(g["lab_bin"], add_dustbin=False), g["l3_nodust"])
+    close(O.getMasks(g["mask2d"]), g["mask3d"])
+    loss, d = O.detector_loss(g["semi"], g["l3_bin"], g["mask3d"], grad=True)
+    close(loss, g["loss"])
+    close(d, g["dsemi"], atol=1e-7)
+    loss2, d2 = O.detector_loss(g["semi2"], g["l3_soft"], g["mask3d"], grad=True)
+    close(loss2, g["loss2"])
+    close(d2 * g["g2"], g["dsemi2"], atol=1e-7)
+
+
+def test_flatten_and_combine(golden):
+    g = golden("flatten")
+    close(O.flattenDetection(g["semi"]), g["heat"])
+    close(O.flattenDetection(g["semi"][0]), g["heat3d"])
+    c = golden("combine")
+    out = O.combine_heatmap(c["heat"], c["Hwarp"][None], c["mask"])
+    assert np.array_equal(np.isnan(out), np.isnan(c["out"]))
+    close(np.nan_to_num(out), np.nan_to_num(c["out"]), atol=2e-6)
+
+
+def test_nms(golden):
+    g = golden("nms")
+    for key, (h, w, seed, thr, r) in {"pts_120": (120, 160, 61, 0.015, 4), "pts_240": (240, 320, 62, 0.015, 4),
+                                      "pts_64": (64, 96, 63, 0.03, 2)}.items():
+        pts = O.getPtsFromHeatmap(synth.unique_heatmap(h, w, seed), thr, r)
+        assert pts.dtype == np.float64 and np.array_equal(pts, g[key]), key
+    assert np.array_equal(O.getPtsFromHeatmap(g["sparse"], 0.015, 4), g["pts_sparse"])
+    one = np.zeros((48, 64), np.float32); one[20, 30] = 0.5
+    assert np.array_equal(O.getPtsFromHeatmap(one, 0.015, 4), g["pts_one"])
+    assert O.getPtsFromHeatmap(np.zeros((48, 64), np.float32), 0.015, 4).shape == (3, 0)
+    out, inds = O.nms_fast(g["corners"], 48, 64, 4)
+    assert np.array_equal(out, g["nms_fast_out"]) and np.array_equal(inds, g["nms_fast_inds"])
+
+
+def test_box_nms(golden):
+    g = golden("box_nms")
+    assert np.array_equal(O.box_nms(g["prob"], 4, 0.1, 0.01), g["out"])
+
+
+def test_descriptor_loss_small(golden):
+    g = golden("desc_small")
+    for tag, gr in (("a", (1.0, 0.0, 0.0)), ("b", tuple(g["g_b"]))):
+        loss, mask, pos, neg, dD, dDw = O.descriptor_loss(g["D"], g["Dw"], g["H"], g["mv"], grad=gr, return_mask=True)
+        close(loss, g["loss_" + tag]); close(pos, g["pos_" + tag]); close(neg, g["neg_" + tag])
+        assert np.array_equal(mask.astype(np.uint8), g["mask_" + tag])
+        scale = np.abs(g["dD_" + tag]).max()
+        close(dD, g["dD_" + tag], atol=1e-4 * scale)
+        close(dDw, g["dDw_" + tag], atol=1e-4 * scale)
+
+
+def test_descriptor_loss_30x40(golden):
+    g = golden("desc_30x40")
+    D = synth.unit_descriptors(1, 256, 30, 40, 91, smooth=0.3)
+    Dw = synth.unit_descriptors(1, 256, 30, 40, 92, smooth=0.3)
+    loss, mask, pos, neg, dD, dDw = O.descriptor_loss(D, Dw, g["H"], g["mv"], grad=(1, 1, 1), return_mask=True)
+    close(loss, g["loss"]); close(pos, g["pos"]); close(neg, g["neg"])
+    assert np.array_equal(mask.reshape(1, 1200, 1200).sum(-1), g["mask_rowsum"])
+    scale = np.abs(g["dD_sample"]).max()
+    close(dD[0, :, ::7, ::9], g["dD_sample"], atol=2e-4 * scale)
+    close(dDw[0, :, ::7, ::9], g["dDw_sample"], atol=2e-4 * scale)
+
+
+def test_descriptor_identity_kat(golden):
+    """identical descriptors + identity homography: the positive term vanishes (reference's informal KAT)."""
+    g = golden("desc_identity")
+    D = synth.unit_descriptors(1, 256, 30, 40, 91, smooth=0.3)
+    loss, _, pos, neg = O.descriptor_loss(D, D.copy(), np.eye(3)[None], np.ones((1, 1, 30, 40), np.float32))
+    close(pos, g["pos"], atol=1e-7); close(neg, g["neg"]); close(loss, g["loss"])
+    assert abs(float(pos)) < 1e-6
