@@ -1,0 +1,363 @@
+"""bench.py -- loss-step pairs/s @240x320 B32 (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...       # the CPU path (oracle port) on the box's host cores
+
+A "step" is one pass of the hot path over one batch: detector loss on both images + dense descriptor loss,
+forward and backward, on 32 synthetic 240x320 pairs per GPU (head outputs `semi`/`desc` are the inputs; the
+conv backbone is not on this path).  Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H_IMG, W_IMG, HC, WC, DCH, B_PER_GPU = 240, 320, 30, 40, 256, 32
+NC = HC * WC
+METRIC = "loss-step pairs/s @240x320 B32"
+N_ADAPT = 100
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+
+
+def host_inputs(B, seed):
+    """One batch of synthetic loss-step inputs as numpy arrays."""
+    from ssp_b200 import synth
+    rng = np.random.default_rng(seed)
+    Hs = np.stack([np.linalg.inv(synth.sample_homography(rng)) for _ in range(B)]).astype(np.float32)
+    return {
+        "semi": synth.pseudo_normal((B, 65, HC, WC), seed * 10 + 1),
+        "semi_warp": synth.pseudo_normal((B, 65, HC, WC), seed * 10 + 2),
+        "desc": synth.unit_descriptors(B, DCH, HC, WC, seed * 10 + 3, smooth=0.3),
+        "desc_warp": synth.unit_descriptors(B, DCH, HC, WC, seed * 10 + 4, smooth=0.3),
+        "labels_2D": synth.keypoint_labels(B, H_IMG, W_IMG, seed * 10 + 5),
+        "warped_labels": synth.keypoint_labels(B, H_IMG, W_IMG, seed * 10 + 6),
+        "mat_H": Hs,
+        "inv_H": np.linalg.inv(Hs).astype(np.float32),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_loss_step(inp):
+    from oracle import ssp_oracle as O
+    B = inp["semi"].shape[0]
+    m2 = np.ones((B, 1, H_IMG, W_IMG), np.float32)
+    mw2 = O.compute_valid_mask((H_IMG, W_IMG), inp["inv_H"], 3)[:, None]
+    m3, mw3 = O.getMasks(m2), O.getMasks(mw2)
+    l1, _ = O.detector_loss(inp["semi"], O.labels2Dto3D(inp["labels_2D"]), m3, grad=True)
+    l2, _ = O.detector_loss(inp["semi_warp"], O.labels2Dto3D(inp["warped_labels"]), mw3, grad=True)
+    r = O.descriptor_loss(inp["desc"], inp["desc_warp"], inp["mat_H"], mw3[:, None], grad=(1.0, 0.0, 0.0))
+    return float(l1) + float(l2) + float(r[0])
+
+
+def cpu_baseline(sample_pairs, reps):
+    inp = host_inputs(sample_pairs, 99)
+    cpu_loss_step(inp)  # warm-up (BLAS threads, page faults)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_loss_step(inp)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": sample_pairs / dt, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d pairs of 240x320 per step (fwd+bwd, numpy/BLAS oracle port of the reference path; the reference "
+                      "itself materialises a 1.47 GB/pair product and ran ~1 pair/s on 8 cores), %d reps" % (sample_pairs, reps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = 2  # BASELINE configs[0]: the reference's own CPU-runnable case
+    inp = host_inputs(pairs, 99)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_loss_step(inp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_loss_step(inp)
+    dt = time.perf_counter() - t0
+    val = pairs * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "loss step (detector x2 + dense descriptor, fwd+bwd), bounded sample of %d pairs 240x320 per step" % pairs},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d pairs per step, %d steps" % (pairs, args.steps)},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import ssp_b200 as S
+    from ssp_b200 import _lib, dist as sdist
+
+    rank, world, local = sdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = True if world > 1 else None
+    S.set_descriptor_engine(args.engine)
+    B = B_PER_GPU
+    NSETS = 3  # 3 x 138 MB of inputs rotate, > 126 MB L2: every step reads its inputs from HBM
+
+    host_sets = [host_inputs(B, 1000 * rank + s) for s in range(NSETS)]
+    keys = ["semi", "semi_warp", "desc", "desc_warp", "labels_2D", "warped_labels", "mat_H", "inv_H"]
+    pinned = [{k: torch.from_numpy(hs[k]).pin_memory() for k in keys} for hs in host_sets]
+    dsets = []
+    for p in pinned:
+        d = {k: p[k].to(dev) for k in keys}
+        d["mask_2D"] = torch.ones((B, 1, H_IMG, W_IMG), device=dev)
+        d["mask_warp_2D"] = S.compute_valid_mask(torch.tensor([H_IMG, W_IMG]), d["inv_H"], device=dev, erosion_radius=3).unsqueeze(1)
+        dsets.append(d)
+    for p, d in zip(pinned, dsets):
+        p["mask_2D"] = d["mask_2D"].cpu().pin_memory()
+        p["mask_warp_2D"] = d["mask_warp_2D"].cpu().pin_memory()
+    in_keys = ["semi", "semi_warp", "desc", "desc_warp", "labels_2D", "warped_labels", "mask_2D", "mask_warp_2D", "mat_H"]
+    h2d_bytes = sum(pinned[0][k].numel() * pinned[0][k].element_size() for k in in_keys)
+
+    def step(d):
+        leaves = [d[k].detach().requires_grad_(True) for k in ("semi", "semi_warp", "desc", "desc_warp")]
+        out = S.step.loss_step(leaves[0], leaves[1], leaves[2], leaves[3], d["labels_2D"], d["warped_labels"], d["mask_2D"],
+                               d["mask_warp_2D"], d["mat_H"], dist_group=group)
+        out["loss"].backward()
+        return out["loss"], leaves
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(dsets[i % NSETS])
+    barrier()
+
+    # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    calls0, kern0 = _lib.launch_count, _lib.kernel_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        loss, _ = step(dsets[i % NSETS])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    kernels = _lib.kernel_count - kern0
+    clocks = sampler.stop()
+    ms = sdist.max_over_ranks(ms, dev)
+    value = B * world * args.steps / (ms * 1e-3)
+    loss_val = float(loss)
+
+    # ---- e2e: same step through the public API from pinned HOST buffers, H2D inside the timed region
+    #      (double-buffered on a copy stream), loss scalar read back every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [{k: torch.empty_like(dsets[0][k]) for k in in_keys} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            for k in in_keys:
+                bufs[slot][k].copy_(pinned[i % NSETS][k], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n):
+        for f in freed:
+            f.record()
+        upload(0)
+        last = 0.0
+        for i in range(n):
+            slot = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            l, _ = step(bufs[slot])
+            freed[slot].record()
+            last = float(l)  # device -> host read of the step's result
+        return last
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = sdist.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)), dev)
+    e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-entry-point CUDA-event durations over K more steps
+    _lib.profile_begin()
+    for i in range(args.steps):
+        step(dsets[i % NSETS])
+    torch.cuda.synchronize()
+    prof = _lib.profile_end()  # {entry point: (calls, total ms)}
+    total_prof = sum(v[1] for v in prof.values())
+    shares = {k: {"calls_per_step": v[0] / args.steps, "us_per_call": 1e3 * v[1] / v[0], "share": v[1] / total_prof}
+              for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    top = next(iter(shares))
+    pk = peaks()
+    flops_pair = 2.0 * NC * NC * DCH
+    bound_tbl = {
+        "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
+        "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
+        "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
+        "ssp_desc_pos_bwd": ("hbm", 6.0 * B * NC * DCH * 4),
+        "ssp_detector_loss_fwd": ("hbm", B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+        "ssp_detector_loss_bwd": ("hbm", B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+    }
+    kind, work = bound_tbl.get(top, ("hbm", 0.0))
+    dur_s = shares[top]["us_per_call"] * 1e-6
+    if kind == "tensor":
+        achieved, peak, unit = work / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
+    else:
+        achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+    roofline = {"kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "traffic": None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
+                "us_per_launch": shares[top]["us_per_call"],
+                "note": "algorithmic 2*Nc^2*256 flop per pair x 32 pairs per launch; bf16x3 issues 3 (fwd) / 2 (bwd) MMAs per "
+                        "algorithmic MAC, so its ceiling is 1/3 (1/2) of the bf16 peak"}
+
+    # ---- second headline of BASELINE.json: homography adaptation images/s (N=100), measured in the same run
+    extra = {}
+    if not args.no_adapt:
+        extra = bench_adaptation(torch, S, dev, rank, world, sdist, barrier)
+
+    if rank == 0:
+        cpu = cpu_baseline(8, 2) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "bf16x3 (hi/lo split bf16 on tcgen05, fp32 accumulate, fp32-grade)", "bf16": "bf16", "fp32": "f32"}[args.engine],
+            "data": "synthetic",
+            "config": {"workload": "SSp loss step: detector loss x2 + dense descriptor loss, fwd+bwd, 32 pairs of 240x320 per GPU "
+                                   "(Nc=1200 cells, 256-d), inputs = head outputs resident in HBM",
+                       "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine,
+                       "l2": "3 input sets x 138 MB rotate (> 126 MB L2)", "exchange": "all-reduce of 6 scalars (global normalisers)" if world > 1 else "none"},
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs (head outputs + labels + masks), double-buffered H2D on a copy stream, loss read back per step; PCIe-bound"},
+            "gpu_launches": kernels, "clocks": clocks, "roofline": roofline, "kernel_shares": shares, "loss": loss_val,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, images_per_step=4, steps=6):
+    """export_detector_homoAdapt hot loop: flattenDetection -> combine_heatmap -> getPtsFromHeatmap -> top-k for
+    N=100 views per source image; source images sharded over ranks (no collective)."""
+    from ssp_b200 import synth
+    I, N = images_per_step, N_ADAPT
+    rng = np.random.default_rng(500 + rank)
+    Hs = np.stack([[np.linalg.inv(synth.sample_homography(rng, max_angle=3.14 / 2)) for _ in range(N)] for _ in range(I)])
+    Hs[:, 0] = np.eye(3)
+    Hs = Hs.astype(np.float32)
+    Hinv = torch.from_numpy(np.linalg.inv(Hs).astype(np.float32)).to(dev)
+    sets = []
+    for s in range(2):  # 2 x 250 MB > L2
+        semi = torch.from_numpy(synth.pseudo_normal((I, N, 65, HC, WC), 7000 + 10 * rank + s) * 3).to(dev)
+        mask = S.compute_valid_mask(torch.tensor([H_IMG, W_IMG]), Hinv.reshape(-1, 3, 3), device=dev).reshape(I, N, H_IMG, W_IMG)
+        sets.append((semi, mask))
+    Hw = torch.from_numpy(Hs).to(dev)
+    for s in range(2):
+        pts = S.step.adaptation_step(sets[s][0], Hw, sets[s][1])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        pts = S.step.adaptation_step(sets[i % 2][0], Hw, sets[i % 2][1])
+    e1.record()
+    barrier()
+    ms = sdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    return {"homography_adaptation": {"metric": "homography-adapt imgs/s (N=100)", "value": I * world * steps / (ms * 1e-3),
+                                      "unit": "images/s", "images_per_step_per_gpu": I, "steps": steps,
+                                      "keypoints_first_image": int(pts[0].shape[0]),
+                                      "note": "detector logits of the 100 warped views resident in HBM; flatten + aggregate + NMS + top-600, keypoints copied to host"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--no-adapt", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,11 +89,43 @@ def check(rc, what):
         raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
 
 
+# kernels launched per entry point (memsets / copies not counted); the NMS drivers launch init + >= 2 rounds +
+# compact + rank, counted at their minimum
+KERNELS_PER_CALL = {"ssp_desc_pos_bwd": 2, "ssp_nms_fast": 5, "ssp_box_nms": 4}
+kernel_count = 0
+_prof = None
+
+
+def profile_begin():
+    """Start bracketing every entry point with CUDA events on the launching (current) stream."""
+    global _prof
+    _prof = {}
+
+
+def profile_end():
+    """Stop profiling; returns {entry point: (calls, total milliseconds)}."""
+    global _prof
+    torch.cuda.synchronize()
+    out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in _prof.items()}
+    _prof = None
+    return out
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and raise RuntimeError(ssp_last_error()) on failure."""
-    global launch_count
+    global launch_count, kernel_count
     launch_count += 1
-    check(getattr(load(), name)(*args), name)
+    kernel_count += KERNELS_PER_CALL.get(name, 1)
+    fn = getattr(load(), name)
+    if _prof is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    _prof.setdefault(name, []).append((e0, e1))
+    check(rc, name)
 
 
 def ptr(t):

@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+The loss step shards by batch; its only exchange is the global-batch normalisers (both reference losses
+divide by whole-batch quantities: Train_model_heatmap_all.py:178, utils/utils.py:886-887).  Homography
+adaptation shards by source image with no data-path collective.
+"""
+import os
+
+import torch
+import torch.distributed as tdist
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment.  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not tdist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        tdist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def _group(group):
+    return None if group is True else group
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of n_items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def globalize_detector(out3, group):
+    """out3 = [loss, numerator, sum(mask) + 1e-5] of the local shard -> same triple for the global batch."""
+    sums = torch.stack((out3[1], out3[2] - 1e-5))
+    tdist.all_reduce(sums, op=tdist.ReduceOp.SUM, group=_group(group))
+    out3[1] = sums[0]
+    out3[2] = sums[1] + 1e-5
+    out3[0] = out3[1] / out3[2]
+    return out3
+
+
+def globalize_descriptor(out8, B_local, Hc, Wc, group):
+    """out8 = [loss, pos, neg, norm, num_loss, num_pos, num_neg, sum(mask_valid)] of the local shard -> global batch.
+    norm_global = B_global * (sum_global(mask_valid) + 1) * Hc * Wc  (utils/utils.py:886-887)."""
+    sums = out8[4:8].clone()
+    tdist.all_reduce(sums, op=tdist.ReduceOp.SUM, group=_group(group))
+    world = tdist.get_world_size(_group(group))
+    norm = float(B_local * world) * (sums[3] + 1.0) * float(Hc * Wc)
+    out8[3] = norm
+    out8[0:3] = sums[0:3] / norm
+    out8[4:8] = sums
+    return out8
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over all ranks (timing is reported as the slowest rank)."""
+    if not tdist.is_initialized():
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    return float(t.item())

@@ -27,11 +27,6 @@ def get_descriptor_engine():
     return _engine
 
 
-def _all_reduce(t, group):
-    import torch.distributed as dist
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if group is True else group)
-
-
 # ------------------------------------------------------------------------------------------------
 class DetectorLossFn(torch.autograd.Function):
     """loss = sum_cells mask * sum_c BCE(softmax(semi)_c, target_c) / (sum mask + 1e-5)
@@ -62,11 +57,8 @@ class DetectorLossFn(torch.autograd.Function):
         call("ssp_detector_loss_fwd", ptr(x), ptr(t), ptr(m), B, Hc, Wc, 1 if fused2d else 0, ptr(out3), ptr(ws),
              nbytes, stream_of(x))
         if dist_group is not None:
-            sums = torch.stack((out3[1], out3[2] - 1e-5))
-            _all_reduce(sums, dist_group)
-            out3[1] = sums[0]
-            out3[2] = sums[1] + 1e-5
-            out3[0] = out3[1] / out3[2]
+            from .dist import globalize_detector
+            globalize_detector(out3, dist_group)
         ctx.save_for_backward(x, t, m, out3)
         ctx.fused2d = fused2d
         return out3[0]
@@ -147,13 +139,8 @@ class DescriptorLossFn(torch.autograd.Function):
         out8 = torch.empty((8,), dtype=torch.float32, device=dev)
         call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_pad), B, Hc, Wc, ptr(out8), st)
         if dist_group is not None:
-            import torch.distributed as tdist
-            sums = out8[4:8].clone()
-            _all_reduce(sums, dist_group)
-            world = tdist.get_world_size(None if dist_group is True else dist_group)
-            norm = float(B * world) * (sums[3] + 1.0) * float(Hc * Wc)
-            out8[3] = norm
-            out8[0:3] = sums[0:3] / norm
+            from .dist import globalize_descriptor
+            globalize_descriptor(out8, B, Hc, Wc, dist_group)
 
         if need_grad:
             ctx.save_for_backward(Dc, Dwc, wpts, mv_pad, out8, bitsR, bitsC,

@@ -84,10 +84,9 @@ def sample_homography(rng, shift=-1, perspective=True, scaling=True, rotation=Tr
             ((scaled >= 0) & (scaled < 1)).all(axis=(1, 2)))[0]
         pts2 = scaled[valid[rng.integers(0, len(valid))]]
     if translation:
-        t_min, t_max = pts2.min(axis=0), (1 - pts2).min(axis=0)
-        if allow_artifacts:
-            t_min, t_max = t_min + margin, t_max + margin
-        pts2 += np.array([rng.uniform(-t_min[0], t_max[0]), rng.uniform(-t_min[1], t_max[1])])[None]
+        t_min, t_max = pts2.min(axis=0), (1 - pts2).min(axis=0)  # translation_overflow = 0 (homographies.py:100-105)
+        lo, hi = -t_min, t_max  # like numpy's legacy uniform, lo > hi is allowed (artifacts enabled)
+        pts2 += (lo + (hi - lo) * rng.random(2))[None]
     if rotation:
         angles = np.concatenate([np.linspace(-max_angle, max_angle, n_angles), [0.0]])
         center = pts2.mean(axis=0, keepdims=True)

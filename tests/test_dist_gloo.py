@@ -1,0 +1,66 @@
+"""world_size-2 gloo test of the only exchange step on the path: the global-batch normalisers of both losses
+(SURVEY 8e).  Each rank holds half of the batch; after the all-reduce every rank must report the loss the
+oracle computes on the whole batch."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+from oracle import ssp_oracle as O
+from ssp_b200 import synth
+
+B, HC, WC, DCH = 4, 6, 8, 32
+
+
+def _inputs():
+    rng = np.random.default_rng(3)
+    Hs = np.stack([np.linalg.inv(synth.sample_homography(rng)) for _ in range(B)]).astype(np.float32)
+    D = synth.unit_descriptors(B, DCH, HC, WC, 1, smooth=0.4)
+    Dw = synth.unit_descriptors(B, DCH, HC, WC, 2, smooth=0.4)
+    mv = (synth.uniform((B, 1, HC, WC), 3) < 0.7).astype(np.float32)
+    semi = synth.pseudo_normal((B, 65, HC, WC), 4)
+    lab = O.labels2Dto3D(synth.keypoint_labels(B, HC * 8, WC * 8, 5, p=0.02))
+    m3 = (synth.uniform((B, HC, WC), 6) < 0.8).astype(np.float32)
+    return Hs, D, Dw, mv, semi, lab, m3
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as tdist
+    from ssp_b200.dist import globalize_descriptor, globalize_detector, init_from_env, shard_range
+    init_from_env(backend="gloo")
+    Hs, D, Dw, mv, semi, lab, m3 = _inputs()
+    lo, hi = shard_range(B, rank, world)
+    # local shard through the oracle -> the raw sums the kernels would emit (out8 / out3 layouts)
+    l, _, p, n = O.descriptor_loss(D[lo:hi], Dw[lo:hi], Hs[lo:hi], mv[lo:hi])
+    norm = np.float32(hi - lo) * (mv[lo:hi].sum() + 1) * HC * WC
+    out8 = torch.tensor([l, p, n, norm, l * norm, p * norm, n * norm, mv[lo:hi].sum()], dtype=torch.float32)
+    globalize_descriptor(out8, hi - lo, HC, WC, True)
+    ld = O.detector_loss(semi[lo:hi], lab[lo:hi], m3[lo:hi])
+    den = np.float32(m3[lo:hi].sum() + 1e-5)
+    out3 = torch.tensor([ld, ld * den, den], dtype=torch.float32)
+    globalize_detector(out3, True)
+    q.put((rank, out8.numpy().copy(), out3.numpy().copy()))
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+def test_global_normalisers_world2():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    Hs, D, Dw, mv, semi, lab, m3 = _inputs()
+    l, _, p, n = O.descriptor_loss(D, Dw, Hs, mv)
+    ld = O.detector_loss(semi, lab, m3)
+    for rank, out8, out3 in res:
+        np.testing.assert_allclose(out8[:3], [l, p, n], rtol=1e-5)
+        np.testing.assert_allclose(out8[3], B * (mv.sum() + 1) * HC * WC, rtol=1e-6)
+        np.testing.assert_allclose(out3[0], ld, rtol=1e-5)
+    np.testing.assert_array_equal(res[0][1], res[1][1])  # identical on both ranks

@@ -1,0 +1,95 @@
+"""Host-side logic that needs no GPU: structuring elements, NMS stencils, input generators, drop-in binding,
+loud failure without CUDA."""
+import hashlib
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ssp_b200 as S
+from ssp_b200 import synth
+
+
+def test_ellipse_kernel_matches_opencv(golden):
+    g = golden("valid_mask")
+    for r in range(1, 9):
+        assert np.array_equal(S.ellipse_kernel(r), g["ellipse_%d" % r])
+    assert S.ellipse_kernel(3).tolist() == [[0, 0, 0, 1, 0, 0], [0, 1, 1, 1, 1, 1], [1] * 6, [1] * 6, [1] * 6, [0, 1, 1, 1, 1, 1]]
+
+
+def test_box_nms_stencil_size4():
+    """with size=4, IoU>0.1 suppresses exactly these |dx|,|dy| offsets."""
+    from ssp_b200.utils import _iou_stencil
+    st, R = _iou_stencil(4, 0.1, "cpu")
+    assert R == 3
+    st = st.numpy().reshape(7, 7)
+    want = {(0, 1), (0, 2), (0, 3), (1, 0), (1, 1), (1, 2), (1, 3), (2, 0), (2, 1), (2, 2), (3, 0), (3, 1), (0, 0)}
+    got = {(abs(dx), abs(dy)) for dy in range(-3, 4) for dx in range(-3, 4) if st[dy + 3, dx + 3]}
+    assert got == want
+
+
+def test_synth_is_bit_reproducible():
+    h = hashlib.sha256(synth.uniform((1000,), 7).tobytes()).hexdigest()
+    assert h == hashlib.sha256(synth.uniform((1000,), 7).tobytes()).hexdigest()
+    u = synth.uniform((4096,), 1)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
+    assert float(u[0]) == pytest.approx(float(synth.uniform((1,), 1)[0]))
+    d = synth.unit_descriptors(2, 256, 3, 4, 5)
+    np.testing.assert_allclose((d.astype(np.float64) ** 2).sum(1), 1.0, atol=1e-6)
+    hm = synth.unique_heatmap(24, 32, 3)
+    assert len(np.unique(hm)) == 24 * 32
+    Hm = synth.sample_homography(np.random.default_rng(0))
+    assert Hm.shape == (3, 3) and abs(Hm[2, 2] - 1.0) < 0.2 and abs(np.linalg.det(Hm)) > 0.1
+
+
+def test_dropin_binds_and_restores():
+    fake = types.ModuleType("fake_utils")
+    fake.descriptor_loss = lambda *a, **k: "ref"
+    fake.warp_points = lambda *a, **k: "ref"
+
+    class Trainer:
+        def detector_loss(self, *a, **k):
+            return "ref"
+
+    bound = S.dropin.install(utils_module=fake, trainer_class=Trainer)
+    assert fake.descriptor_loss is S.utils.descriptor_loss and fake.labels2Dto3D is S.utils.labels2Dto3D
+    assert any(b.endswith("detector_loss") for b in bound)
+    S.dropin.uninstall()
+    assert fake.descriptor_loss() == "ref" and Trainer().detector_loss() == "ref"
+
+
+def test_signatures_mirror_reference():
+    import inspect
+    sig = inspect.signature(S.descriptor_loss)
+    assert list(sig.parameters)[:8] == ["descriptors", "descriptors_warped", "homographies", "mask_valid", "cell_size",
+                                        "lamda_d", "device", "descriptor_dist"]
+    assert sig.parameters["lamda_d"].default == 250 and sig.parameters["descriptor_dist"].default == 4
+    assert any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())  # **config swallows lambda_d=800
+    assert list(inspect.signature(S.inv_warp_image_batch).parameters) == ["img", "mat_homo_inv", "device", "mode"]
+    assert list(inspect.signature(S.warp_points).parameters) == ["points", "homographies", "device"]
+    assert list(inspect.signature(S.getPtsFromHeatmap).parameters) == ["heatmap", "conf_thresh", "nms_dist"]
+    assert list(inspect.signature(S.box_nms).parameters) == ["prob", "size", "iou", "min_prob", "keep_top_k"]
+    assert list(inspect.signature(S.compute_valid_mask).parameters)[:4] == ["image_shape", "inv_homography", "device", "erosion_radius"]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_cuda():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        S.warp_points(torch.zeros(4, 2), torch.eye(3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        S.descriptor_loss(torch.zeros(1, 256, 4, 4), torch.zeros(1, 256, 4, 4), torch.eye(3)[None])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        S.detector_loss(torch.zeros(1, 65, 4, 4), torch.zeros(1, 65, 4, 4), torch.ones(1, 4, 4))
+    with pytest.raises(NotImplementedError):
+        S.box_nms(torch.zeros(8, 8), 4)
+
+
+def test_shard_range_covers_everything():
+    from ssp_b200.dist import shard_range
+    for n in (0, 1, 7, 8, 100):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
