@@ -186,24 +186,35 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # kernels per step, counted on one eager step
+    step(dsets[0])
+    k0 = _lib.kernel_count
+    step(dsets[0])
+    kernels_per_step = _lib.kernel_count - k0
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
+    if use_graph:
+        # fwd+bwd of the whole step captured once per input set and replayed: the step is ~25 short kernels
+        graphs = [S.step.GraphedLossStep(d, dist_group=group) for d in dsets]
+        run = lambda i: graphs[i % NSETS].replay()["loss"]
+    else:
+        run = lambda i: step(dsets[i % NSETS])[0]
     for i in range(max(args.warmup, 3)):
-        step(dsets[i % NSETS])
+        run(i)
     barrier()
 
     # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    calls0, kern0 = _lib.launch_count, _lib.kernel_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for i in range(args.steps):
-        loss, _ = step(dsets[i % NSETS])
+        loss = run(i)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    kernels = _lib.kernel_count - kern0
+    kernels = kernels_per_step * args.steps
     clocks = sampler.stop()
     ms = sdist.max_over_ranks(ms, dev)
     value = B * world * args.steps / (ms * 1e-3)
@@ -212,7 +223,11 @@ def run_ours(args):
     # ---- e2e: same step through the public API from pinned HOST buffers, H2D inside the timed region
     #      (double-buffered on a copy stream), loss scalar read back every step
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [{k: torch.empty_like(dsets[0][k]) for k in in_keys} for _ in range(2)]
+    if use_graph:
+        slots = [S.step.GraphedLossStep(dsets[0], dist_group=group) for _ in range(2)]
+        bufs = [g.static for g in slots]
+    else:
+        bufs = [{k: torch.empty_like(dsets[0][k]) for k in in_keys} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
@@ -224,6 +239,9 @@ def run_ours(args):
                 bufs[slot][k].copy_(pinned[i % NSETS][k], non_blocking=True)
             ready[slot].record(copy_stream)
 
+    def run_slot(slot):
+        return slots[slot].replay()["loss"] if use_graph else step(bufs[slot])[0]
+
     def e2e_loop(n):
         for f in freed:
             f.record()
@@ -234,7 +252,7 @@ def run_ours(args):
             if i + 1 < n:
                 upload(i + 1)
             torch.cuda.current_stream().wait_event(ready[slot])
-            l, _ = step(bufs[slot])
+            l = run_slot(slot)
             freed[slot].record()
             last = float(l)  # device -> host read of the step's result
         return last
@@ -266,7 +284,7 @@ def run_ours(args):
         "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
         "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
         "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
-        "ssp_desc_pos_bwd": ("hbm", 6.0 * B * NC * DCH * 4),
+        "ssp_desc_pos_coef": ("hbm", 8.0 * B * NC * 16 * 4),
         "ssp_detector_loss_fwd": ("hbm", B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
         "ssp_detector_loss_bwd": ("hbm", B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
     }
@@ -296,7 +314,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "SSp loss step: detector loss x2 + dense descriptor loss, fwd+bwd, 32 pairs of 240x320 per GPU "
                                    "(Nc=1200 cells, 256-d), inputs = head outputs resident in HBM",
-                       "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine,
+                       "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine, "cuda_graph": use_graph,
                        "l2": "3 input sets x 138 MB rotate (> 126 MB L2)", "exchange": "all-reduce of 6 scalars (global normalisers)" if world > 1 else "none"},
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs (head outputs + labels + masks), double-buffered H2D on a copy stream, loss read back per step; PCIe-bound"},
@@ -351,6 +369,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-adapt", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph-multi", action="store_true", help="also use CUDA graphs when world > 1 (NCCL inside the graph)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -83,32 +83,42 @@ int ssp_box_nms(const float* prob /*[I,H,W]*/, int I, int H, int W, float min_pr
 int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/, int B, int Hc, int Wc,
                       int cell, float* wpts, float* mv_pad, void* stream);
 int ssp_desc_pos_nblocks(int B, int Nc);
+int ssp_desc_maxp(void); /* DESC_MAXP: list slots per row / column */
+/* sparse positive pairs: exact fp32 dots, partial sums (4 doubles per block: pos_u, pos_w, negcorr_u, negcorr_w)
+ * and the pair lists rowcol/rowdot/colrow/coldot [B,Nc_pad,DESC_MAXP], colcnt [B,Nc_pad] used by the backward */
 int ssp_desc_pos_fwd(const float* D /*[B,Dch,Hc,Wc]*/, const float* Dw, const float* wpts, const float* mv_pad, int B,
-                     int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos, double* partials,
+                     int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos, float mneg,
+                     double* partials, int* rowcol, float* rowdot, int* colcnt, int* colrow, float* coldot,
                      void* stream);
 int ssp_desc_dense_simt_nblocks(int B, int Nc);
-int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* wpts, const float* mv_pad, int B, int Hc,
-                            int Wc, int Dch, int cell, float dist, float mneg, double* partials, uint32_t* bitsR,
-                            uint32_t* bitsC, float* dbgS /*[B,Nc,Nc] or NULL*/, void* stream);
+int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* mv_pad, int B, int Hc, int Wc, int Dch,
+                            float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
+                            float* dbgS /*[B,Nc,Nc] or NULL*/, void* stream);
 int ssp_desc_pack(const float* src /*[B,Dch,Nc]*/, const float* scale /*[B,Nc_pad] or NULL*/, int B, int Dch, int Nc,
                   void* hi /*bf16 [B,Nc_pad,Dch]*/, void* lo /*or NULL*/, void* stream);
 int ssp_desc_dense_tc_nblocks(int B, int Nc);
-int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* wpts,
-                          const float* mv_pad, int B, int Hc, int Wc, int cell, float dist, float mneg,
-                          double* partials, uint32_t* bitsR, uint32_t* bitsC, float* dbgS, void* stream);
+int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
+                          int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
+                          float* dbgS, void* stream);
 int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const float* mv_pad, int B,
                       int Hc, int Wc, float* out8, void* stream);
 int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,
                        void* stream);
 int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)*/, const float* out8, int B,
                    int Nc_pad, float* alpha /*[B,Nc_pad]*/, void* stream);
+/* backward coefficients of the positive pairs (and removal of their negative term); sorts colrow in place */
+int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, int* colrow, const float* coldot,
+                      const uint32_t* bitsR, const float* mv_pad, const float* alpha, const float* g3,
+                      const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, float* colcoef,
+                      void* stream);
+/* indicator GEMM  out[b,d,r] = rowscale[b,r] * sum_k bit(r,k) * colscale[b,k] * src[b,d,k]
+ *                            + sum_n pcoef[b,r,n] * possrc[b,d,plist[b,r,n]]   (plist may be NULL) */
 int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src /*[B,Dch,Nc]*/, const float* colscale,
-                            const float* rowscale, int B, int Dch, int Nc, float* out /*[B,Dch,Nc]*/, void* stream);
-int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale, int B, int Nc,
+                            const float* rowscale, const int* plist, const float* pcoef, const float* possrc, int B,
+                            int Dch, int Nc, float* out /*[B,Dch,Nc]*/, void* stream);
+int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
+                          const int* plist, const float* pcoef, const float* possrc /*[B,256,Nc]*/, int B, int Nc,
                           float* out /*[B,256,Nc]*/, void* stream);
-int ssp_desc_pos_bwd(const float* D, const float* Dw, const float* wpts, const float* mv_pad, const float* g3,
-                     const float* out8, int B, int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos,
-                     float* dD, float* dDw, void* stream);
 
 #ifdef __cplusplus
 }

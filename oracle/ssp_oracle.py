@@ -383,6 +383,31 @@ def descriptor_loss(descriptors, descriptors_warped, homographies, mask_valid=No
     return res
 
 
+def descriptor_boundary_slack(descriptors, descriptors_warped, homographies, mask_valid=None, cell_size=8, lamda_d=250,
+                              descriptor_dist=4, eps=1e-3):
+    """Largest change of (loss, pos_sum, neg_sum) if every pair whose centre distance lies within `eps` of
+    descriptor_dist flipped its mask bit (the mask is a step function of fp32 coordinates ~1e3 in magnitude, so
+    1-ulp differences in the warp arithmetic flip such pairs; each flip moves the numerator by up to lamda_d)."""
+    D = np.asarray(descriptors, dtype=f32)
+    Dw = np.asarray(descriptors_warped, dtype=f32)
+    B, Dch, Hc, Wc = D.shape
+    Nc = Hc * Wc
+    _, w = descriptor_pair_mask(homographies, Hc, Wc, cell_size, descriptor_dist)
+    kk, ll = np.meshgrid(np.arange(Hc), np.arange(Wc), indexing="ij")
+    cy = (kk.reshape(-1) * cell_size + cell_size // 2).astype(np.float64)
+    cx = (ll.reshape(-1) * cell_size + cell_size // 2).astype(np.float64)
+    mv = np.ones((B, Nc), f32) if mask_valid is None else np.asarray(mask_valid, dtype=f32).reshape(B, Nc)
+    norm = float(B) * (float(mv.sum()) + 1.0) * Hc * Wc
+    slack = 0.0
+    for b in range(B):
+        d = np.sqrt((cy[None, :] - w[b, :, 1:2].astype(np.float64)) ** 2 + (cx[None, :] - w[b, :, 0:1].astype(np.float64)) ** 2)
+        rr, cc = np.nonzero(np.abs(d - descriptor_dist) < eps)
+        for r, c in zip(rr, cc):
+            dot = float(D[b].reshape(Dch, Nc)[:, r].astype(np.float64) @ Dw[b].reshape(Dch, Nc)[:, c].astype(np.float64))
+            slack += lamda_d * max(1.0 - dot, 0.0) + max(dot - 0.2, 0.0)
+    return slack / norm
+
+
 def descriptor_dots(descriptors, descriptors_warped):
     """float64 all-pairs dot products [B,Nc,Nc] (used by tests to locate hinge kinks)."""
     D = np.asarray(descriptors, dtype=np.float64)

@@ -40,18 +40,19 @@ SIGNATURES = {
     "ssp_box_nms": (_I, [_P, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "ssp_desc_geometry": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_pos_nblocks": (_I, [_I, _I]),
-    "ssp_desc_pos_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
+    "ssp_desc_maxp": (_I, []),
+    "ssp_desc_pos_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ssp_desc_dense_simt_nblocks": (_I, [_I, _I]),
-    "ssp_desc_dense_fwd_simt": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "ssp_desc_dense_fwd_simt": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "ssp_desc_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
-    "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P]),
     "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
     "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P]),
-    "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
-    "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
-    "ssp_desc_pos_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
+    "ssp_desc_pos_coef": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -91,7 +92,7 @@ def check(rc, what):
 
 # kernels launched per entry point (memsets / copies not counted); the NMS drivers launch init + >= 2 rounds +
 # compact + rank, counted at their minimum
-KERNELS_PER_CALL = {"ssp_desc_pos_bwd": 2, "ssp_nms_fast": 5, "ssp_box_nms": 4}
+KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4}
 kernel_count = 0
 _prof = None
 

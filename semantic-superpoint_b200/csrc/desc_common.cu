@@ -61,50 +61,101 @@ __device__ __forceinline__ void pos_window(float wx, float wy, float dist, int H
   if (!(a <= (float)Hc && b >= -1.f && c <= (float)Wc && d >= -1.f)) { k0 = 1; k1 = 0; }
 }
 
-__device__ __forceinline__ float dot_exact(const float* __restrict__ a, const float* __restrict__ b, int Dch,
-                                           size_t stride) {
-  float acc = 0.f;
-  for (int d = 0; d < Dch; ++d) acc = fmaf(__ldg(a + d * stride), __ldg(b + d * stride), acc);
-  return acc;
-}
-
 // ----------------------------------------------------------------------------------------------
-// positive pairs, forward:  partial sums of lamda * max(mpos - dot, 0)  (unweighted, mv-weighted)
+// positive pairs, forward.  The dense GEMM kernel treats EVERY pair as a negative (no geometry in its
+// epilogue); this kernel owns the sparse positive set (<= DESC_MAXP per row for descriptor_dist <= cell):
+//   * exact fp32 dot product of every positive pair (block = 32 rows x 8 channel groups, coalesced in NCHW)
+//   * partial sums  lamda*max(mpos-dot,0)  and the correction  max(dot-mneg,0)  that the dense sum wrongly
+//     contains for these pairs (the hinge is continuous, so the mismatch between this exact dot and the
+//     tensor-core dot is bounded by their difference, ~1e-6)
+//   * pair lists for the backward: per row (partner column, dot) and, through an atomic slot counter, per
+//     column (partner row, dot)
+// partials: 4 doubles per block = { pos_unweighted, pos_weighted, negcorr_unweighted, negcorr_weighted }
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+#define POS_ROWS 32
+#define POS_DG 8
+__global__ void __launch_bounds__(POS_ROWS * POS_DG)
 desc_pos_fwd_kernel(const float* __restrict__ D, const float* __restrict__ Dw, const float2* __restrict__ wpts,
-                    const float* __restrict__ mv_pad, DescGeom g, double* __restrict__ partials) {
+                    const float* __restrict__ mv_pad, DescGeom g, double* __restrict__ partials,
+                    int* __restrict__ rowcol, float* __restrict__ rowdot, int* __restrict__ colcnt,
+                    int* __restrict__ colrow, float* __restrict__ coldot) {
+  __shared__ int scol[POS_ROWS][DESC_MAXP];
+  __shared__ int scnt[POS_ROWS];
+  __shared__ float spart[POS_DG][POS_ROWS];
   __shared__ double sh[32];
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc_u = 0.0, acc_w = 0.0;
-  if (row < g.B * g.Nc) {
-    int b = row / g.Nc, ij = row - b * g.Nc;
-    float2 w = wpts[(size_t)b * g.Nc_pad + ij];
-    int k0, k1, l0, l1;
-    pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
-    const float* Db = D + (size_t)b * g.Dch * g.Nc + ij;
-    const float* Dwb = Dw + (size_t)b * g.Dch * g.Nc;
-    for (int k = k0; k <= k1; ++k)
-      for (int l = l0; l <= l1; ++l) {
-        int c = k * g.Wc + l;
-        float cx, cy;
-        cell_center(c, g.Wc, g.cell, cx, cy);
-        if (!pair_positive(w.x, w.y, cx, cy, g.dist)) continue;
-        float dot = dot_exact(Db, Dwb + c, g.Dch, g.Nc);
-        float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
-        acc_u += (double)pos;
-        acc_w += (double)(pos * mv_pad[(size_t)b * g.Nc_pad + c]);
-      }
+  __shared__ int smax;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int r = blockIdx.x * POS_ROWS + lane;
+  if (threadIdx.x == 0) smax = 0;
+  __syncthreads();
+  if (dg == 0) {
+    int cnt = 0;
+    if (r < g.Nc) {
+      float2 w = wpts[(size_t)b * g.Nc_pad + r];
+      int k0, k1, l0, l1;
+      pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
+      for (int k = k0; k <= k1; ++k)
+        for (int l = l0; l <= l1; ++l) {
+          int c = k * g.Wc + l;
+          float cx, cy;
+          cell_center(c, g.Wc, g.cell, cx, cy);
+          if (pair_positive(w.x, w.y, cx, cy, g.dist) && cnt < DESC_MAXP) scol[lane][cnt++] = c;
+        }
+    }
+    scnt[lane] = cnt;
+    if (r < g.Nc_pad)
+      for (int n = 0; n < DESC_MAXP; ++n) rowcol[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n] = n < cnt ? scol[lane][n] : -1;
+    atomicMax(&smax, cnt);
   }
-  double ru = block_sum_d(acc_u, sh);
-  double rw = block_sum_d(acc_w, sh);
-  if (threadIdx.x == 0) {
-    partials[2 * (size_t)blockIdx.x] = ru;
-    partials[2 * (size_t)blockIdx.x + 1] = rw;
+  __syncthreads();
+  const int nmax = smax;
+  const int dper = (g.Dch + POS_DG - 1) / POS_DG;
+  const int d0 = dg * dper, d1 = min(g.Dch, d0 + dper);
+  const float* Db = D + (size_t)b * g.Dch * g.Nc + r;
+  const float* Dwb = Dw + (size_t)b * g.Dch * g.Nc;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int n = 0; n < nmax; ++n) {
+    bool has = n < scnt[lane];
+    int c = has ? scol[lane][n] : 0;
+    float part = 0.f;
+    if (has) {
+#pragma unroll 8
+      for (int d = d0; d < d1; ++d) part = fmaf(__ldg(Db + (size_t)d * g.Nc), __ldg(Dwb + (size_t)d * g.Nc + c), part);
+    }
+    spart[dg][lane] = part;
+    __syncthreads();
+    if (dg == 0 && has) {
+      float dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < POS_DG; ++q) dot += spart[q][lane];
+      float mv = mv_pad[(size_t)b * g.Nc_pad + c];
+      float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
+      float negc = fmaxf(dot - g.mneg, 0.f);
+      acc[0] += (double)pos;
+      acc[1] += (double)(pos * mv);
+      acc[2] += (double)negc;
+      acc[3] += (double)(negc * mv);
+      rowdot[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n] = dot;
+      int slot = atomicAdd(colcnt + (size_t)b * g.Nc_pad + c, 1);
+      if (slot < DESC_MAXP) {
+        colrow[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = r;
+        coldot[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = dot;
+      } else {
+        atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, 1);  // overflow counter
+      }
+    }
+    __syncthreads();
+  }
+  size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double v = block_sum_d(acc[i], sh);
+    if (threadIdx.x == 0) partials[4 * blk + i] = v;
   }
 }
 
-extern "C" int ssp_desc_pos_nblocks(int B, int Nc) { return ssp_ceil_div(B * Nc, 128); }
+extern "C" int ssp_desc_pos_nblocks(int B, int Nc) { return B * ssp_ceil_div(Nc, POS_ROWS); }
+extern "C" int ssp_desc_maxp(void) { return DESC_MAXP; }
 
 static int fill_geom(DescGeom& g, int B, int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos,
                      float mneg) {
@@ -113,14 +164,24 @@ static int fill_geom(DescGeom& g, int B, int Hc, int Wc, int Dch, int cell, floa
   return (B > 0 && Hc > 0 && Wc > 0 && Dch > 0 && cell > 0) ? 0 : -1;
 }
 
+// Lists: rowcol/rowdot/colrow/coldot [B, Nc_pad, DESC_MAXP], colcnt [B*Nc_pad + 1] (zeroed here; the last
+// element counts pairs that did not fit a column list).
 extern "C" int ssp_desc_pos_fwd(const float* D, const float* Dw, const float* wpts, const float* mv_pad, int B,
-                                int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos,
-                                double* partials, void* stream) {
-  SSP_REQUIRE(D && Dw && wpts && mv_pad && partials, "ssp_desc_pos_fwd: null pointer");
+                                int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos, float mneg,
+                                double* partials, int* rowcol, float* rowdot, int* colcnt, int* colrow,
+                                float* coldot, void* stream) {
+  SSP_REQUIRE(D && Dw && wpts && mv_pad && partials && rowcol && rowdot && colcnt && colrow && coldot,
+              "ssp_desc_pos_fwd: null pointer");
   DescGeom g;
-  SSP_REQUIRE(fill_geom(g, B, Hc, Wc, Dch, cell, dist, lamda, mpos, 0.f) == 0, "ssp_desc_pos_fwd: bad sizes");
-  desc_pos_fwd_kernel<<<ssp_desc_pos_nblocks(B, g.Nc), 128, 0, (cudaStream_t)stream>>>(
-      D, Dw, reinterpret_cast<const float2*>(wpts), mv_pad, g, partials);
+  SSP_REQUIRE(fill_geom(g, B, Hc, Wc, Dch, cell, dist, lamda, mpos, mneg) == 0 && B <= 65535, "ssp_desc_pos_fwd: bad sizes");
+  SSP_REQUIRE(dist >= 0.f && dist <= (float)cell,
+              "ssp_desc_pos_fwd: descriptor_dist %.3f > cell_size %d is not supported (sparse positive lists hold %d pairs per cell)",
+              dist, cell, DESC_MAXP);
+  cudaStream_t st = (cudaStream_t)stream;
+  SSP_CUDA_CALL(cudaMemsetAsync(colcnt, 0, ((size_t)B * g.Nc_pad + 1) * sizeof(int), st));
+  dim3 grid(ssp_ceil_div(g.Nc, POS_ROWS), B);
+  desc_pos_fwd_kernel<<<grid, POS_ROWS * POS_DG, 0, st>>>(D, Dw, reinterpret_cast<const float2*>(wpts), mv_pad, g,
+                                                           partials, rowcol, rowdot, colcnt, colrow, coldot);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_fwd_kernel");
   return SSP_OK;
 }
@@ -134,7 +195,10 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
                      const float* __restrict__ mv_pad, size_t nmv, int B, int Hc, int Wc, float* __restrict__ out4) {
   __shared__ double sh[32];
   double pu = 0, pw = 0, nu = 0, nw = 0, sm = 0;
-  for (int i = threadIdx.x; i < npos; i += blockDim.x) { pu += pos_part[2 * i]; pw += pos_part[2 * i + 1]; }
+  double cu = 0, cw = 0;  // negative-hinge contribution of the positive pairs, contained in the dense sums
+  for (int i = threadIdx.x; i < npos; i += blockDim.x) {
+    pu += pos_part[4 * i]; pw += pos_part[4 * i + 1]; cu += pos_part[4 * i + 2]; cw += pos_part[4 * i + 3];
+  }
   for (int i = threadIdx.x; i < nneg; i += blockDim.x) { nu += neg_part[2 * i]; nw += neg_part[2 * i + 1]; }
   for (size_t i = threadIdx.x; i < nmv; i += blockDim.x) sm += (double)mv_pad[i];
   pu = block_sum_d(pu, sh);
@@ -142,7 +206,11 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
   nu = block_sum_d(nu, sh);
   nw = block_sum_d(nw, sh);
   sm = block_sum_d(sm, sh);
+  cu = block_sum_d(cu, sh);
+  cw = block_sum_d(cw, sh);
   if (threadIdx.x == 0) {
+    nu -= cu;
+    nw -= cw;
     float norm = (float)B * ((float)sm + 1.f) * (float)Hc * (float)Wc;
     out4[0] = (float)((pw + nw) / (double)norm);
     out4[1] = (float)(pu / (double)norm);
@@ -211,97 +279,88 @@ extern "C" int ssp_desc_alpha(const float* mv_pad, const float* g3, const float*
 }
 
 // ----------------------------------------------------------------------------------------------
-// positive pairs, backward.  Runs after the dense indicator-GEMMs stored dD / dDw.
-//   coef = -lamda * ind(mpos - dot) * (g_loss * mv[c] + g_pos) / norm,  ind = 1 (x>0), 0.5 (x==0), 0
-//   rows  (thread per ij): dD [b,:,ij] += coef * Dw[b,:,c]
-//   cols  (thread per c, brute-force scan of all rows): dDw[b,:,c] += coef * D[b,:,ij]
-// Each output column has exactly one writer, so the result is deterministic (no atomics).
+// positive pairs, backward: per-list-entry coefficients consumed by the indicator-GEMM epilogues.
+//   coef = -lamda * ind(mpos - dot) * (g_loss * mv[c] + g_pos) / norm,  ind = 1 (x>0), 0.5 (x==0), 0 (x<0)
+//          - (bit(r,c) ? alpha[c] : 0)        <- removes the negative-hinge term the indicator GEMM adds for
+//                                                this pair (its bit is set whenever the dense dot exceeded mneg)
+//   rows: rowcoef[b,r,n] for partner column rowcol[b,r,n]          (dD [b,:,r] += coef * Dw[b,:,c])
+//   cols: entries sorted by row index (deterministic sum order), colcoef (dDw[b,:,c] += coef * D [b,:,r])
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float pos_coef(float dot, float mv, const float* __restrict__ g3, float norm,
-                                          const DescGeom& g) {
-  float x = g.mpos - dot;
+__device__ __forceinline__ float pos_coef(float dot, float mv, const float* __restrict__ g3, float norm, float lamda,
+                                          float mpos) {
+  float x = mpos - dot;
   float ind = x > 0.f ? 1.f : (x == 0.f ? 0.5f : 0.f);
-  return -g.lamda * ind * (g3[0] * mv + g3[1]) / norm;
+  return -lamda * ind * (g3[0] * mv + g3[1]) / norm;
 }
 
-__global__ void __launch_bounds__(128)
-desc_pos_bwd_rows_kernel(const float* __restrict__ D, const float* __restrict__ Dw,
-                         const float2* __restrict__ wpts, const float* __restrict__ mv_pad,
-                         const float* __restrict__ g3, const float* __restrict__ out4, DescGeom g,
-                         float* __restrict__ dD) {
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= g.B * g.Nc) return;
-  int b = row / g.Nc, ij = row - b * g.Nc;
-  float2 w = wpts[(size_t)b * g.Nc_pad + ij];
-  int k0, k1, l0, l1;
-  pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
-  const float* Db = D + (size_t)b * g.Dch * g.Nc + ij;
-  const float* Dwb = Dw + (size_t)b * g.Dch * g.Nc;
-  float* dDb = dD + (size_t)b * g.Dch * g.Nc + ij;
-  float norm = out4[3];
-  for (int k = k0; k <= k1; ++k)
-    for (int l = l0; l <= l1; ++l) {
-      int c = k * g.Wc + l;
-      float cx, cy;
-      cell_center(c, g.Wc, g.cell, cx, cy);
-      if (!pair_positive(w.x, w.y, cx, cy, g.dist)) continue;
-      float dot = dot_exact(Db, Dwb + c, g.Dch, g.Nc);
-      float coef = pos_coef(dot, mv_pad[(size_t)b * g.Nc_pad + c], g3, norm, g);
-      if (coef == 0.f) continue;
-      for (int d = 0; d < g.Dch; ++d) dDb[(size_t)d * g.Nc] += coef * __ldg(Dwb + c + (size_t)d * g.Nc);
-    }
-}
-
-__global__ void __launch_bounds__(128)
-desc_pos_bwd_cols_kernel(const float* __restrict__ D, const float* __restrict__ Dw,
-                         const float2* __restrict__ wpts, const float* __restrict__ mv_pad,
-                         const float* __restrict__ g3, const float* __restrict__ out4, DescGeom g,
-                         float* __restrict__ dDw) {
-  __shared__ float2 sw[128];
+__global__ void desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowdot,
+                                     const int* __restrict__ colcnt, int* __restrict__ colrow,
+                                     const float* __restrict__ coldot, const uint32_t* __restrict__ bitsR,
+                                     const float* __restrict__ mv_pad, const float* __restrict__ alpha,
+                                     const float* __restrict__ g3, const float* __restrict__ out8, int Nc_pad,
+                                     float lamda, float mpos, float* __restrict__ rowcoef, float* __restrict__ colcoef) {
   int b = blockIdx.y;
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = c < g.Nc;
-  float cx = 0.f, cy = 0.f, mv = 0.f;
-  if (active) {
-    cell_center(c, g.Wc, g.cell, cx, cy);
-    mv = mv_pad[(size_t)b * g.Nc_pad + c];
-  }
-  const float* Db = D + (size_t)b * g.Dch * g.Nc;
-  const float* Dwb = Dw + (size_t)b * g.Dch * g.Nc + c;
-  float* dDwb = dDw + (size_t)b * g.Dch * g.Nc + c;
-  float norm = out4[3];
-  for (int r0 = 0; r0 < g.Nc; r0 += 128) {
-    __syncthreads();
-    int r = r0 + threadIdx.x;
-    sw[threadIdx.x] = r < g.Nc ? wpts[(size_t)b * g.Nc_pad + r] : make_float2(SSP_FAR, SSP_FAR);
-    __syncthreads();
-    if (!active) continue;
-    int lim = min(128, g.Nc - r0);
-    for (int q = 0; q < lim; ++q) {
-      float2 w = sw[q];
-      if (!pair_positive(w.x, w.y, cx, cy, g.dist)) continue;
-      int ij = r0 + q;
-      float dot = dot_exact(Db + ij, Dwb, g.Dch, g.Nc);
-      float coef = pos_coef(dot, mv, g3, norm, g);
-      if (coef == 0.f) continue;
-      for (int d = 0; d < g.Dch; ++d) dDwb[(size_t)d * g.Nc] += coef * __ldg(Db + ij + (size_t)d * g.Nc);
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= Nc_pad) return;
+  const int NW = Nc_pad / 32;
+  const float norm = out8[3];
+  size_t base = ((size_t)b * Nc_pad + cell) * DESC_MAXP;
+  // row list of cell = r
+#pragma unroll
+  for (int n = 0; n < DESC_MAXP; ++n) {
+    int c = rowcol[base + n];
+    float coef = 0.f;
+    if (c >= 0) {
+      coef = pos_coef(rowdot[base + n], mv_pad[(size_t)b * Nc_pad + c], g3, norm, lamda, mpos);
+      uint32_t w = bitsR[((size_t)b * NW + (c >> 5)) * Nc_pad + cell];
+      if ((w >> (c & 31)) & 1u) coef -= alpha[(size_t)b * Nc_pad + c];
     }
+    rowcoef[base + n] = coef;
+  }
+  // column list of cell = c: sort by row, then coefficients
+  int cnt = min(colcnt[(size_t)b * Nc_pad + cell], DESC_MAXP);
+  int rr[DESC_MAXP];
+  float dd[DESC_MAXP];
+#pragma unroll
+  for (int n = 0; n < DESC_MAXP; ++n) {
+    rr[n] = n < cnt ? colrow[base + n] : 0x7fffffff;
+    dd[n] = n < cnt ? coldot[base + n] : 0.f;
+  }
+#pragma unroll
+  for (int i = 1; i < DESC_MAXP; ++i)
+#pragma unroll
+    for (int j = DESC_MAXP - 1; j >= 1; --j)
+      if (j >= i && rr[j] < rr[j - 1]) {
+        int t = rr[j]; rr[j] = rr[j - 1]; rr[j - 1] = t;
+        float u = dd[j]; dd[j] = dd[j - 1]; dd[j - 1] = u;
+      }
+  float mv = mv_pad[(size_t)b * Nc_pad + cell], al = alpha[(size_t)b * Nc_pad + cell];
+#pragma unroll
+  for (int n = 0; n < DESC_MAXP; ++n) {
+    float coef = 0.f;
+    int r = -1;
+    if (n < cnt) {
+      r = rr[n];
+      coef = pos_coef(dd[n], mv, g3, norm, lamda, mpos);
+      uint32_t w = bitsR[((size_t)b * NW + (cell >> 5)) * Nc_pad + r];
+      if ((w >> (cell & 31)) & 1u) coef -= al;
+    }
+    colrow[base + n] = r;
+    colcoef[base + n] = coef;
   }
 }
 
-extern "C" int ssp_desc_pos_bwd(const float* D, const float* Dw, const float* wpts, const float* mv_pad,
-                                const float* g3, const float* out4, int B, int Hc, int Wc, int Dch, int cell,
-                                float dist, float lamda, float mpos, float* dD, float* dDw, void* stream) {
-  SSP_REQUIRE(D && Dw && wpts && mv_pad && g3 && out4 && dD && dDw, "ssp_desc_pos_bwd: null pointer");
-  DescGeom g;
-  SSP_REQUIRE(fill_geom(g, B, Hc, Wc, Dch, cell, dist, lamda, mpos, 0.f) == 0 && B <= 65535, "ssp_desc_pos_bwd: bad sizes");
-  cudaStream_t st = (cudaStream_t)stream;
-  desc_pos_bwd_rows_kernel<<<ssp_ceil_div(B * g.Nc, 128), 128, 0, st>>>(
-      D, Dw, reinterpret_cast<const float2*>(wpts), mv_pad, g3, out4, g, dD);
-  SSP_CUDA_CHECK_LAUNCH("desc_pos_bwd_rows_kernel");
-  dim3 grid(ssp_ceil_div(g.Nc, 128), B);
-  desc_pos_bwd_cols_kernel<<<grid, 128, 0, st>>>(D, Dw, reinterpret_cast<const float2*>(wpts), mv_pad, g3, out4, g, dDw);
-  SSP_CUDA_CHECK_LAUNCH("desc_pos_bwd_cols_kernel");
+extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, int* colrow,
+                                 const float* coldot, const uint32_t* bitsR, const float* mv_pad, const float* alpha,
+                                 const float* g3, const float* out8, int B, int Nc_pad, float lamda, float mpos,
+                                 float* rowcoef, float* colcoef, void* stream) {
+  SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && alpha && g3 && out8 && rowcoef && colcoef,
+              "ssp_desc_pos_coef: null pointer");
+  SSP_REQUIRE(B > 0 && B <= 65535 && Nc_pad > 0 && Nc_pad % DESC_PAD == 0, "ssp_desc_pos_coef: bad sizes");
+  dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
+  desc_pos_coef_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rowcol, rowdot, colcnt, colrow, coldot, bitsR, mv_pad, alpha,
+                                                               g3, out8, Nc_pad, lamda, mpos, rowcoef, colcoef);
+  SSP_CUDA_CHECK_LAUNCH("desc_pos_coef_kernel");
   return SSP_OK;
 }
 

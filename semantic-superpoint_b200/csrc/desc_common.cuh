@@ -1,11 +1,11 @@
 // Shared definitions for the dense descriptor hinge loss (reference: utils/utils.py:779-893).
 //
 // Decomposition used by every engine (SIMT fp32 and tcgen05):
-//   loss terms split into the sparse POSITIVE pairs (mask == 1, <= a handful per row; evaluated in
-//   exact fp32 by the pos kernels, weight lamda_d) and the dense NEGATIVE part over all other pairs
-//   (hinge max(dot - margin_neg, 0), evaluated by the GEMM kernel with the positive pairs zeroed).
-//   The GEMM kernel also emits the indicator bit-matrix I[r,c] = (1 - mask) * 1[dot > margin_neg] in two
-//   orientations so that the backward is two pure indicator-GEMMs and never recomputes S.
+//   The GEMM kernel evaluates the negative hinge max(dot - margin_neg, 0) over ALL pairs (no geometry in
+//   its epilogue) and emits the indicator bit-matrix I[r,c] = 1[dot > margin_neg] in two orientations, so
+//   that the backward is two pure indicator-GEMMs and never recomputes S.  The sparse POSITIVE pairs
+//   (mask == 1, <= DESC_MAXP per row) are owned by the pos kernels: exact fp32 dots, weight lamda_d, and the
+//   removal of the negative term the dense part contributed for them (forward sums and backward GEMM).
 //
 // Layouts:
 //   wpts   [B, Nc_pad] float2  warped cell centres (x, y) in pixels; padded rows hold SSP_FAR
@@ -18,6 +18,8 @@
 
 #define SSP_FAR 1.0e30f
 #define DESC_PAD 128
+#define DESC_MAXP 16  // positive pairs per row / column kept in the sparse lists (descriptor_dist <= cell);
+                      // colcnt[B*Nc_pad] counts entries that did not fit (0 unless the warp shrinks by > 3x)
 
 struct DescGeom {
   int B, Hc, Wc, Nc, Nc_pad, Dch;

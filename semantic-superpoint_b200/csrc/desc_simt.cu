@@ -9,7 +9,7 @@
 
 __global__ void __launch_bounds__(256)
 desc_dense_fwd_simt_kernel(const float* __restrict__ D, const float* __restrict__ Dw,
-                           const float2* __restrict__ wpts, const float* __restrict__ mv_pad, DescGeom g,
+                           const float* __restrict__ mv_pad, DescGeom g,
                            double* __restrict__ partials, uint32_t* __restrict__ bitsR,
                            uint32_t* __restrict__ bitsC, float* __restrict__ dbgS) {
   __shared__ float As[SK][ST];
@@ -48,17 +48,12 @@ desc_dense_fwd_simt_kernel(const float* __restrict__ D, const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int r = r0 + ty * 4 + i;
-    float2 w = wpts[(size_t)b * g.Nc_pad + r];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int c = c0 + tx * 4 + j;
-      float neg = 0.f;
-      if (r < g.Nc && c < g.Nc) {
-        float cx, cy;
-        cell_center(c, g.Wc, g.cell, cx, cy);
-        if (!pair_positive(w.x, w.y, cx, cy, g.dist)) neg = fmaxf(acc[i][j] - g.mneg, 0.f);
-        if (dbgS) dbgS[((size_t)b * g.Nc + r) * g.Nc + c] = acc[i][j];
-      }
+      // zero padding gives dot = 0 -> hinge 0 (mneg > 0), so padded rows / columns need no masking
+      float neg = fmaxf(acc[i][j] - g.mneg, 0.f);
+      if (dbgS && r < g.Nc && c < g.Nc) dbgS[((size_t)b * g.Nc + r) * g.Nc + c] = acc[i][j];
       su += neg;
       sw = fmaf(neg, mv_pad[(size_t)b * g.Nc_pad + c], sw);
       pred[ty * 4 + i][tx * 4 + j] = neg > 0.f ? 1 : 0;
@@ -93,20 +88,20 @@ extern "C" int ssp_desc_dense_simt_nblocks(int B, int Nc) {
   return B * t * t;
 }
 
-extern "C" int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* wpts, const float* mv_pad,
-                                       int B, int Hc, int Wc, int Dch, int cell, float dist, float mneg,
-                                       double* partials, uint32_t* bitsR, uint32_t* bitsC, float* dbgS,
-                                       void* stream) {
-  SSP_REQUIRE(D && Dw && wpts && mv_pad && partials, "ssp_desc_dense_fwd_simt: null pointer");
+extern "C" int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* mv_pad, int B, int Hc, int Wc,
+                                       int Dch, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
+                                       float* dbgS, void* stream) {
+  SSP_REQUIRE(D && Dw && mv_pad && partials, "ssp_desc_dense_fwd_simt: null pointer");
+  SSP_REQUIRE(mneg > 0.f, "ssp_desc_dense_fwd_simt: margin_neg must be > 0 (zero padding relies on it)");
   SSP_REQUIRE((bitsR == nullptr) == (bitsC == nullptr), "ssp_desc_dense_fwd_simt: bitsR/bitsC must both be given or both null");
   DescGeom g;
-  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = Dch; g.cell = cell;
-  g.dist = dist; g.lamda = 0.f; g.mpos = 0.f; g.mneg = mneg;
-  SSP_REQUIRE(B > 0 && B <= 65535 && Hc > 0 && Wc > 0 && Dch > 0 && cell > 0, "ssp_desc_dense_fwd_simt: bad sizes");
+  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = Dch; g.cell = 0;
+  g.dist = 0.f; g.lamda = 0.f; g.mpos = 0.f; g.mneg = mneg;
+  SSP_REQUIRE(B > 0 && B <= 65535 && Hc > 0 && Wc > 0 && Dch > 0, "ssp_desc_dense_fwd_simt: bad sizes");
   int t = g.Nc_pad / ST;
   dim3 grid(t, t, B);
   desc_dense_fwd_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      D, Dw, reinterpret_cast<const float2*>(wpts), mv_pad, g, partials, bitsR, bitsC, dbgS);
+      D, Dw, mv_pad, g, partials, bitsR, bitsC, dbgS);
   SSP_CUDA_CHECK_LAUNCH("desc_dense_fwd_simt_kernel");
   return SSP_OK;
 }
@@ -117,8 +112,9 @@ extern "C" int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const fl
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 desc_bits_gemm_simt_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ src,
-                           const float* __restrict__ colscale, const float* __restrict__ rowscale, int Dch,
-                           int Nc, int Nc_pad, float* __restrict__ out) {
+                           const float* __restrict__ colscale, const float* __restrict__ rowscale,
+                           const int* __restrict__ plist, const float* __restrict__ pcoef,
+                           const float* __restrict__ possrc, int Dch, int Nc, int Nc_pad, float* __restrict__ out) {
   __shared__ float sv[256][33];
   __shared__ uint32_t wb[32];
   int b = blockIdx.y, r0 = blockIdx.x * 32, d0 = blockIdx.z * 256;
@@ -158,20 +154,34 @@ desc_bits_gemm_simt_kernel(const uint32_t* __restrict__ bits, const float* __res
   int r = r0 + lane;
   if (r < Nc) {
     float rs = rowscale ? rowscale[(size_t)b * Nc_pad + r] : 1.f;
+    // sparse positive pairs of this row (and removal of their negative term), see desc_pos_coef_kernel
+    int npos = 0;
+    if (plist) {
+      for (int n = 0; n < DESC_MAXP; ++n)
+        if (plist[((size_t)b * Nc_pad + r) * DESC_MAXP + n] >= 0) npos = n + 1;
+    }
     for (int dd = w; dd < 256; dd += 8) {
       int d = d0 + dd;
-      if (d < Dch) out[((size_t)b * Dch + d) * Nc + r] = sv[dd][lane] * rs;
+      if (d >= Dch) continue;
+      float v = sv[dd][lane] * rs;
+      for (int n = 0; n < npos; ++n) {
+        int pc = plist[((size_t)b * Nc_pad + r) * DESC_MAXP + n];
+        if (pc >= 0) v = fmaf(pcoef[((size_t)b * Nc_pad + r) * DESC_MAXP + n], __ldg(possrc + ((size_t)b * Dch + d) * Nc + pc), v);
+      }
+      out[((size_t)b * Dch + d) * Nc + r] = v;
     }
   }
 }
 
 extern "C" int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src, const float* colscale,
-                                       const float* rowscale, int B, int Dch, int Nc, float* out, void* stream) {
+                                       const float* rowscale, const int* plist, const float* pcoef,
+                                       const float* possrc, int B, int Dch, int Nc, float* out, void* stream) {
   SSP_REQUIRE(bits && src && out, "ssp_desc_bits_gemm_simt: null pointer");
+  SSP_REQUIRE(!plist || (pcoef && possrc), "ssp_desc_bits_gemm_simt: plist needs pcoef and possrc");
   SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0, "ssp_desc_bits_gemm_simt: bad sizes");
   int Nc_pad = desc_nc_pad(Nc);
   dim3 grid(Nc_pad / 32, B, ssp_ceil_div(Dch, 256));
-  desc_bits_gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, src, colscale, rowscale, Dch, Nc, Nc_pad, out);
+  desc_bits_gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, src, colscale, rowscale, plist, pcoef, possrc, Dch, Nc, Nc_pad, out);
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_simt_kernel");
   return SSP_OK;
 }

@@ -11,9 +11,9 @@
 //   warp 9      MMA issuer: tcgen05.mma kind::f16 M=128 N=128 K=16 into a double-buffered TMEM
 //               accumulator (2 x 128 columns); tcgen05.commit frees ring slots / publishes tiles
 //   warps 0-7   epilogue: tcgen05.ld 32x32b (one row per thread, 64 columns per warp), hinge,
-//               positive-pair masking on the few warps that can contain one, mask_valid weighting,
-//               running sums, indicator bit-matrix in both orientations.  The pair matrix never
-//               reaches HBM.
+//               mask_valid weighting, running sums, indicator bit-matrix in both orientations.
+//               No geometry here: the sparse positive pairs are corrected by the pos kernels.  The
+//               pair matrix never reaches HBM.
 //
 // Backward kernel = indicator GEMM  out[b, d, r] = rowscale[r] * sum_k bit(r,k) * Bp[b, k, d]:
 //   warps 0-3   expand 64 indicator bits per row into bf16 {0,1} and tcgen05.st them as the A
@@ -45,13 +45,14 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 
-// One 32-column slice of the accumulator row owned by this thread.
-template <bool SLOW, bool BITS>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ mvp, int cbase, float wx,
-                                          float wy, const DescGeom& g, float& su, float& sw, uint32_t& rowword,
-                                          uint32_t& colword, int lane) {
+// One 32-column slice of the accumulator row owned by this thread: negative hinge over every pair (the sparse
+// positive pairs are corrected by the pos kernels), mask_valid weighting, indicator bits in both orientations.
+template <bool BITS>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ mvp, float mneg, float& su,
+                                          float& sw, uint32_t& rowword, uint32_t& colword, int lane) {
   rowword = 0;
   colword = 0;
+  float su1 = 0.f, sw1 = 0.f;  // second accumulator pair: halves the dependent-add chains
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     float4 m4 = __ldg(reinterpret_cast<const float4*>(mvp) + j4);
@@ -59,15 +60,9 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int j = j4 * 4 + jj;
-      float s = __uint_as_float(v[j]);
-      float neg = fmaxf(s - g.mneg, 0.f);
-      if (SLOW) {
-        float cx, cy;
-        cell_center(cbase + j, g.Wc, g.cell, cx, cy);
-        if (pair_positive(wx, wy, cx, cy, g.dist)) neg = 0.f;
-      }
-      su += neg;
-      sw = fmaf(neg, mvv[jj], sw);
+      float neg = fmaxf(__uint_as_float(v[j]) - mneg, 0.f);
+      if (jj & 1) { su1 += neg; sw1 = fmaf(neg, mvv[jj], sw1); }
+      else        { su += neg;  sw = fmaf(neg, mvv[jj], sw); }
       if (BITS) {
         bool p = neg > 0.f;
         rowword |= p ? (1u << j) : 0u;
@@ -76,13 +71,15 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
       }
     }
   }
+  su += su1;
+  sw += sw1;
 }
 
 template <int P, bool BITS>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const float2* __restrict__ wpts, const float* __restrict__ mv_pad, DescGeom g,
+                         const float* __restrict__ mv_pad, DescGeom g,
                          double* __restrict__ partials, uint32_t* __restrict__ bitsR, uint32_t* __restrict__ bitsC,
                          float* __restrict__ dbgS) {
   using Cfg = FwdCfg<P>;
@@ -185,7 +182,6 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     // ------------------------------ epilogue warps 0..7 ------------------------------
     const int q = warp & 3, half = warp >> 2;
     const int row = m0 + q * 32 + lane;  // row inside the padded pair
-    const float2 w = wpts[(size_t)row_base + row];
     const int NW = g.Nc_pad / 32;
     double su_d = 0.0, sw_d = 0.0;
     for (int nt = 0; nt < NT; ++nt) {
@@ -199,16 +195,10 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const int cbase = nt * BN + half * 64 + ch * 32;
         uint32_t v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * 64 + ch * 32, v);
-        // can any row of this warp have a positive pair among these 32 columns? (conservative, y only)
-        int kA = cbase / g.Wc, kB = (cbase + 31) / g.Wc;
-        float ylo = (float)(kA * g.cell + g.cell / 2) - g.dist - 1.f;
-        float yhi = (float)(kB * g.cell + g.cell / 2) + g.dist + 1.f;
-        bool slow = __any_sync(0xffffffffu, w.y >= ylo && w.y <= yhi) && cbase < g.Nc;
         tc::tmem_ld_wait();
         const float* mvp = mv_pad + (size_t)row_base + cbase;
         uint32_t rowword, colword;
-        if (slow) epi_chunk<true, BITS>(v, mvp, cbase, w.x, w.y, g, su, sw, rowword, colword, lane);
-        else epi_chunk<false, BITS>(v, mvp, cbase, w.x, w.y, g, su, sw, rowword, colword, lane);
+        epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, lane);
         if (BITS) {
           bitsR[((size_t)b * NW + cbase / 32) * g.Nc_pad + row] = rowword;
           bitsC[((size_t)b * NW + (m0 + q * 32) / 32) * g.Nc_pad + cbase + lane] = colword;
@@ -261,8 +251,9 @@ template <int P> struct BgCfg {
 template <int P>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale, int Nc, int Nc_pad,
-                         float* __restrict__ out) {
+                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
+                         const int* __restrict__ plist, const float* __restrict__ pcoef,
+                         const float* __restrict__ possrc, int Nc, int Nc_pad, float* __restrict__ out) {
   using Cfg = BgCfg<P>;
   constexpr int NS = Cfg::NS;
   extern __shared__ uint8_t smem_raw[];
@@ -365,14 +356,34 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     tc::fence_after_sync();
     float rs = 1.f;
     if (rowscale && row < Nc) rs = rowscale[(size_t)row_base + row];
+    // sparse positive pairs of this row (and removal of their negative term), see desc_pos_coef_kernel
+    int npos = 0;
+    if (plist && row < Nc) {
+#pragma unroll
+      for (int n = 0; n < DESC_MAXP; ++n)
+        if (plist[((size_t)row_base + row) * DESC_MAXP + n] >= 0) npos = n + 1;
+    }
+    const int nmax = __reduce_max_sync(0xffffffffu, npos);
 #pragma unroll 1
     for (int ch = 0; ch < 8; ++ch) {
       uint32_t v[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, v);
       tc::tmem_ld_wait();
       if (row < Nc) {
+        float val[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) out[((size_t)b * KD + ch * 32 + j) * Nc + row] = __uint_as_float(v[j]) * rs;
+        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]) * rs;
+#pragma unroll 1
+        for (int n = 0; n < nmax; ++n) {
+          int pc = plist[((size_t)row_base + row) * DESC_MAXP + n];
+          if (pc < 0) continue;
+          float pf = pcoef[((size_t)row_base + row) * DESC_MAXP + n];
+          const float* ps = possrc + ((size_t)b * KD + ch * 32) * Nc + pc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[((size_t)b * KD + ch * 32 + j) * Nc + row] = val[j];
       }
     }
   }
@@ -433,19 +444,18 @@ extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) { return B * (desc_nc_pa
 // Ahi/Alo: packed planes of `descriptors`, Bhi/Blo: packed planes of `descriptors_warped`
 // ([B, Nc_pad, 256] bf16).  Alo == Blo == NULL selects single-pass bf16; otherwise bf16x3.
 extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
-                                     const float* wpts, const float* mv_pad, int B, int Hc, int Wc, int cell,
-                                     float dist, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
-                                     float* dbgS, void* stream) {
-  SSP_REQUIRE(Ahi && Bhi && wpts && mv_pad && partials, "ssp_desc_dense_fwd_tc: null pointer");
+                                     const float* mv_pad, int B, int Hc, int Wc, float mneg, double* partials,
+                                     uint32_t* bitsR, uint32_t* bitsC, float* dbgS, void* stream) {
+  SSP_REQUIRE(Ahi && Bhi && mv_pad && partials, "ssp_desc_dense_fwd_tc: null pointer");
   SSP_REQUIRE((Alo == nullptr) == (Blo == nullptr), "ssp_desc_dense_fwd_tc: lo planes must both be given or both null");
   SSP_REQUIRE((bitsR == nullptr) == (bitsC == nullptr), "ssp_desc_dense_fwd_tc: bitsR/bitsC must both be given or both null");
-  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0 && cell > 0, "ssp_desc_dense_fwd_tc: bad sizes");
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_desc_dense_fwd_tc: bad sizes");
   SSP_REQUIRE(mneg > 0.f, "ssp_desc_dense_fwd_tc: margin_neg must be > 0 (zero padding relies on it)");
   SSP_REQUIRE((((uintptr_t)Ahi | (uintptr_t)Bhi | (uintptr_t)Alo | (uintptr_t)Blo | (uintptr_t)mv_pad) & 15) == 0,
               "ssp_desc_dense_fwd_tc: operands must be 16-byte aligned");
   DescGeom g;
-  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = KD; g.cell = cell;
-  g.dist = dist; g.lamda = 0.f; g.mpos = 0.f; g.mneg = mneg;
+  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = KD; g.cell = 0;
+  g.dist = 0.f; g.lamda = 0.f; g.mpos = 0.f; g.mneg = mneg;
   uint64_t rows = (uint64_t)B * g.Nc_pad;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
@@ -455,11 +465,10 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   if ((rc = make_plane_map(&mBl, Blo ? Blo : Bhi, rows, BN))) return rc;
   int grid = ssp_desc_dense_tc_nblocks(B, g.Nc);
   cudaStream_t st = (cudaStream_t)stream;
-  const float2* wp = reinterpret_cast<const float2*>(wpts);
 #define LAUNCH_FWD(PP, BB)                                                                                   \
   do {                                                                                                       \
     if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB>, FwdCfg<PP>::SMEM))) return rc;                      \
-    desc_dense_fwd_tc_kernel<PP, BB><<<grid, FWD_THREADS, FwdCfg<PP>::SMEM, st>>>(mAh, mAl, mBh, mBl, wp, mv_pad, g, \
+    desc_dense_fwd_tc_kernel<PP, BB><<<grid, FWD_THREADS, FwdCfg<PP>::SMEM, st>>>(mAh, mAl, mBh, mBl, mv_pad, g, \
                                                                                    partials, bitsR, bitsC, dbgS);  \
   } while (0)
   if (Alo) { if (bitsR) LAUNCH_FWD(2, true); else LAUNCH_FWD(2, false); }
@@ -471,8 +480,10 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
 
 // out[b, d, r] = rowscale[b, r] * sum_k bit(r, k) * (Bhi + Blo)[b, k, d]      (out is [B, 256, Nc] fp32)
 extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
-                                     int B, int Nc, float* out, void* stream) {
+                                     const int* plist, const float* pcoef, const float* possrc, int B, int Nc,
+                                     float* out, void* stream) {
   SSP_REQUIRE(bits && Bhi && out, "ssp_desc_bits_gemm_tc: null pointer");
+  SSP_REQUIRE(!plist || (pcoef && possrc), "ssp_desc_bits_gemm_tc: plist needs pcoef and possrc");
   SSP_REQUIRE(B > 0 && Nc > 0, "ssp_desc_bits_gemm_tc: bad sizes");
   SSP_REQUIRE((((uintptr_t)Bhi | (uintptr_t)Blo) & 15) == 0, "ssp_desc_bits_gemm_tc: operands must be 16-byte aligned");
   int Nc_pad = desc_nc_pad(Nc);
@@ -485,10 +496,10 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (Blo) {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
-    desc_bits_gemm_tc_kernel<2><<<grid, BG_THREADS, BgCfg<2>::SMEM, st>>>(mh, ml, bits, rowscale, Nc, Nc_pad, out);
+    desc_bits_gemm_tc_kernel<2><<<grid, BG_THREADS, BgCfg<2>::SMEM, st>>>(mh, ml, bits, rowscale, plist, pcoef, possrc, Nc, Nc_pad, out);
   } else {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
-    desc_bits_gemm_tc_kernel<1><<<grid, BG_THREADS, BgCfg<1>::SMEM, st>>>(mh, ml, bits, rowscale, Nc, Nc_pad, out);
+    desc_bits_gemm_tc_kernel<1><<<grid, BG_THREADS, BgCfg<1>::SMEM, st>>>(mh, ml, bits, rowscale, plist, pcoef, possrc, Nc, Nc_pad, out);
   }
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;

@@ -13,6 +13,7 @@ from ._lib import call, f32c, ptr, stream_of
 
 _ENGINES = ("bf16x3", "bf16", "fp32")
 _engine = "bf16x3"
+CHECK_LIST_OVERFLOW = False  # tests turn this on (costs a host sync per call)
 
 
 def set_descriptor_engine(name):
@@ -107,10 +108,16 @@ class DescriptorLossFn(torch.autograd.Function):
         mv_pad = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
         call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), st)
 
+        # sparse positive pairs: exact dots, partial sums, pair lists for the backward
+        maxp = lib.ssp_desc_maxp()
         npos = lib.ssp_desc_pos_nblocks(B, Nc)
-        pos_part = torch.empty((npos, 2), dtype=torch.float64, device=dev)
-        call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos,
-             ptr(pos_part), st)
+        pos_part = torch.empty((npos, 4), dtype=torch.float64, device=dev)
+        lists_i = torch.empty((3, B, Ncp, maxp), dtype=torch.int32, device=dev)   # rowcol, colrow, (colcnt in [2,:,:,0])
+        lists_f = torch.empty((2, B, Ncp, maxp), dtype=torch.float32, device=dev)  # rowdot, coldot
+        rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2].view(-1)[: B * Ncp + 1]
+        rowdot, coldot = lists_f[0], lists_f[1]
+        call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos, mneg,
+             ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
 
         bitsR = bitsC = None
         if need_grad:
@@ -120,8 +127,8 @@ class DescriptorLossFn(torch.autograd.Function):
         if engine == "fp32":
             nneg = lib.ssp_desc_dense_simt_nblocks(B, Nc)
             neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
-            call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist,
-                 mneg, ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+            call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
+                 ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
         else:
             split = engine == "bf16x3"
             Ahi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
@@ -132,10 +139,12 @@ class DescriptorLossFn(torch.autograd.Function):
             call("ssp_desc_pack", ptr(Dwc), None, B, Dch, Nc, ptr(Bhi), ptr(Blo), st)
             nneg = lib.ssp_desc_dense_tc_nblocks(B, Nc)
             neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
-            call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc,
-                 cell, dist, mneg, ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+            call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
+                 ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             planes = (Ahi, Alo)
 
+        if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
+            raise RuntimeError("descriptor_loss: %d positive pairs overflowed the per-column lists" % int(colcnt[B * Ncp]))
         out8 = torch.empty((8,), dtype=torch.float32, device=dev)
         call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_pad), B, Hc, Wc, ptr(out8), st)
         if dist_group is not None:
@@ -143,7 +152,7 @@ class DescriptorLossFn(torch.autograd.Function):
             globalize_descriptor(out8, B, Hc, Wc, dist_group)
 
         if need_grad:
-            ctx.save_for_backward(Dc, Dwc, wpts, mv_pad, out8, bitsR, bitsC,
+            ctx.save_for_backward(Dc, Dwc, mv_pad, out8, bitsR, bitsC, lists_i, lists_f,
                                   *( [planes[0]] + ([planes[1]] if planes[1] is not None else []) if planes else []))
         ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
         ctx.mark_non_differentiable(wpts)
@@ -153,7 +162,7 @@ class DescriptorLossFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g_loss, g_pos, g_neg, _g_wpts):
         saved = ctx.saved_tensors
-        Dc, Dwc, wpts, mv_pad, out8, bitsR, bitsC = saved[:7]
+        Dc, Dwc, mv_pad, out8, bitsR, bitsC, lists_i, lists_f = saved[:8]
         B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, split = ctx.meta
         dev = Dc.device
         Nc = Hc * Wc
@@ -162,24 +171,33 @@ class DescriptorLossFn(torch.autograd.Function):
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g3 = torch.stack([(g if g is not None else zero).reshape(()).to(torch.float32) for g in (g_loss, g_pos, g_neg)])
         g3 = g3.contiguous()
+        # alpha[b,c] = (g_loss * mv[c] + g_neg) / norm: coefficient of the negative hinge of column c
         alpha = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
         call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), st)
+        rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2]
+        rowdot, coldot = lists_f[0], lists_f[1]
+        coefs = torch.empty((2,) + tuple(rowdot.shape), dtype=torch.float32, device=dev)
+        call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR), ptr(mv_pad),
+             ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(coefs[1]), st)
         dD = torch.empty_like(Dc)
         dDw = torch.empty_like(Dwc)
+        # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
+        # dDw[b,:,c] = alpha[c] sum_r I[r,c] D[b,:,r]  + sum_n colcoef[c,n] D [b,:,colrow[c,n]]
         if engine == "fp32":
-            # dD[b,:,r] = sum_c I[r,c] * alpha[c] * Dw[b,:,c];   dDw[b,:,c] = alpha[c] * sum_r I[r,c] * D[b,:,r]
-            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, B, Dch, Nc, ptr(dD), st)
-            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), B, Dch, Nc, ptr(dDw), st)
+            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc),
+                 B, Dch, Nc, ptr(dD), st)
+            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc),
+                 B, Dch, Nc, ptr(dDw), st)
         else:
-            Ahi = saved[7]
-            Alo = saved[8] if split else None
+            Ahi = saved[8]
+            Alo = saved[9] if split else None
             Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Slo = torch.empty_like(Shi) if split else None
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
-            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, B, Nc, ptr(dD), st)
-            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), B, Nc, ptr(dDw), st)
-        call("ssp_desc_pos_bwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), ptr(g3), ptr(out8), B, Hc, Wc, Dch, cell,
-             dist, lamda, mpos, ptr(dD), ptr(dDw), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc), B, Nc,
+                 ptr(dD), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc), B,
+                 Nc, ptr(dDw), st)
         return dD, dDw, None, None, None, None, None, None, None, None
 
 

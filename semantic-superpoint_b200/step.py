@@ -46,3 +46,47 @@ def adaptation_step(semi, inv_homographies, mask_2D, conf_thresh=0.015, nms_dist
             p = p[:top_k, :]
         out.append(p)
     return out
+
+
+class GraphedLossStep(object):
+    """loss_step forward + backward captured once into a CUDA graph and replayed (the step is a chain of ~25 short
+    kernels; replay removes the per-launch host cost).  Inputs are copied into static buffers; outputs (loss
+    scalars and the four gradients) live in static buffers that the next replay overwrites."""
+
+    IN_KEYS = ("semi", "semi_warp", "desc", "desc_warp", "labels_2D", "warped_labels", "mask_2D", "mask_warp_2D", "mat_H")
+
+    def __init__(self, example, **kw):
+        self.kw = kw
+        self.static = {k: example[k].detach().clone() for k in self.IN_KEYS}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+
+    def _run(self):
+        s = self.static
+        leaves = [s[k].detach().requires_grad_(True) for k in ("semi", "semi_warp", "desc", "desc_warp")]
+        out = loss_step(leaves[0], leaves[1], leaves[2], leaves[3], s["labels_2D"], s["warped_labels"], s["mask_2D"],
+                        s["mask_warp_2D"], s["mat_H"], **self.kw)
+        out["loss"].backward()
+        res = {k: v.detach() for k, v in out.items()}
+        res["grads"] = [l.grad for l in leaves]
+        return res
+
+    def load(self, inputs, non_blocking=True):
+        for k in self.IN_KEYS:
+            self.static[k].copy_(inputs[k], non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, inputs):
+        self.load(inputs)
+        return self.replay()

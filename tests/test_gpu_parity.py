@@ -14,6 +14,7 @@ from oracle import ssp_oracle as O
 from ssp_b200 import synth
 
 pytestmark = pytest.mark.gpu
+S.losses.CHECK_LIST_OVERFLOW = True
 TOL = 1e-4
 BF16_LOSS_RTOL = 3e-3   # single-pass bf16 inputs: loss scalars
 BF16_GRAD_COS = 0.995   # single-pass bf16 inputs: gradient direction
@@ -302,7 +303,7 @@ def test_descriptor_engines_agree_b32():
     for e in ("bf16x3", "bf16"):
         rt = TOL if e == "bf16x3" else BF16_LOSS_RTOL
         for i in (0, 2, 3):
-            close(res[e][i], res["fp32"][i].cpu().numpy(), rtol=rt)
+            close(res[e][i], res["fp32"][i].detach().cpu().numpy(), rtol=rt)
         for i in (4, 5):
             a, b = res[e][i].cpu().numpy(), res["fp32"][i].cpu().numpy()
             cos = (a * b).sum() / np.sqrt((a * a).sum() * (b * b).sum())
@@ -327,9 +328,11 @@ def test_descriptor_kitti_shape():
     Hs, _ = homographies(1, 22)
     mv = (synth.uniform((1, 1, 47, 155), 113) < 0.9).astype(np.float32)
     ref = O.descriptor_loss(D, Dw, Hs, mv)
+    # coordinates reach 1240 px (fp32 ulp 1.2e-4): pairs within 1e-3 px of the distance threshold may flip
+    slack = O.descriptor_boundary_slack(D, Dw, Hs, mv, eps=1e-3)
     for e in ("bf16x3", "fp32"):
         loss, _, pos, neg = S.descriptor_loss(cu(D), cu(Dw), cu(Hs), mask_valid=cu(mv), device=DEV, engine=e)
-        close(loss, ref[0]); close(pos, ref[2]); close(neg, ref[3])
+        close(loss, ref[0], atol=slack + 1e-9); close(pos, ref[2], atol=slack + 1e-9); close(neg, ref[3], atol=slack + 1e-9)
 
 
 def test_descriptor_other_channel_count():
