@@ -1,0 +1,19 @@
+import json, sys
+for f in sys.argv[1:]:
+    try:
+        d=json.load(open(f))
+    except Exception as e:
+        print(f, 'ERR', e); 
+        try: print(open(f.replace('.json','.err')).read()[-1500:])
+        except Exception: pass
+        continue
+    print('==',f, 'value=%.1f'%d['value'], 'ms/step=%.3f'%d['ms_per_step'], 'e2e', d.get('e2e',{}).get('value'), 'launches', d.get('gpu_launches'), d.get('config',{}).get('cuda_graph'))
+    if 'roofline' in d: print('  roofline', {k:d['roofline'][k] for k in ('kernel','achieved','peak','frac','us_per_launch')})
+    if 'kernel_shares' in d:
+        tot=0
+        for k,v in d['kernel_shares'].items():
+            print('   %-28s calls/step %.1f us/call %8.1f share %.3f'%(k,v['calls_per_step'],v['us_per_call'],v['share'])); tot+=v['calls_per_step']*v['us_per_call']
+        print('   sum of kernel time per step: %.1f us'%tot)
+    if 'clocks' in d: print('  clocks', d['clocks'])
+    if 'homography_adaptation' in d: print('  adapt', d['homography_adaptation']['value'])
+    if 'cpu_baseline' in d: print('  cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])

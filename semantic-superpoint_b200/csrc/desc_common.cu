@@ -154,7 +154,8 @@ desc_pos_fwd_kernel(const float* __restrict__ D, const float* __restrict__ Dw, c
   }
 }
 
-extern "C" int ssp_desc_pos_nblocks(int B, int Nc) { return B * ssp_ceil_div(Nc, POS_ROWS); }
+// the grid covers all Nc_pad rows so that every list row is initialised (padded rows get empty lists)
+extern "C" int ssp_desc_pos_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / POS_ROWS); }
 extern "C" int ssp_desc_maxp(void) { return DESC_MAXP; }
 
 static int fill_geom(DescGeom& g, int B, int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos,
@@ -179,7 +180,7 @@ extern "C" int ssp_desc_pos_fwd(const float* D, const float* Dw, const float* wp
               dist, cell, DESC_MAXP);
   cudaStream_t st = (cudaStream_t)stream;
   SSP_CUDA_CALL(cudaMemsetAsync(colcnt, 0, ((size_t)B * g.Nc_pad + 1) * sizeof(int), st));
-  dim3 grid(ssp_ceil_div(g.Nc, POS_ROWS), B);
+  dim3 grid(g.Nc_pad / POS_ROWS, B);
   desc_pos_fwd_kernel<<<grid, POS_ROWS * POS_DG, 0, st>>>(D, Dw, reinterpret_cast<const float2*>(wpts), mv_pad, g,
                                                            partials, rowcol, rowdot, colcnt, colrow, coldot);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_fwd_kernel");

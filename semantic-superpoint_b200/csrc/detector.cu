@@ -123,6 +123,227 @@ extern "C" int ssp_cell_mask(const float* mask2d, int B, int H, int W, float* ou
 
 // ----------------------------------------------------------------------------------------------
 // detector loss: sum_cells mask * sum_c BCE(softmax(semi)_c, target_c) / (sum mask + 1e-5)
+// Block = 32 cells x 4 channel groups (warp g owns channels 16g..16g+15, warp 3 also the dustbin 64), i.e.
+// 4 threads per cell: 4x the memory-level parallelism and a quarter of the registers of a thread-per-cell
+// layout.  In the fused-2D variant warp g reads pixel rows 2g, 2g+1 of every 8x8 cell (channel = dy*8+dx).
+// ----------------------------------------------------------------------------------------------
+#define DET_CELLS 32
+#define DET_GROUPS 4
+#define DET_CPG 16  // channels per group
+
+__device__ __forceinline__ float bce_term(float p, float t) {
+  // nn.BCELoss: log terms clamped at -100
+  float lp = fmaxf(logf(p), -100.f);
+  float lq = fmaxf(logf(1.f - p), -100.f);
+  return -(t * lp + (1.f - t) * lq);
+}
+
+struct DetShared {
+  float red[DET_GROUPS][DET_CELLS];
+};
+
+// combine one value per channel group into the per-cell total (fixed order 0..3), all threads get it
+template <typename Op>
+__device__ __forceinline__ float det_combine(DetShared& sh, float v, int lane, int grp, Op op) {
+  __syncthreads();
+  sh.red[grp][lane] = v;
+  __syncthreads();
+  return op(op(sh.red[0][lane], sh.red[1][lane]), op(sh.red[2][lane], sh.red[3][lane]));
+}
+
+// loads this thread's 16 (+1) logits, returns softmax probabilities p[0..15], pd = dustbin probability (grp 3)
+__device__ __forceinline__ void det_softmax(DetShared& sh, const float* __restrict__ semi_cell, size_t Nc, bool valid,
+                                            int lane, int grp, float (&p)[DET_CPG], float& pd) {
+  float m = -INFINITY;
+  pd = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) {
+    p[c] = valid ? __ldg(semi_cell + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
+    m = fmaxf(m, p[c]);
+  }
+  if (grp == 3) {
+    pd = valid ? __ldg(semi_cell + (size_t)64 * Nc) : 0.f;
+    m = fmaxf(m, pd);
+  }
+  m = det_combine(sh, m, lane, grp, [](float a, float b) { return fmaxf(a, b); });
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) {
+    p[c] = expf(p[c] - m);
+    s += p[c];
+  }
+  if (grp == 3) {
+    pd = expf(pd - m);
+    s += pd;
+  }
+  s = det_combine(sh, s, lane, grp, [](float a, float b) { return a + b; });
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) p[c] = p[c] / s;
+  pd = pd / s;
+}
+
+// target / mask of this thread's channels.  FUSED2D: built from the 2-D maps with the reference's dustbin rule.
+template <int FUSED2D>
+__device__ __forceinline__ void det_target(DetShared& sh, const float* __restrict__ target, const float* __restrict__ mask,
+                                           int b, int ij, int cell, int Hc, int Wc, bool valid, int lane, int grp,
+                                           float (&t)[DET_CPG], float& td, float& mk) {
+  int Nc = Hc * Wc;
+  td = 0.f;
+  if (FUSED2D) {
+    int H = Hc * CELL, W = Wc * CELL;
+    int y0 = (ij / Wc) * CELL + 2 * grp, x0 = (ij % Wc) * CELL;
+    float mp = 1.f, ls = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      float4 a = make_float4(0, 0, 0, 0), c4 = a, ma = make_float4(1, 1, 1, 1), mb = ma;
+      if (valid) {
+        const float4* r = reinterpret_cast<const float4*>(target + ((size_t)b * H + y0 + dy) * W + x0);
+        const float4* q = reinterpret_cast<const float4*>(mask + ((size_t)b * H + y0 + dy) * W + x0);
+        a = __ldg(r); c4 = __ldg(r + 1); ma = __ldg(q); mb = __ldg(q + 1);
+      }
+      t[dy * 8 + 0] = a.x; t[dy * 8 + 1] = a.y; t[dy * 8 + 2] = a.z; t[dy * 8 + 3] = a.w;
+      t[dy * 8 + 4] = c4.x; t[dy * 8 + 5] = c4.y; t[dy * 8 + 6] = c4.z; t[dy * 8 + 7] = c4.w;
+      mp *= ma.x * ma.y * ma.z * ma.w * mb.x * mb.y * mb.z * mb.w;
+    }
+#pragma unroll
+    for (int c = 0; c < DET_CPG; ++c) ls += t[c];
+    mk = det_combine(sh, mp, lane, grp, [](float a, float b) { return a * b; });
+    float s = det_combine(sh, ls, lane, grp, [](float a, float b) { return a + b; });
+    // dustbin: d = 1 - sum; d < 1 -> 0; all 65 channels divided by their sum   [utils/utils.py:431-439]
+    float dust = 1.f - s;
+    if (dust < 1.f) dust = 0.f;
+    float dn = s + dust;
+#pragma unroll
+    for (int c = 0; c < DET_CPG; ++c) t[c] = t[c] / dn;
+    td = dust / dn;
+  } else {
+    mk = valid ? __ldg(mask + cell) : 0.f;
+    const float* tp = target + (size_t)b * NCH * Nc + ij;
+#pragma unroll
+    for (int c = 0; c < DET_CPG; ++c) t[c] = valid ? __ldg(tp + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
+    if (grp == 3) td = valid ? __ldg(tp + (size_t)64 * Nc) : 0.f;
+  }
+}
+
+// FUSED2D = 0: target [B,65,Hc,Wc] and mask [B,Hc,Wc] are given (reference call signature).
+// FUSED2D = 1: target/mask are built on the fly from labels_2D / mask_2D [B,1,H,W].
+template <int FUSED2D>
+__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
+detector_loss_fwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
+                         const float* __restrict__ mask, int B, int Hc, int Wc, double* __restrict__ partials,
+                         unsigned int* __restrict__ counter, float* __restrict__ out) {
+  __shared__ DetShared sh;
+  int Nc = Hc * Wc;
+  int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  int cell = blockIdx.x * DET_CELLS + lane;
+  bool valid = cell < B * Nc;
+  int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
+  float p[DET_CPG], t[DET_CPG], pd, td, mk;
+  det_softmax(sh, semi + (size_t)b * NCH * Nc + ij, Nc, valid, lane, grp, p, pd);
+  det_target<FUSED2D>(sh, target, mask, b, ij, cell, Hc, Wc, valid, lane, grp, t, td, mk);
+  float bce = 0.f;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) bce += bce_term(p[c], t[c]);
+  if (grp == 3) bce += bce_term(pd, td);
+  bce = det_combine(sh, bce, lane, grp, [](float a, float b) { return a + b; });
+  double acc[2] = {0.0, 0.0};
+  if (valid && grp == 0) {
+    acc[0] = (double)(bce * mk);
+    acc[1] = (double)mk;
+  }
+  double tot[2];
+  if (block_reduce_publish<2>(acc, partials, counter, tot)) {
+    float num = (float)tot[0];
+    float den = (float)tot[1] + 1e-5f;
+    out[0] = num / den;  // loss
+    out[1] = num;
+    out[2] = den;
+    *counter = 0;
+  }
+}
+
+// d semi = gout * mask/den * softmax_bwd( (p - t) / max(p (1-p), 1e-12) )
+template <int FUSED2D>
+__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
+detector_loss_bwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
+                         const float* __restrict__ mask, int B, int Hc, int Wc, const float* __restrict__ fwd_out,
+                         const float* __restrict__ gout, float* __restrict__ dsemi) {
+  __shared__ DetShared sh;
+  int Nc = Hc * Wc;
+  int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  int cell = blockIdx.x * DET_CELLS + lane;
+  bool valid = cell < B * Nc;
+  int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
+  float p[DET_CPG], t[DET_CPG], pd, td, mk;
+  det_softmax(sh, semi + (size_t)b * NCH * Nc + ij, Nc, valid, lane, grp, p, pd);
+  det_target<FUSED2D>(sh, target, mask, b, ij, cell, Hc, Wc, valid, lane, grp, t, td, mk);
+  float scale = __ldg(gout) * mk / __ldg(fwd_out + 2);
+  float dot = 0.f, dpd = 0.f;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) {
+    float dp = scale * (p[c] - t[c]) / fmaxf((1.f - p[c]) * p[c], 1e-12f);
+    t[c] = dp;
+    dot += p[c] * dp;
+  }
+  if (grp == 3) {
+    dpd = scale * (pd - td) / fmaxf((1.f - pd) * pd, 1e-12f);
+    dot += pd * dpd;
+  }
+  dot = det_combine(sh, dot, lane, grp, [](float a, float b) { return a + b; });
+  if (!valid) return;
+  float* o = dsemi + (size_t)b * NCH * Nc + ij;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) o[(size_t)(grp * DET_CPG + c) * Nc] = p[c] * (t[c] - dot);
+  if (grp == 3) o[(size_t)64 * Nc] = pd * (dpd - dot);
+}
+
+extern "C" size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc) {
+  size_t nblk = (size_t)ssp_ceil_div(B * Hc * Wc, DET_CELLS);
+  return 16 + nblk * 2 * sizeof(double);
+}
+
+extern "C" int ssp_detector_loss_fwd(const float* semi, const float* target, const float* mask, int B, int Hc,
+                                     int Wc, int fused2d, float* out3, void* ws, size_t ws_bytes, void* stream) {
+  SSP_REQUIRE(semi && target && mask && out3 && ws, "ssp_detector_loss_fwd: null pointer");
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_fwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
+  SSP_REQUIRE(ws_bytes >= ssp_detector_loss_ws_bytes(B, Hc, Wc), "ssp_detector_loss_fwd: workspace too small");
+  SSP_REQUIRE(((uintptr_t)ws & 15) == 0, "ssp_detector_loss_fwd: workspace must be 16-byte aligned");
+  if (fused2d)
+    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
+                "ssp_detector_loss_fwd: 2-D label/mask pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* counter = (unsigned int*)ws;
+  double* partials = (double*)((char*)ws + 16);
+  SSP_CUDA_CALL(cudaMemsetAsync(counter, 0, 16, st));
+  int nblk = ssp_ceil_div(B * Hc * Wc, DET_CELLS);
+  if (fused2d)
+    detector_loss_fwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
+  else
+    detector_loss_fwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_fwd_kernel");
+  return SSP_OK;
+}
+
+extern "C" int ssp_detector_loss_bwd(const float* semi, const float* target, const float* mask, int B, int Hc,
+                                     int Wc, int fused2d, const float* fwd_out3, const float* gout, float* dsemi,
+                                     void* stream) {
+  SSP_REQUIRE(semi && target && mask && fwd_out3 && gout && dsemi, "ssp_detector_loss_bwd: null pointer");
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_bwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
+  if (fused2d)
+    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
+                "ssp_detector_loss_bwd: 2-D label/mask pointers must be 16-byte aligned");
+  int nblk = ssp_ceil_div(B * Hc * Wc, DET_CELLS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fused2d)
+    detector_loss_bwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
+  else
+    detector_loss_bwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_bwd_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// flattenDetection: softmax(65) -> drop dustbin -> pixel-shuffle(8)
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void softmax65(const float* __restrict__ semi_cell, size_t Nc, float (&p)[NCH]) {
   float m = -INFINITY;
@@ -141,152 +362,6 @@ __device__ __forceinline__ void softmax65(const float* __restrict__ semi_cell, s
   for (int c = 0; c < NCH; ++c) p[c] = p[c] / s;
 }
 
-__device__ __forceinline__ float bce_term(float p, float t) {
-  // nn.BCELoss: log terms clamped at -100
-  float lp = fmaxf(logf(p), -100.f);
-  float lq = fmaxf(logf(1.f - p), -100.f);
-  return -(t * lp + (1.f - t) * lq);
-}
-
-// FUSED2D = 0: target [B,65,Hc,Wc] and mask [B,Hc,Wc] are given (reference call signature).
-// FUSED2D = 1: target/mask are built on the fly from labels_2D / mask_2D [B,1,H,W].
-template <int FUSED2D>
-__global__ void __launch_bounds__(128)
-detector_loss_fwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
-                         const float* __restrict__ mask, int B, int Hc, int Wc, double* __restrict__ partials,
-                         unsigned int* __restrict__ counter, float* __restrict__ out) {
-  int Nc = Hc * Wc;
-  int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc[2] = {0.0, 0.0};
-  if (cell < B * Nc) {
-    int b = cell / Nc, ij = cell % Nc;
-    float p[NCH];
-    softmax65(semi + (size_t)b * NCH * Nc + ij, Nc, p);
-    float mk, bce = 0.f;
-    if (FUSED2D) {
-      int H = Hc * CELL, W = Wc * CELL;
-      float v[64], dust;
-      load_cell(mask + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
-      mk = v[0];
-#pragma unroll
-      for (int c = 1; c < 64; ++c) mk *= v[c];
-      load_cell(target + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
-      dustbin_norm(v, dust);
-#pragma unroll
-      for (int c = 0; c < 64; ++c) bce += bce_term(p[c], v[c]);
-      bce += bce_term(p[64], dust);
-    } else {
-      mk = __ldg(mask + cell);
-      const float* t = target + (size_t)b * NCH * Nc + ij;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) bce += bce_term(p[c], __ldg(t + (size_t)c * Nc));
-    }
-    acc[0] = (double)(bce * mk);
-    acc[1] = (double)mk;
-  }
-  double tot[2];
-  if (block_reduce_publish<2>(acc, partials, counter, tot)) {
-    float num = (float)tot[0];
-    float den = (float)tot[1] + 1e-5f;
-    out[0] = num / den;  // loss
-    out[1] = num;
-    out[2] = den;
-    *counter = 0;
-  }
-}
-
-// d semi = gout * mask/den * softmax_bwd( (p - t) / max(p (1-p), 1e-12) )
-template <int FUSED2D>
-__global__ void __launch_bounds__(128)
-detector_loss_bwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
-                         const float* __restrict__ mask, int B, int Hc, int Wc, const float* __restrict__ fwd_out,
-                         const float* __restrict__ gout, float* __restrict__ dsemi) {
-  int Nc = Hc * Wc;
-  int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= B * Nc) return;
-  int b = cell / Nc, ij = cell % Nc;
-  float p[NCH], t[NCH];
-  softmax65(semi + (size_t)b * NCH * Nc + ij, Nc, p);
-  float mk;
-  if (FUSED2D) {
-    int H = Hc * CELL, W = Wc * CELL;
-    float v[64], dust;
-    load_cell(mask + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
-    mk = v[0];
-#pragma unroll
-    for (int c = 1; c < 64; ++c) mk *= v[c];
-    load_cell(target + (size_t)b * H * W, W, (ij / Wc) * CELL, (ij % Wc) * CELL, v);
-    dustbin_norm(v, dust);
-#pragma unroll
-    for (int c = 0; c < 64; ++c) t[c] = v[c];
-    t[64] = dust;
-  } else {
-    mk = __ldg(mask + cell);
-    const float* tp = target + (size_t)b * NCH * Nc + ij;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) t[c] = __ldg(tp + (size_t)c * Nc);
-  }
-  float scale = __ldg(gout) * mk / __ldg(fwd_out + 2);
-  float dot = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    float dp = scale * (p[c] - t[c]) / fmaxf((1.f - p[c]) * p[c], 1e-12f);
-    t[c] = dp;
-    dot += p[c] * dp;
-  }
-  float* o = dsemi + (size_t)b * NCH * Nc + ij;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) o[(size_t)c * Nc] = p[c] * (t[c] - dot);
-}
-
-extern "C" size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc) {
-  size_t nblk = (size_t)ssp_ceil_div(B * Hc * Wc, 128);
-  return 16 + nblk * 2 * sizeof(double);
-}
-
-extern "C" int ssp_detector_loss_fwd(const float* semi, const float* target, const float* mask, int B, int Hc,
-                                     int Wc, int fused2d, float* out3, void* ws, size_t ws_bytes, void* stream) {
-  SSP_REQUIRE(semi && target && mask && out3 && ws, "ssp_detector_loss_fwd: null pointer");
-  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_fwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
-  SSP_REQUIRE(ws_bytes >= ssp_detector_loss_ws_bytes(B, Hc, Wc), "ssp_detector_loss_fwd: workspace too small");
-  SSP_REQUIRE(((uintptr_t)ws & 15) == 0, "ssp_detector_loss_fwd: workspace must be 16-byte aligned");
-  if (fused2d)
-    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
-                "ssp_detector_loss_fwd: 2-D label/mask pointers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned int* counter = (unsigned int*)ws;
-  double* partials = (double*)((char*)ws + 16);
-  SSP_CUDA_CALL(cudaMemsetAsync(counter, 0, 16, st));
-  int nblk = ssp_ceil_div(B * Hc * Wc, 128);
-  if (fused2d)
-    detector_loss_fwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
-  else
-    detector_loss_fwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
-  SSP_CUDA_CHECK_LAUNCH("detector_loss_fwd_kernel");
-  return SSP_OK;
-}
-
-extern "C" int ssp_detector_loss_bwd(const float* semi, const float* target, const float* mask, int B, int Hc,
-                                     int Wc, int fused2d, const float* fwd_out3, const float* gout, float* dsemi,
-                                     void* stream) {
-  SSP_REQUIRE(semi && target && mask && fwd_out3 && gout && dsemi, "ssp_detector_loss_bwd: null pointer");
-  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_bwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
-  if (fused2d)
-    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
-                "ssp_detector_loss_bwd: 2-D label/mask pointers must be 16-byte aligned");
-  int nblk = ssp_ceil_div(B * Hc * Wc, 128);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (fused2d)
-    detector_loss_bwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
-  else
-    detector_loss_bwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
-  SSP_CUDA_CHECK_LAUNCH("detector_loss_bwd_kernel");
-  return SSP_OK;
-}
-
-// ----------------------------------------------------------------------------------------------
-// flattenDetection: softmax(65) -> drop dustbin -> pixel-shuffle(8)
-// ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 flatten_detection_kernel(const float* __restrict__ semi, int N, int Hc, int Wc, float* __restrict__ heat) {
   int Nc = Hc * Wc;
