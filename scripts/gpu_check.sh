@@ -8,9 +8,9 @@ run() { # name, timeout, pytest args...
   timeout $to python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider "$@" > gpurun_out/$name.log 2>&1
   echo "== $name exit=$? $(tail -1 gpurun_out/$name.log)"
 }
-run simple 900 -k "not descriptor and not loss_step"
-run desc_fp32 600 -k "descriptor and fp32 or other_channel"
-run desc_bf16x3 600 -k "descriptor and bf16x3"
-run desc_bf16 600 -k "descriptor and bf16 and not bf16x3"
-run desc_rest 900 -k "engines_agree or kitti or loss_step"
+run desc_bf16x3 300 -k "descriptor and bf16x3"
+run desc_bf16 300 -k "descriptor and bf16 and not bf16x3"
+run desc_fp32 300 -k "descriptor and fp32 or other_channel"
+run desc_rest 600 -k "engines_agree or kitti or loss_step"
+run simple 600 -k "not descriptor and not loss_step"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "== smoke exit=$? $(tail -1 gpurun_out/smoke.log)"

@@ -99,8 +99,14 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = g.Nc_pad / BM, NT = g.Nc_pad / BN;
-  const int b = blockIdx.x / MT, m0 = (blockIdx.x % MT) * BM;
+  // Clusters of 2 CTAs own two row tiles of the same pair and share every B chunk: each CTA fetches half of the
+  // chunk and TMA-multicasts it into both shared memories (halves the L2 -> SM traffic that bounds this kernel).
+  const int MTE = (MT + 1) & ~1;  // row tiles per pair rounded up to the cluster size
+  const int b = blockIdx.x / MTE, mt = blockIdx.x % MTE;
+  const bool tile_valid = mt < MT;  // the odd tile out still takes part in the B multicast, its results are dropped
+  const int m0 = tile_valid ? mt * BM : 0;
   const int row_base = b * g.Nc_pad;  // first packed row of this pair
+  const uint32_t cta_rank = tc::cluster_ctarank();
 
   if (warp == 8 && lane == 0) {
     tc::prefetch_tmap(&tmA_hi);
@@ -110,7 +116,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 9) {
     if (lane == 0) {
       tc::mbar_init(a_full, 1);
-      for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
+      for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 2); }  // 2 = both CTAs' MMAs
       for (int s = 0; s < 2; ++s) { tc::mbar_init(t_full + s, 1); tc::mbar_init(t_empty + s, 8); }
       tc::fence_barrier_init();
     }
@@ -118,7 +124,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     tc::tmem_alloc(tmem_ptr, 256);
   }
   tc::fence_before_sync();
-  __syncthreads();
+  tc::cluster_sync_all();  // barriers of both CTAs are live before any remote arrive / multicast write
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -135,9 +141,11 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           for (int p = 0; p < P; ++p, ++it) {
             int s = it % NSTAGE;
             uint32_t ph = (it / NSTAGE) & 1;
-            tc::mbar_wait(b_empty + s, ph ^ 1);
+            tc::mbar_wait(b_empty + s, ph ^ 1);  // slot s is free in BOTH CTAs
             tc::mbar_expect_tx(b_full + s, CHUNK_BYTES);
-            tc::tma_load_2d(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * CHUNK_BYTES, kc * KC, row_base + nt * BN);
+            // my half (64 of the 128 cells) of the chunk, written into both CTAs' slot s
+            tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * CHUNK_BYTES + cta_rank * (CHUNK_BYTES / 2),
+                               kc * KC, row_base + nt * BN + cta_rank * (BN / 2), (uint16_t)0x3);
           }
     }
     __syncwarp();
@@ -172,7 +180,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
                 first = 0;
               }
             }
-            tc::mma_commit(b_empty + s);  // slot reusable once these MMAs have read it
+            tc::mma_commit_mc(b_empty + s, (uint16_t)0x3);  // tell both producers: this CTA is done with slot s
           }
         tc::mma_commit(t_full + as);  // accumulator tile complete
       }
@@ -199,11 +207,11 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const float* mvp = mv_pad + (size_t)row_base + cbase;
         uint32_t rowword, colword;
         epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, lane);
-        if (BITS) {
+        if (BITS && tile_valid) {
           bitsR[((size_t)b * NW + cbase / 32) * g.Nc_pad + row] = rowword;
           bitsC[((size_t)b * NW + (m0 + q * 32) / 32) * g.Nc_pad + cbase + lane] = colword;
         }
-        if (dbgS && row < g.Nc) {
+        if (dbgS && tile_valid && row < g.Nc) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (cbase + j < g.Nc) dbgS[((size_t)b * g.Nc + row) * g.Nc + cbase + j] = __uint_as_float(v[j]);
@@ -218,11 +226,11 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     }
     su_d = warp_sum_d(su_d);
     sw_d = warp_sum_d(sw_d);
-    if (lane == 0) { red[warp * 2] = su_d; red[warp * 2 + 1] = sw_d; }
+    if (lane == 0) { red[warp * 2] = tile_valid ? su_d : 0.0; red[warp * 2 + 1] = tile_valid ? sw_d : 0.0; }
   }
 
   tc::fence_before_sync();
-  __syncthreads();
+  tc::cluster_sync_all();  // nobody exits while the peer may still multicast into / arrive on this CTA
   if (threadIdx.x == 0) {
     double a = 0.0, c = 0.0;
     for (int i = 0; i < 8; ++i) { a += red[2 * i]; c += red[2 * i + 1]; }
@@ -267,8 +275,13 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = Nc_pad / BM, NK = Nc_pad / KT, NW = Nc_pad / 32;
-  const int b = blockIdx.x / MT, m0 = (blockIdx.x % MT) * BM;
+  // 2-CTA clusters share every B tile through TMA multicast, exactly as in the forward kernel
+  const int MTE = (MT + 1) & ~1;
+  const int b = blockIdx.x / MTE, mt = blockIdx.x % MTE;
+  const bool tile_valid = mt < MT;
+  const int m0 = tile_valid ? mt * BM : 0;
   const int row_base = b * Nc_pad;
+  const uint32_t cta_rank = tc::cluster_ctarank();
   constexpr uint32_t A_COL0 = 256;  // TMEM columns [0,256) accumulator, then NS x 32 columns of A
 
   if (warp == 4 && lane == 0) {
@@ -277,7 +290,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   }
   if (warp == 5) {
     if (lane == 0) {
-      for (int s = 0; s < NS; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(a_full + s, 128); tc::mbar_init(s_free + s, 1); }
+      for (int s = 0; s < NS; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(a_full + s, 128); tc::mbar_init(s_free + s, 2); }
       tc::mbar_init(d_full, 1);
       tc::fence_barrier_init();
     }
@@ -285,7 +298,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     tc::tmem_alloc(tmem_ptr, 512);
   }
   tc::fence_before_sync();
-  __syncthreads();
+  tc::cluster_sync_all();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -298,8 +311,10 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
         tc::mbar_expect_tx(b_full + s, Cfg::STAGE_BYTES);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         for (int p = 0; p < P; ++p)
-          for (int dc = 0; dc < 4; ++dc)
-            tc::tma_load_2d(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, st + (p * 4 + dc) * BG_BOX_BYTES, dc * 64, row_base + kc * KT);
+          for (int dc = 0; dc < 4; ++dc)  // my 32 of the 64 cells of every box, multicast to both CTAs
+            tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s,
+                               st + (p * 4 + dc) * BG_BOX_BYTES + cta_rank * (BG_BOX_BYTES / 2), dc * 64,
+                               row_base + kc * KT + cta_rank * (KT / 2), (uint16_t)0x3);
       }
     }
     __syncwarp();
@@ -324,7 +339,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
             first = 0;
           }
         }
-        tc::mma_commit(s_free + s);
+        tc::mma_commit_mc(s_free + s, (uint16_t)0x3);
       }
       tc::mma_commit(d_full);
     }
@@ -354,11 +369,12 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // epilogue: accumulator row of this thread -> out[b, d, row] (coalesced over rows)
     tc::mbar_wait(d_full, 0);
     tc::fence_after_sync();
+    const bool row_ok = tile_valid && row < Nc;
     float rs = 1.f;
-    if (rowscale && row < Nc) rs = rowscale[(size_t)row_base + row];
+    if (rowscale && row_ok) rs = rowscale[(size_t)row_base + row];
     // sparse positive pairs of this row (and removal of their negative term), see desc_pos_coef_kernel
     int npos = 0;
-    if (plist && row < Nc) {
+    if (plist && row_ok) {
 #pragma unroll
       for (int n = 0; n < DESC_MAXP; ++n)
         if (plist[((size_t)row_base + row) * DESC_MAXP + n] >= 0) npos = n + 1;
@@ -369,7 +385,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       uint32_t v[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, v);
       tc::tmem_ld_wait();
-      if (row < Nc) {
+      if (row_ok) {
         float val[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]) * rs;
@@ -389,7 +405,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   }
 
   tc::fence_before_sync();
-  __syncthreads();
+  tc::cluster_sync_all();
   if (warp == 5) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
@@ -430,6 +446,26 @@ int make_plane_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box
   return SSP_OK;
 }
 
+// launch with thread-block clusters of 2 along x
+template <typename... KArgs, typename... Args>
+int launch_cluster2(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e != cudaSuccess) { ssp_set_error("cluster launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+  return SSP_OK;
+}
+
 template <typename K>
 int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -439,7 +475,8 @@ int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
-extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / BM); }
+// CTAs (= partial-sum slots) of the forward kernel: row tiles per pair rounded up to the cluster size 2
+extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) { return B * (((desc_nc_pad(Nc) / BM) + 1) & ~1); }
 
 // Ahi/Alo: packed planes of `descriptors`, Bhi/Blo: packed planes of `descriptors_warped`
 // ([B, Nc_pad, 256] bf16).  Alo == Blo == NULL selects single-pass bf16; otherwise bf16x3.
@@ -460,16 +497,16 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_plane_map(&mAh, Ahi, rows, BM))) return rc;
-  if ((rc = make_plane_map(&mBh, Bhi, rows, BN))) return rc;
+  if ((rc = make_plane_map(&mBh, Bhi, rows, BN / 2))) return rc;  // half boxes: each CTA of a cluster fetches one half
   if ((rc = make_plane_map(&mAl, Alo ? Alo : Ahi, rows, BM))) return rc;
-  if ((rc = make_plane_map(&mBl, Blo ? Blo : Bhi, rows, BN))) return rc;
+  if ((rc = make_plane_map(&mBl, Blo ? Blo : Bhi, rows, BN / 2))) return rc;
   int grid = ssp_desc_dense_tc_nblocks(B, g.Nc);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FWD(PP, BB)                                                                                   \
   do {                                                                                                       \
     if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB>, FwdCfg<PP>::SMEM))) return rc;                      \
-    desc_dense_fwd_tc_kernel<PP, BB><<<grid, FWD_THREADS, FwdCfg<PP>::SMEM, st>>>(mAh, mAl, mBh, mBl, mv_pad, g, \
-                                                                                   partials, bitsR, bitsC, dbgS);  \
+    if ((rc = launch_cluster2(desc_dense_fwd_tc_kernel<PP, BB>, grid, FWD_THREADS, FwdCfg<PP>::SMEM, st, mAh, mAl, mBh, \
+                              mBl, mv_pad, g, partials, bitsR, bitsC, dbgS))) return rc;                       \
   } while (0)
   if (Alo) { if (bitsR) LAUNCH_FWD(2, true); else LAUNCH_FWD(2, false); }
   else     { if (bitsR) LAUNCH_FWD(1, true); else LAUNCH_FWD(1, false); }
@@ -490,16 +527,18 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   uint64_t rows = (uint64_t)B * Nc_pad;
   CUtensorMap mh, ml;
   int rc;
-  if ((rc = make_plane_map(&mh, Bhi, rows, KT))) return rc;
-  if ((rc = make_plane_map(&ml, Blo ? Blo : Bhi, rows, KT))) return rc;
-  int grid = B * (Nc_pad / BM);
+  if ((rc = make_plane_map(&mh, Bhi, rows, KT / 2))) return rc;  // half boxes (cluster multicast)
+  if ((rc = make_plane_map(&ml, Blo ? Blo : Bhi, rows, KT / 2))) return rc;
+  int grid = B * (((Nc_pad / BM) + 1) & ~1);
   cudaStream_t st = (cudaStream_t)stream;
   if (Blo) {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
-    desc_bits_gemm_tc_kernel<2><<<grid, BG_THREADS, BgCfg<2>::SMEM, st>>>(mh, ml, bits, rowscale, plist, pcoef, possrc, Nc, Nc_pad, out);
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, mh, ml, bits, rowscale, plist,
+                              pcoef, possrc, Nc, Nc_pad, out))) return rc;
   } else {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
-    desc_bits_gemm_tc_kernel<1><<<grid, BG_THREADS, BgCfg<1>::SMEM, st>>>(mh, ml, bits, rowscale, plist, pcoef, possrc, Nc, Nc_pad, out);
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, mh, ml, bits, rowscale, plist,
+                              pcoef, possrc, Nc, Nc_pad, out))) return rc;
   }
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;

@@ -3,7 +3,7 @@
 //   out = sum_n warp_n(heat_n * mask_n) / sum_n warp_n(mask_n), both warps bilinear with the same H_n.
 // One kernel: the heat*mask product is formed at the gather, the N-sum stays in registers, the two
 // intermediate [N,1,H,W] warped stacks of the reference never exist.  HBM traffic = the algorithmic
-// (2N+1)*H*W*4 bytes.  A block owns 64 consecutive output pixels x 4 interleaved view groups.
+// (2N+1)*H*W*4 bytes.  A block owns an 8x8 output tile x 4 interleaved view groups.
 #include "common.cuh"
 
 #define CH_PIX 64
@@ -24,10 +24,14 @@ combine_heatmap_kernel(const float* __restrict__ heat, const float* __restrict__
   for (int i = threadIdx.x; i < N * 9; i += blockDim.x) hs[i] = Hinv[i];
   __syncthreads();
   int lp = threadIdx.x % CH_PIX, g = threadIdx.x / CH_PIX;
-  int pix = blockIdx.x * CH_PIX + lp;
+  // a block owns an 8x8 pixel tile, a warp an 8x4 patch: under any rotation the bilinear footprints of a warp
+  // stay inside a compact source patch (few 32 B sectors per gather instead of one per lane)
+  int tiles_x = (W + 7) / 8;
+  int x = (blockIdx.x % tiles_x) * 8 + (lp & 7), y = (blockIdx.x / tiles_x) * 8 + (lp >> 3);
+  bool inside = x < W && y < H;
+  int pix = y * W + x;
   float sum_h = 0.f, sum_m = 0.f;
-  if (pix < H * W) {
-    int y = pix / W, x = pix % W;
+  if (inside) {
     float gx = __ldg(xs + x), gy = __ldg(ys + y);
     size_t plane = (size_t)H * W;
     for (int n = g; n < N; n += CH_GROUPS) {
@@ -63,7 +67,7 @@ combine_heatmap_kernel(const float* __restrict__ heat, const float* __restrict__
   part[threadIdx.x] = sum_h;
   part[CH_PIX * CH_GROUPS + threadIdx.x] = sum_m;
   __syncthreads();
-  if (g == 0 && pix < H * W) {
+  if (g == 0 && inside) {
     float th = 0.f, tm = 0.f;
 #pragma unroll
     for (int q = 0; q < CH_GROUPS; ++q) {
@@ -80,7 +84,7 @@ extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const f
   SSP_REQUIRE(I > 0 && I <= 65535 && N > 0 && H > 0 && W > 0, "ssp_combine_heatmap: bad sizes I=%d N=%d H=%d W=%d", I, N, H, W);
   size_t smem = ((size_t)N * 9 + 2 * CH_PIX * CH_GROUPS) * sizeof(float);
   SSP_REQUIRE(smem <= 48 * 1024, "ssp_combine_heatmap: N=%d views exceed the shared-memory table (max ~1100)", N);
-  dim3 nblk(ssp_ceil_div(H * W, CH_PIX), I);
+  dim3 nblk(ssp_ceil_div(W, 8) * ssp_ceil_div(H, 8), I);
   combine_heatmap_kernel<<<nblk, CH_PIX * CH_GROUPS, smem, (cudaStream_t)stream>>>(heat, mask, Hinv, N, H, W, xs, ys, out);
   SSP_CUDA_CHECK_LAUNCH("combine_heatmap_kernel");
   return SSP_OK;

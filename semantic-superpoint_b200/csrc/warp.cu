@@ -137,8 +137,10 @@ inv_warp_kernel(const float* __restrict__ img, int C, int H, int W, const float*
   __shared__ float h[9];
   if (threadIdx.x < 9 && threadIdx.y == 0) h[threadIdx.x] = Hinv[b * 9 + threadIdx.x];
   __syncthreads();
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  // the 32x8 block is covered by 4x2 warps of 8x4 pixels: compact source footprint per warp under rotation
+  int tid = threadIdx.y * 32 + threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+  int x = blockIdx.x * 32 + (wrp & 3) * 8 + (lane & 7);
+  int y = blockIdx.y * 8 + (wrp >> 2) * 4 + (lane >> 3);
   if (x >= W || y >= H) return;
   float ix, iy;
   src_coord(h, __ldg(xs + x), __ldg(ys + y), H, W, ix, iy);
