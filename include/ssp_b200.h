@@ -77,7 +77,7 @@ int ssp_box_nms(const float* prob /*[I,H,W]*/, int I, int H, int W, float min_pr
                 float* out /*[I,H,W]*/, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- a5: descriptor_loss (utils/utils.py:779-893), forward and backward, split into stages.
- *      Nc = Hc*Wc, Nc_pad = ceil(Nc/128)*128.  wpts [B,Nc_pad,2], mv_pad [B,Nc_pad],
+ *      Nc = Hc*Wc, Nc_pad = ceil(Nc/256)*256.  wpts [B,Nc_pad,2], mv_pad [B,Nc_pad],
  *      bitsR/bitsC [B,Nc_pad/32,Nc_pad] u32 indicator bit-matrices, partials = per-CTA (unweighted, weighted)
  *      double pairs.  out8 = { loss, pos_sum, neg_sum, norm, num_loss, num_pos, num_neg, sum(mask_valid) } ---- */
 int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/, int B, int Hc, int Wc,

@@ -12,12 +12,12 @@
 //   mv_pad [B, Nc_pad] float   mask_valid per warped-image cell, zero padded
 //   bitsR  [B, Nc_pad/32, Nc_pad] u32   word (cw, r): columns 32cw..32cw+31 of row r
 //   bitsC  [B, Nc_pad/32, Nc_pad] u32   word (rw, c): rows 32rw..32rw+31 of column c
-//   Nc_pad = ceil(Nc / 128) * 128
+//   Nc_pad = ceil(Nc / 256) * 256
 #pragma once
 #include "common.cuh"
 
 #define SSP_FAR 1.0e30f
-#define DESC_PAD 128
+#define DESC_PAD 256
 #define DESC_MAXP 16  // positive pairs per row / column kept in the sparse lists (descriptor_dist <= cell);
                       // colcnt[B*Nc_pad] counts entries that did not fit (0 unless the warp shrinks by > 3x)
 

@@ -6,11 +6,11 @@
 // product error = fp32-grade dot products on the tensor pipe).
 //
 // Forward kernel, one CTA per (pair b, 128-row tile):
-//   warp 8      TMA producer: A rows (all 256 channels, resident) once, then the B ring of 16 KB
-//               K-chunks (64 channels x 128 cells, SWIZZLE_128B) for every 128-column tile
-//   warp 9      MMA issuer: tcgen05.mma kind::f16 M=128 N=128 K=16 into a double-buffered TMEM
-//               accumulator (2 x 128 columns); tcgen05.commit frees ring slots / publishes tiles
-//   warps 0-7   epilogue: tcgen05.ld 32x32b (one row per thread, 64 columns per warp), hinge,
+//   warp 8      TMA producer: A rows (all 256 channels, resident) once, then the B ring of 32 KB
+//               K-chunks (64 channels x 256 cells, SWIZZLE_128B) for every 256-column tile
+//   warp 9      MMA issuer: tcgen05.mma kind::f16 M=128 N=256 K=16 into a double-buffered TMEM
+//               accumulator (2 x 256 columns = all of TMEM); tcgen05.commit frees ring slots / publishes tiles
+//   warps 0-7   epilogue: tcgen05.ld 32x32b (one row per thread, 128 columns per warp), hinge,
 //               mask_valid weighting, running sums, indicator bit-matrix in both orientations.
 //               No geometry here: the sparse positive pairs are corrected by the pos kernels.  The
 //               pair matrix never reaches HBM.
@@ -26,18 +26,19 @@
 namespace {
 
 constexpr int BM = 128;        // rows per CTA
-constexpr int BN = 128;        // columns per accumulator tile
+constexpr int BN = 256;        // columns per accumulator tile (one MMA instruction = M128 x N256 x K16, 128 cycles)
 constexpr int KD = 256;        // descriptor channels (GEMM K of the forward)
 constexpr int KC = 64;         // channels per smem chunk = 128 B of bf16 = one swizzle row
 constexpr int NKC = KD / KC;   // 4
-constexpr int CHUNK_BYTES = BM * KC * 2;  // 16 KB
+constexpr int CHUNK_BYTES = BM * KC * 2;  // 16 KB: one A chunk (128 rows x 64 channels)
+constexpr int BCHUNK_BYTES = BN * KC * 2; // 32 KB: one B chunk (256 cells x 64 channels)
 constexpr int FWD_THREADS = 320;
-constexpr int BAR_BYTES = 1024;
+constexpr int BAR_BYTES = 1536;  // mbarriers, TMEM pointer, warp partial sums, 8 x 32-word ballot scratch
 
 template <int P> struct FwdCfg {
-  static constexpr int NSTAGE = (P == 1) ? 8 : 5;
+  static constexpr int NSTAGE = (P == 1) ? 4 : 3;
   static constexpr int A_BYTES = P * NKC * CHUNK_BYTES;
-  static constexpr int B_BYTES = NSTAGE * CHUNK_BYTES;
+  static constexpr int B_BYTES = NSTAGE * BCHUNK_BYTES;
   static constexpr int SMEM = A_BYTES + B_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
@@ -47,9 +48,12 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // One 32-column slice of the accumulator row owned by this thread: negative hinge over every pair (the sparse
 // positive pairs are corrected by the pos kernels), mask_valid weighting, indicator bits in both orientations.
+// Row-orientation bits are OR-ed into a register; column-orientation words are warp ballots (bit r = row r of this
+// warp), parked in a 32-word shared scratch by lane 0 and picked up one per lane after the loop.
 template <bool BITS>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ mvp, float mneg, float& su,
-                                          float& sw, uint32_t& rowword, uint32_t& colword, int lane) {
+                                          float& sw, uint32_t& rowword, uint32_t& colword, uint32_t* __restrict__ scratch,
+                                          int lane) {
   rowword = 0;
   colword = 0;
   float su1 = 0.f, sw1 = 0.f;  // second accumulator pair: halves the dependent-add chains
@@ -67,9 +71,14 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
         bool p = neg > 0.f;
         rowword |= p ? (1u << j) : 0u;
         uint32_t bal = __ballot_sync(0xffffffffu, p);
-        if (lane == j) colword = bal;
+        if (lane == 0) scratch[j] = bal;
       }
     }
+  }
+  if (BITS) {
+    __syncwarp();
+    colword = scratch[lane];
+    __syncwarp();
   }
   su += su1;
   sw += sw1;
@@ -96,6 +105,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
   double* red = reinterpret_cast<double*>(tmem_ptr + 2);  // 8 warps x 2
+  uint32_t* ballot_scratch = reinterpret_cast<uint32_t*>(red + 16);  // 8 warps x 32 words
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = g.Nc_pad / BM, NT = g.Nc_pad / BN;
@@ -121,7 +131,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       tc::fence_barrier_init();
     }
     __syncwarp();
-    tc::tmem_alloc(tmem_ptr, 256);
+    tc::tmem_alloc(tmem_ptr, 512);
   }
   tc::fence_before_sync();
   tc::cluster_sync_all();  // barriers of both CTAs are live before any remote arrive / multicast write
@@ -142,9 +152,9 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             int s = it % NSTAGE;
             uint32_t ph = (it / NSTAGE) & 1;
             tc::mbar_wait(b_empty + s, ph ^ 1);  // slot s is free in BOTH CTAs
-            tc::mbar_expect_tx(b_full + s, CHUNK_BYTES);
-            // my half (64 of the 128 cells) of the chunk, written into both CTAs' slot s
-            tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * CHUNK_BYTES + cta_rank * (CHUNK_BYTES / 2),
+            tc::mbar_expect_tx(b_full + s, BCHUNK_BYTES);
+            // my half (128 of the 256 cells) of the chunk, written into both CTAs' slot s
+            tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * BCHUNK_BYTES + cta_rank * (BCHUNK_BYTES / 2),
                                kc * KC, row_base + nt * BN + cta_rank * (BN / 2), (uint16_t)0x3);
           }
     }
@@ -171,14 +181,11 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             tc::fence_after_sync();
             // B plane p (0 = hi, 1 = lo) meets A hi; B hi additionally meets A lo (lo*lo is dropped)
             const int n_a = (P == 2 && p == 0) ? 2 : 1;
+            const uint64_t db = tc::smem_desc_sw128(sB_u + s * BCHUNK_BYTES, 16, 1024);
             for (int pa = 0; pa < n_a; ++pa) {
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                uint64_t da = tc::smem_desc_sw128(sA_u + (pa * NKC + kc) * CHUNK_BYTES + k * 32, 16, 1024);
-                uint64_t db = tc::smem_desc_sw128(sB_u + s * CHUNK_BYTES + k * 32, 16, 1024);
-                tc::mma_ss(d_tmem, da, db, idesc, first ? 0u : 1u);
-                first = 0;
-              }
+              const uint64_t da = tc::smem_desc_sw128(sA_u + (pa * NKC + kc) * CHUNK_BYTES, 16, 1024);
+              tc::mma_ss_x4(d_tmem, da, db, idesc, first ? 0u : 1u);  // 4 x (M128 N256 K16) over this 64-channel chunk
+              first = 0;
             }
             tc::mma_commit_mc(b_empty + s, (uint16_t)0x3);  // tell both producers: this CTA is done with slot s
           }
@@ -198,15 +205,15 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       tc::mbar_wait(t_full + as, aph);
       tc::fence_after_sync();
       float su = 0.f, sw = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int cbase = nt * BN + half * 64 + ch * 32;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int cbase = nt * BN + half * 128 + ch * 32;
         uint32_t v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * 64 + ch * 32, v);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * 128 + ch * 32, v);
         tc::tmem_ld_wait();
         const float* mvp = mv_pad + (size_t)row_base + cbase;
         uint32_t rowword, colword;
-        epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, lane);
+        epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane);
         if (BITS && tile_valid) {
           bitsR[((size_t)b * NW + cbase / 32) * g.Nc_pad + row] = rowword;
           bitsC[((size_t)b * NW + (m0 + q * 32) / 32) * g.Nc_pad + cbase + lane] = colword;
@@ -239,7 +246,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   }
   if (warp == 9) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, 256);
+    tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -330,14 +337,11 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
         tc::mbar_wait(a_full + s, ph);
         tc::fence_after_sync();
         for (int p = 0; p < P; ++p) {
-#pragma unroll
-          for (int k = 0; k < KT / 16; ++k) {
-            // 16 cells = two 8-row groups (SBO 1024 B); 256 channels = four 64-wide blocks (LBO 8 KB)
-            uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * 4 * BG_BOX_BYTES + k * 2048, BG_BOX_BYTES, 1024);
-            uint32_t a_tmem = tmem_base + A_COL0 + s * 32 + k * 8;
-            tc::mma_ts(tmem_base, a_tmem, db, idesc, first ? 0u : 1u);
-            first = 0;
-          }
+          // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B per step); 256 channels = four
+          // 64-wide blocks (LBO 8 KB); A advances 8 TMEM columns per step
+          uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * 4 * BG_BOX_BYTES, BG_BOX_BYTES, 1024);
+          tc::mma_ts_x4(tmem_base, tmem_base + A_COL0 + s * 32, db, idesc, first ? 0u : 1u);
+          first = 0;
         }
         tc::mma_commit_mc(s_free + s, (uint16_t)0x3);
       }

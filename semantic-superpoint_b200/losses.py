@@ -78,7 +78,7 @@ class DetectorLossFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------------------------------------
 def _nc_pad(nc):
-    return (nc + 127) // 128 * 128
+    return (nc + 255) // 256 * 256
 
 
 class DescriptorLossFn(torch.autograd.Function):
