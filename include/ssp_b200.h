@@ -111,6 +111,9 @@ int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt,
                       const uint32_t* bitsR, const float* mv_pad, const float* alpha, const float* g3,
                       const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, float* colcoef,
                       void* stream);
+/* dD[b,:,r] += sum_n rowcoef[b,r,n] Dw[b,:,rowcol[b,r,n]];  dDw[b,:,c] += sum_n colcoef[b,c,n] D[b,:,colrow[b,c,n]] */
+int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef, const float* D,
+                       const float* Dw, int B, int Dch, int Nc, float* dD, float* dDw, void* stream);
 /* indicator GEMM  out[b,d,r] = rowscale[b,r] * sum_k bit(r,k) * colscale[b,k] * src[b,d,k]
  *                            + sum_n pcoef[b,r,n] * possrc[b,d,plist[b,r,n]]   (plist may be NULL) */
 int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src /*[B,Dch,Nc]*/, const float* colscale,

@@ -366,6 +366,47 @@ extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const i
 }
 
 // ----------------------------------------------------------------------------------------------
+// positive pairs, backward apply: out[b, d, r] += sum_n coef[b, r, n] * src[b, d, list[b, r, n]]
+// for both gradients in one launch (blockIdx.z = 0: dD with Dw as src, 1: dDw with D as src).  Streaming
+// kernel: block = 32 cells x 8 channel groups, every access is a 128 B line per warp (list partners of
+// neighbouring cells are neighbours).  Runs after the indicator GEMMs stored dD / dDw.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+desc_pos_apply_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowcoef, const int* __restrict__ colrow,
+                      const float* __restrict__ colcoef, const float* __restrict__ D, const float* __restrict__ Dw,
+                      int Dch, int Nc, int Nc_pad, float* __restrict__ dD, float* __restrict__ dDw) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int r = blockIdx.x * 32 + lane;
+  if (r >= Nc) return;
+  const bool second = blockIdx.z == 1;
+  const int* list = (second ? colrow : rowcol) + ((size_t)b * Nc_pad + r) * DESC_MAXP;
+  const float* coef = (second ? colcoef : rowcoef) + ((size_t)b * Nc_pad + r) * DESC_MAXP;
+  const float* src = (second ? D : Dw) + (size_t)b * Dch * Nc;
+  float* out = (second ? dDw : dD) + (size_t)b * Dch * Nc + r;
+  const int dper = (Dch + 7) / 8, d0 = dg * dper, d1 = min(Dch, d0 + dper);
+  for (int n = 0; n < DESC_MAXP; ++n) {
+    int pc = list[n];
+    if (pc < 0) break;  // lists are filled front to back
+    float cf = coef[n];
+    if (cf == 0.f) continue;
+#pragma unroll 8
+    for (int d = d0; d < d1; ++d) out[(size_t)d * Nc] = fmaf(cf, __ldg(src + (size_t)d * Nc + pc), out[(size_t)d * Nc]);
+  }
+}
+
+extern "C" int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef,
+                                  const float* D, const float* Dw, int B, int Dch, int Nc, float* dD, float* dDw,
+                                  void* stream) {
+  SSP_REQUIRE(rowcol && rowcoef && colrow && colcoef && D && Dw && dD && dDw, "ssp_desc_pos_apply: null pointer");
+  SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0, "ssp_desc_pos_apply: bad sizes");
+  dim3 grid(ssp_ceil_div(Nc, 32), B, 2);
+  desc_pos_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rowcol, rowcoef, colrow, colcoef, D, Dw, Dch, Nc,
+                                                                desc_nc_pad(Nc), dD, dDw);
+  SSP_CUDA_CHECK_LAUNCH("desc_pos_apply_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
 // operand pack for the tcgen05 engine: [B, Dch, Nc] fp32 (NCHW) -> K-major bf16 planes
 //   hi[b, c, d] = bf16(s * x),  lo[b, c, d] = bf16(s * x - hi)   (lo optional), rows c >= Nc zeroed
 //   s = scale[b, c] if given (backward: alpha), else 1.

@@ -184,20 +184,19 @@ class DescriptorLossFn(torch.autograd.Function):
         # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
         # dDw[b,:,c] = alpha[c] sum_r I[r,c] D[b,:,r]  + sum_n colcoef[c,n] D [b,:,colrow[c,n]]
         if engine == "fp32":
-            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc),
-                 B, Dch, Nc, ptr(dD), st)
-            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc),
-                 B, Dch, Nc, ptr(dDw), st)
+            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
+            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
         else:
             Ahi = saved[8]
             Alo = saved[9] if split else None
             Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Slo = torch.empty_like(Shi) if split else None
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
-            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc), B, Nc,
-                 ptr(dD), st)
-            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc), B,
-                 Nc, ptr(dDw), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, None, None, None, B, Nc, ptr(dD), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), None, None, None, B, Nc, ptr(dDw), st)
+        # sparse positive pairs (and removal of their negative term) on top of the GEMM results, one streaming launch
+        call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc,
+             ptr(dD), ptr(dDw), st)
         return dD, dDw, None, None, None, None, None, None, None, None
 
 

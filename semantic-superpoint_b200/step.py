@@ -10,19 +10,31 @@ from . import utils as U
 
 
 def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2D, mask_warp_2D, mat_H,
-              lamda_d=250, descriptor_dist=4, lambda_loss=1.0, engine=None, dist_group=None):
+              lamda_d=250, descriptor_dist=4, lambda_loss=1.0, engine=None, dist_group=None, side_stream=None):
     """Returns dict(loss, loss_det, loss_det_warp, loss_desc, positive_dist, negative_dist).
 
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc   (uniform weighting, Train_model_heatmap_all.py:361-365)
+    side_stream: run the two detector losses (forward and, through autograd, backward) on this stream so that their
+    HBM-bound kernels overlap the tensor-core descriptor kernels (used by GraphedLossStep, where buffer lifetimes are
+    static; in eager mode the caller must keep the inputs alive until the streams are joined).
     """
-    loss_det = U.detector_loss_2d(semi, labels_2D, mask_2D, dist_group=dist_group)
-    loss_det_warp = U.detector_loss_2d(semi_warp, warped_labels, mask_warp_2D, dist_group=dist_group)
+    if side_stream is not None:
+        cur = torch.cuda.current_stream()
+        side_stream.wait_stream(cur)
+        with torch.cuda.stream(side_stream):
+            loss_det = U.detector_loss_2d(semi, labels_2D, mask_2D, dist_group=dist_group)
+            loss_det_warp = U.detector_loss_2d(semi_warp, warped_labels, mask_warp_2D, dist_group=dist_group)
+    else:
+        loss_det = U.detector_loss_2d(semi, labels_2D, mask_2D, dist_group=dist_group)
+        loss_det_warp = U.detector_loss_2d(semi_warp, warped_labels, mask_warp_2D, dist_group=dist_group)
     mask_desc = U.getMasks(mask_warp_2D, 8, device=semi.device).unsqueeze(1)
     kw = {"dist_group": dist_group}
     if engine is not None:
         kw["engine"] = engine
     loss_desc, _mask, pos, neg = U.descriptor_loss(desc, desc_warp, mat_H, mask_valid=mask_desc, device=semi.device,
                                                    lamda_d=lamda_d, descriptor_dist=descriptor_dist, **kw)
+    if side_stream is not None:
+        torch.cuda.current_stream().wait_stream(side_stream)
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc
     return {"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
             "positive_dist": pos, "negative_dist": neg}
@@ -55,8 +67,10 @@ class GraphedLossStep(object):
 
     IN_KEYS = ("semi", "semi_warp", "desc", "desc_warp", "labels_2D", "warped_labels", "mask_2D", "mask_warp_2D", "mat_H")
 
-    def __init__(self, example, **kw):
+    def __init__(self, example, overlap=True, **kw):
         self.kw = kw
+        if overlap and kw.get("dist_group") is None:
+            self.kw["side_stream"] = torch.cuda.Stream()
         self.static = {k: example[k].detach().clone() for k in self.IN_KEYS}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
