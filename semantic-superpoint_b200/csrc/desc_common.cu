@@ -119,8 +119,17 @@ desc_pos_fwd_kernel(const float* __restrict__ D, const float* __restrict__ Dw, c
     int c = has ? scol[lane][n] : 0;
     float part = 0.f;
     if (has) {
-#pragma unroll 8
-      for (int d = d0; d < d1; ++d) part = fmaf(__ldg(Db + (size_t)d * g.Nc), __ldg(Dwb + (size_t)d * g.Nc + c), part);
+      for (int db = d0; db < d1; db += 32) {  // 64 independent loads in flight per thread
+        float a[32], w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          bool ok = db + i < d1;
+          a[i] = ok ? __ldg(Db + (size_t)(db + i) * g.Nc) : 0.f;
+          w[i] = ok ? __ldg(Dwb + (size_t)(db + i) * g.Nc + c) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) part = fmaf(a[i], w[i], part);
+      }
     }
     spart[dg][lane] = part;
     __syncthreads();
@@ -389,8 +398,19 @@ desc_pos_apply_kernel(const int* __restrict__ rowcol, const float* __restrict__ 
     if (pc < 0) break;  // lists are filled front to back
     float cf = coef[n];
     if (cf == 0.f) continue;
-#pragma unroll 8
-    for (int d = d0; d < d1; ++d) out[(size_t)d * Nc] = fmaf(cf, __ldg(src + (size_t)d * Nc + pc), out[(size_t)d * Nc]);
+    // 32 channels per step, all loads issued before the first store (memory-level parallelism)
+    for (int db = d0; db < d1; db += 32) {
+      float o[32], v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        bool ok = db + i < d1;
+        o[i] = ok ? out[(size_t)(db + i) * Nc] : 0.f;
+        v[i] = ok ? __ldg(src + (size_t)(db + i) * Nc + pc) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (db + i < d1) out[(size_t)(db + i) * Nc] = fmaf(cf, v[i], o[i]);
+    }
   }
 }
 
