@@ -146,6 +146,9 @@ class ClockSampler(object):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    # keep stdout clean for the ONE JSON line: libraries (NCCL banner, warnings) write to stderr meanwhile
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import ssp_b200 as S
     from ssp_b200 import _lib, dist as sdist
@@ -191,7 +194,7 @@ def run_ours(args):
     k0 = _lib.kernel_count
     step(dsets[0])
     kernels_per_step = _lib.kernel_count - k0
-    use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
+    use_graph = not args.no_graph  # with world > 1 the three tiny NCCL all-reduces are captured inside the graph
     if use_graph:
         # fwd+bwd of the whole step captured once per input set and replayed: the step is ~25 short kernels
         graphs = [S.step.GraphedLossStep(d, dist_group=group) for d in dsets]
@@ -288,6 +291,8 @@ def run_ours(args):
         "ssp_detector_loss_fwd": ("hbm", B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
         "ssp_detector_loss_bwd": ("hbm", B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
     }
+    bound_tbl["ssp_desc_pos_apply"] = ("hbm", 2.0 * 3.0 * B * NC * DCH * 4)
+    # the roofline is reported for the dominant KERNEL of the dense contraction / its data movement
     kind, work = bound_tbl.get(top, ("hbm", 0.0))
     dur_s = shares[top]["us_per_call"] * 1e-6
     if kind == "tensor":
@@ -323,10 +328,14 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.write(1, (json.dumps(line) + "\n").encode())
     if world > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)  # skip NCCL / graph teardown: destroying a process group with captured collectives can hang
 
 
 def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, images_per_step=4, steps=6):
@@ -370,7 +379,7 @@ def main():
     ap.add_argument("--engine", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-adapt", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--graph-multi", action="store_true", help="also use CUDA graphs when world > 1 (NCCL inside the graph)")
+    ap.add_argument("--graph-multi", action="store_true", help="(default now) kept for compatibility")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -377,40 +377,38 @@ extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const i
 // ----------------------------------------------------------------------------------------------
 // positive pairs, backward apply: out[b, d, r] += sum_n coef[b, r, n] * src[b, d, list[b, r, n]]
 // for both gradients in one launch (blockIdx.z = 0: dD with Dw as src, 1: dDw with D as src).  Streaming
-// kernel: block = 32 cells x 8 channel groups, every access is a 128 B line per warp (list partners of
-// neighbouring cells are neighbours).  Runs after the indicator GEMMs stored dD / dDw.
+// kernel, every access is a 128 B line per warp (list partners of neighbouring cells are neighbours).  Runs after the indicator GEMMs stored dD / dDw.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 desc_pos_apply_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowcoef, const int* __restrict__ colrow,
                       const float* __restrict__ colcoef, const float* __restrict__ D, const float* __restrict__ Dw,
                       int Dch, int Nc, int Nc_pad, float* __restrict__ dD, float* __restrict__ dDw) {
-  const int b = blockIdx.y, lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
-  const int r = blockIdx.x * 32 + lane;
-  if (r >= Nc) return;
-  const bool second = blockIdx.z == 1;
+  // block = 128 consecutive cells x 2 sub-groups of 16 channels: 512 contiguous bytes per channel row per block
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * 128 + (threadIdx.x & 127), sub = threadIdx.x >> 7;
+  const int nd32 = (Dch + 31) / 32;
+  const bool second = (int)blockIdx.z >= nd32;
+  const int d0 = ((int)blockIdx.z % nd32) * 32 + sub * 16;
+  if (r >= Nc || d0 >= Dch) return;
   const int* list = (second ? colrow : rowcol) + ((size_t)b * Nc_pad + r) * DESC_MAXP;
   const float* coef = (second ? colcoef : rowcoef) + ((size_t)b * Nc_pad + r) * DESC_MAXP;
-  const float* src = (second ? D : Dw) + (size_t)b * Dch * Nc;
-  float* out = (second ? dDw : dD) + (size_t)b * Dch * Nc + r;
-  const int dper = (Dch + 7) / 8, d0 = dg * dper, d1 = min(Dch, d0 + dper);
+  const float* src = (second ? D : Dw) + ((size_t)b * Dch + d0) * Nc;
+  float* out = (second ? dDw : dD) + ((size_t)b * Dch + d0) * Nc + r;
+  const int nd = min(16, Dch - d0);
   for (int n = 0; n < DESC_MAXP; ++n) {
     int pc = list[n];
     if (pc < 0) break;  // lists are filled front to back
     float cf = coef[n];
     if (cf == 0.f) continue;
-    // 32 channels per step, all loads issued before the first store (memory-level parallelism)
-    for (int db = d0; db < d1; db += 32) {
-      float o[32], v[32];
+    float o[16], v[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        bool ok = db + i < d1;
-        o[i] = ok ? out[(size_t)(db + i) * Nc] : 0.f;
-        v[i] = ok ? __ldg(src + (size_t)(db + i) * Nc + pc) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (db + i < d1) out[(size_t)(db + i) * Nc] = fmaf(cf, v[i], o[i]);
+    for (int i = 0; i < 16; ++i) {  // all loads issued before the first store
+      o[i] = i < nd ? out[(size_t)i * Nc] : 0.f;
+      v[i] = i < nd ? __ldg(src + (size_t)i * Nc + pc) : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nd) out[(size_t)i * Nc] = fmaf(cf, v[i], o[i]);
   }
 }
 
@@ -419,7 +417,7 @@ extern "C" int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const
                                   void* stream) {
   SSP_REQUIRE(rowcol && rowcoef && colrow && colcoef && D && Dw && dD && dDw, "ssp_desc_pos_apply: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0, "ssp_desc_pos_apply: bad sizes");
-  dim3 grid(ssp_ceil_div(Nc, 32), B, 2);
+  dim3 grid(ssp_ceil_div(Nc, 128), B, 2 * ssp_ceil_div(Dch, 32));
   desc_pos_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rowcol, rowcoef, colrow, colcoef, D, Dw, Dch, Nc,
                                                                 desc_nc_pad(Nc), dD, dDw);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_apply_kernel");
