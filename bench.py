@@ -120,8 +120,11 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:  # nvidia-smi can take a second to produce its first line
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -218,7 +221,6 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     kernels = kernels_per_step * args.steps
-    clocks = sampler.stop()
     ms = sdist.max_over_ranks(ms, dev)
     value = B * world * args.steps / (ms * 1e-3)
     loss_val = float(loss)
@@ -277,6 +279,7 @@ def run_ours(args):
         step(dsets[i % NSETS])
     torch.cuda.synchronize()
     prof = _lib.profile_end()  # {entry point: (calls, total ms)}
+    clocks = sampler.stop()  # sampled every 20 ms from before the timed region to the end of the profiled steps (same workload)
     total_prof = sum(v[1] for v in prof.values())
     shares = {k: {"calls_per_step": v[0] / args.steps, "us_per_call": 1e3 * v[1] / v[0], "share": v[1] / total_prof}
               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}

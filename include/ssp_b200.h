@@ -80,8 +80,9 @@ int ssp_box_nms(const float* prob /*[I,H,W]*/, int I, int H, int W, float min_pr
  *      Nc = Hc*Wc, Nc_pad = ceil(Nc/256)*256.  wpts [B,Nc_pad,2], mv_pad [B,Nc_pad],
  *      bitsR/bitsC [B,Nc_pad/32,Nc_pad] u32 indicator bit-matrices, partials = per-CTA (unweighted, weighted)
  *      double pairs.  out8 = { loss, pos_sum, neg_sum, norm, num_loss, num_pos, num_neg, sum(mask_valid) } ---- */
+int ssp_desc_geometry_nblocks(int B, int Nc);
 int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/, int B, int Hc, int Wc,
-                      int cell, float* wpts, float* mv_pad, void* stream);
+                      int cell, float* wpts, float* mv_pad, double* mv_part /*[geometry_nblocks]*/, void* stream);
 int ssp_desc_pos_nblocks(int B, int Nc);
 int ssp_desc_maxp(void); /* DESC_MAXP: list slots per row / column */
 /* sparse positive pairs: exact fp32 dots, partial sums (4 doubles per block: pos_u, pos_w, negcorr_u, negcorr_w)
@@ -100,8 +101,8 @@ int ssp_desc_dense_tc_nblocks(int B, int Nc);
 int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
                           int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
                           float* dbgS, void* stream);
-int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const float* mv_pad, int B,
-                      int Hc, int Wc, float* out8, void* stream);
+int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const double* mv_part,
+                      int nmv, int B, int Hc, int Wc, float* out8, void* stream);
 int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,
                        void* stream);
 int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)*/, const float* out8, int B,
@@ -113,7 +114,8 @@ int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt,
                       void* stream);
 /* dD[b,:,r] += sum_n rowcoef[b,r,n] Dw[b,:,rowcol[b,r,n]];  dDw[b,:,c] += sum_n colcoef[b,c,n] D[b,:,colrow[b,c,n]] */
 int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef, const float* D,
-                       const float* Dw, int B, int Dch, int Nc, float* dD, float* dDw, void* stream);
+                       const float* Dw, int B, int Dch, int Nc, int which /*0 both, 1 dD, 2 dDw*/, float* dD, float* dDw,
+                       void* stream);
 /* indicator GEMM  out[b,d,r] = rowscale[b,r] * sum_k bit(r,k) * colscale[b,k] * src[b,d,k]
  *                            + sum_n pcoef[b,r,n] * possrc[b,d,plist[b,r,n]]   (plist may be NULL) */
 int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src /*[B,Dch,Nc]*/, const float* colscale,

@@ -38,7 +38,8 @@ SIGNATURES = {
     "ssp_nms_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "ssp_nms_fast": (_I, [_P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _Z, _P]),
     "ssp_box_nms": (_I, [_P, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
-    "ssp_desc_geometry": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "ssp_desc_geometry_nblocks": (_I, [_I, _I]),
+    "ssp_desc_geometry": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ssp_desc_pos_nblocks": (_I, [_I, _I]),
     "ssp_desc_maxp": (_I, []),
     "ssp_desc_pos_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
@@ -47,11 +48,11 @@ SIGNATURES = {
     "ssp_desc_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
     "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
-    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P, _P]),
+    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P]),
     "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
     "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "ssp_desc_pos_coef": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
-    "ssp_desc_pos_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "ssp_desc_pos_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
 }

@@ -9,10 +9,10 @@
 // ----------------------------------------------------------------------------------------------
 __global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* __restrict__ mask_valid, int B,
                                      int Hc, int Wc, int cell, int Nc_pad, float2* __restrict__ wpts,
-                                     float* __restrict__ mv_pad) {
+                                     float* __restrict__ mv_pad, double* __restrict__ mv_part) {
+  __shared__ double shd[32];
   int b = blockIdx.y;
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Nc_pad) return;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;  // Nc_pad is a multiple of the block size
   int Nc = Hc * Wc;
   float2 w = make_float2(SSP_FAR, SSP_FAR);
   float mv = 0.f;
@@ -32,16 +32,21 @@ __global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* 
   }
   wpts[(size_t)b * Nc_pad + c] = w;
   mv_pad[(size_t)b * Nc_pad + c] = mv;
+  // per-block partial of sum(mask_valid) for the global normaliser (summed in fixed order by finalize)
+  double part = block_sum_d((double)mv, shd);
+  if (threadIdx.x == 0) mv_part[(size_t)b * gridDim.x + blockIdx.x] = part;
 }
 
+extern "C" int ssp_desc_geometry_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / 128); }
+
 extern "C" int ssp_desc_geometry(const float* Hm, const float* mask_valid, int B, int Hc, int Wc, int cell,
-                                 float* wpts, float* mv_pad, void* stream) {
-  SSP_REQUIRE(Hm && wpts && mv_pad, "ssp_desc_geometry: null pointer");
+                                 float* wpts, float* mv_pad, double* mv_part, void* stream) {
+  SSP_REQUIRE(Hm && wpts && mv_pad && mv_part, "ssp_desc_geometry: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Hc > 0 && Wc > 0 && cell > 0, "ssp_desc_geometry: bad sizes");
   int Nc_pad = desc_nc_pad(Hc * Wc);
   dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
   desc_geometry_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Hm, mask_valid, B, Hc, Wc, cell, Nc_pad,
-                                                                reinterpret_cast<float2*>(wpts), mv_pad);
+                                                                reinterpret_cast<float2*>(wpts), mv_pad, mv_part);
   SSP_CUDA_CHECK_LAUNCH("desc_geometry_kernel");
   return SSP_OK;
 }
@@ -202,7 +207,7 @@ extern "C" int ssp_desc_pos_fwd(const float* D, const float* Dw, const float* wp
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double* __restrict__ neg_part, int nneg,
-                     const float* __restrict__ mv_pad, size_t nmv, int B, int Hc, int Wc, float* __restrict__ out4) {
+                     const double* __restrict__ mv_part, int nmv, int B, int Hc, int Wc, float* __restrict__ out4) {
   __shared__ double sh[32];
   double pu = 0, pw = 0, nu = 0, nw = 0, sm = 0;
   double cu = 0, cw = 0;  // negative-hinge contribution of the positive pairs, contained in the dense sums
@@ -210,7 +215,7 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
     pu += pos_part[4 * i]; pw += pos_part[4 * i + 1]; cu += pos_part[4 * i + 2]; cw += pos_part[4 * i + 3];
   }
   for (int i = threadIdx.x; i < nneg; i += blockDim.x) { nu += neg_part[2 * i]; nw += neg_part[2 * i + 1]; }
-  for (size_t i = threadIdx.x; i < nmv; i += blockDim.x) sm += (double)mv_pad[i];
+  for (int i = threadIdx.x; i < nmv; i += blockDim.x) sm += mv_part[i];
   pu = block_sum_d(pu, sh);
   pw = block_sum_d(pw, sh);
   nu = block_sum_d(nu, sh);
@@ -235,11 +240,10 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
 }
 
 extern "C" int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg,
-                                 const float* mv_pad, int B, int Hc, int Wc, float* out4, void* stream) {
-  SSP_REQUIRE(pos_part && neg_part && mv_pad && out4, "ssp_desc_finalize: null pointer");
-  SSP_REQUIRE(npos >= 0 && nneg >= 0 && B > 0 && Hc > 0 && Wc > 0, "ssp_desc_finalize: bad sizes");
-  size_t nmv = (size_t)B * desc_nc_pad(Hc * Wc);
-  desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_pad, nmv, B, Hc, Wc, out4);
+                                 const double* mv_part, int nmv, int B, int Hc, int Wc, float* out4, void* stream) {
+  SSP_REQUIRE(pos_part && neg_part && mv_part && out4, "ssp_desc_finalize: null pointer");
+  SSP_REQUIRE(npos >= 0 && nneg >= 0 && nmv >= 0 && B > 0 && Hc > 0 && Wc > 0, "ssp_desc_finalize: bad sizes");
+  desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_part, nmv, B, Hc, Wc, out4);
   SSP_CUDA_CHECK_LAUNCH("desc_finalize_kernel");
   return SSP_OK;
 }
@@ -382,12 +386,12 @@ extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const i
 __global__ void __launch_bounds__(256)
 desc_pos_apply_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowcoef, const int* __restrict__ colrow,
                       const float* __restrict__ colcoef, const float* __restrict__ D, const float* __restrict__ Dw,
-                      int Dch, int Nc, int Nc_pad, float* __restrict__ dD, float* __restrict__ dDw) {
+                      int Dch, int Nc, int Nc_pad, int which, float* __restrict__ dD, float* __restrict__ dDw) {
   // block = 128 consecutive cells x 2 sub-groups of 16 channels: 512 contiguous bytes per channel row per block
   const int b = blockIdx.y;
   const int r = blockIdx.x * 128 + (threadIdx.x & 127), sub = threadIdx.x >> 7;
   const int nd32 = (Dch + 31) / 32;
-  const bool second = (int)blockIdx.z >= nd32;
+  const bool second = which == 2 || (which == 0 && (int)blockIdx.z >= nd32);
   const int d0 = ((int)blockIdx.z % nd32) * 32 + sub * 16;
   if (r >= Nc || d0 >= Dch) return;
   const int* list = (second ? colrow : rowcol) + ((size_t)b * Nc_pad + r) * DESC_MAXP;
@@ -412,14 +416,15 @@ desc_pos_apply_kernel(const int* __restrict__ rowcol, const float* __restrict__ 
   }
 }
 
+// which: 0 = both gradients, 1 = dD only, 2 = dDw only (lets the two halves run on different streams)
 extern "C" int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef,
-                                  const float* D, const float* Dw, int B, int Dch, int Nc, float* dD, float* dDw,
-                                  void* stream) {
+                                  const float* D, const float* Dw, int B, int Dch, int Nc, int which, float* dD,
+                                  float* dDw, void* stream) {
   SSP_REQUIRE(rowcol && rowcoef && colrow && colcoef && D && Dw && dD && dDw, "ssp_desc_pos_apply: null pointer");
-  SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0, "ssp_desc_pos_apply: bad sizes");
-  dim3 grid(ssp_ceil_div(Nc, 128), B, 2 * ssp_ceil_div(Dch, 32));
+  SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0 && which >= 0 && which <= 2, "ssp_desc_pos_apply: bad sizes");
+  dim3 grid(ssp_ceil_div(Nc, 128), B, (which == 0 ? 2 : 1) * ssp_ceil_div(Dch, 32));
   desc_pos_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rowcol, rowcoef, colrow, colcoef, D, Dw, Dch, Nc,
-                                                                desc_nc_pad(Nc), dD, dDw);
+                                                                desc_nc_pad(Nc), which, dD, dDw);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_apply_kernel");
   return SSP_OK;
 }

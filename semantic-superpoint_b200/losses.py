@@ -28,6 +28,36 @@ def get_descriptor_engine():
     return _engine
 
 
+_side_streams = {}
+
+
+class _Fork(object):
+    """`with _Fork(dev):` runs the body on a per-device side stream, ordered after everything queued so far on the
+    current stream; .join() makes the current stream wait for it.  Buffers are allocated on the current stream before
+    the fork and stay referenced until after the join, so the caching allocator never recycles them early."""
+
+    def __init__(self, dev):
+        self.cur = torch.cuda.current_stream(dev)
+        key = (dev.index, self.cur.cuda_stream)
+        if key not in _side_streams:
+            _side_streams[key] = torch.cuda.Stream(device=dev)
+        self.side = _side_streams[key]
+        self.ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        self.cur.wait_stream(self.side)
+
+
 # ------------------------------------------------------------------------------------------------
 class DetectorLossFn(torch.autograd.Function):
     """loss = sum_cells mask * sum_c BCE(softmax(semi)_c, target_c) / (sum mask + 1e-5)
@@ -106,7 +136,9 @@ class DescriptorLossFn(torch.autograd.Function):
 
         wpts = torch.empty((B, Ncp, 2), dtype=torch.float32, device=dev)
         mv_pad = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
-        call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), st)
+        nmv = lib.ssp_desc_geometry_nblocks(B, Nc)
+        mv_part = torch.empty((nmv,), dtype=torch.float64, device=dev)
+        call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), st)
 
         # sparse positive pairs: exact dots, partial sums, pair lists for the backward
         maxp = lib.ssp_desc_maxp()
@@ -116,37 +148,41 @@ class DescriptorLossFn(torch.autograd.Function):
         lists_f = torch.empty((2, B, Ncp, maxp), dtype=torch.float32, device=dev)  # rowdot, coldot
         rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2].view(-1)[: B * Ncp + 1]
         rowdot, coldot = lists_f[0], lists_f[1]
-        call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos, mneg,
-             ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
-
         bitsR = bitsC = None
         if need_grad:
             bitsR = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
             bitsC = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
         planes = None
+        # every buffer of the forward is allocated before the fork (see _Fork)
+        split = engine == "bf16x3"
         if engine == "fp32":
             nneg = lib.ssp_desc_dense_simt_nblocks(B, Nc)
-            neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
-            call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
-                 ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
         else:
-            split = engine == "bf16x3"
+            nneg = lib.ssp_desc_dense_tc_nblocks(B, Nc)
             Ahi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Bhi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Alo = torch.empty_like(Ahi) if split else None
             Blo = torch.empty_like(Bhi) if split else None
+        neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
+        out8 = torch.empty((8,), dtype=torch.float32, device=dev)
+        # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
+        with _Fork(dev) as fork:
+            call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos, mneg,
+                 ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), stream_of(Dc))
+        if engine == "fp32":
+            call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
+                 ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+        else:
             call("ssp_desc_pack", ptr(Dc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), st)
             call("ssp_desc_pack", ptr(Dwc), None, B, Dch, Nc, ptr(Bhi), ptr(Blo), st)
-            nneg = lib.ssp_desc_dense_tc_nblocks(B, Nc)
-            neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
             call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
                  ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             planes = (Ahi, Alo)
+        fork.join()
 
         if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
             raise RuntimeError("descriptor_loss: %d positive pairs overflowed the per-column lists" % int(colcnt[B * Ncp]))
-        out8 = torch.empty((8,), dtype=torch.float32, device=dev)
-        call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_pad), B, Hc, Wc, ptr(out8), st)
+        call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(out8), st)
         if dist_group is not None:
             from .dist import globalize_descriptor
             globalize_descriptor(out8, B, Hc, Wc, dist_group)
@@ -177,26 +213,37 @@ class DescriptorLossFn(torch.autograd.Function):
         rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2]
         rowdot, coldot = lists_f[0], lists_f[1]
         coefs = torch.empty((2,) + tuple(rowdot.shape), dtype=torch.float32, device=dev)
-        call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR), ptr(mv_pad),
-             ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(coefs[1]), st)
         dD = torch.empty_like(Dc)
         dDw = torch.empty_like(Dwc)
-        # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
-        # dDw[b,:,c] = alpha[c] sum_r I[r,c] D[b,:,r]  + sum_n colcoef[c,n] D [b,:,colrow[c,n]]
-        if engine == "fp32":
-            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
-            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
-        else:
+        tc_engine = engine != "fp32"
+        if tc_engine:
             Ahi = saved[8]
             Alo = saved[9] if split else None
             Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Slo = torch.empty_like(Shi) if split else None
+        # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
+        # dDw[b,:,c] = alpha[c] sum_r I[r,c] D[b,:,r]  + sum_n colcoef[c,n] D [b,:,colrow[c,n]]
+        # stream plan:  [pos_coef]      ||  [pack(alpha*Dw) -> GEMM dD]
+        #               [pos_apply dD]  ||  [GEMM dDw]          then pos_apply dDw
+        with _Fork(dev) as f1:
+            call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
+                 ptr(mv_pad), ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(coefs[1]), stream_of(Dc))
+        if tc_engine:
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
             call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, None, None, None, B, Nc, ptr(dD), st)
+        else:
+            call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
+        f1.join()
+        with _Fork(dev) as f2:  # ordered after the dD GEMM and the coefficients
+            call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 1,
+                 ptr(dD), ptr(dDw), stream_of(Dc))
+        if tc_engine:
             call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), None, None, None, B, Nc, ptr(dDw), st)
-        # sparse positive pairs (and removal of their negative term) on top of the GEMM results, one streaming launch
-        call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc,
+        else:
+            call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
+        call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 2,
              ptr(dD), ptr(dDw), st)
+        f2.join()
         return dD, dDw, None, None, None, None, None, None, None, None
 
 
