@@ -5,7 +5,7 @@
 // (mode bf16) or hi + lo with three MMA chains hi*hi + lo*hi + hi*lo (mode bf16x3, ~2^-16 relative
 // product error = fp32-grade dot products on the tensor pipe).
 //
-// Forward kernel, one CTA per (pair b, 128-row tile):
+// Forward kernel, persistent 2-CTA clusters over (pair b, 128-row tile, 256-column tile) items:
 //   warp 8      TMA producer: A rows (all 256 channels, resident) once, then the B ring of 32 KB
 //               K-chunks (64 channels x 256 cells, SWIZZLE_128B) for every 256-column tile
 //   warp 9      MMA issuer: tcgen05.mma kind::f16 M=128 N=256 K=16 into a double-buffered TMEM
@@ -15,13 +15,16 @@
 //               No geometry here: the sparse positive pairs are corrected by the pos kernels.  The
 //               pair matrix never reaches HBM.
 //
-// Backward kernel = indicator GEMM  out[b, d, r] = rowscale[r] * sum_k bit(r,k) * Bp[b, k, d]:
+// Backward kernel = indicator GEMM  out[b, d, r] = rowscale[r] * sum_k bit(r,k) * Bp[b, k, d], persistent over
+// (pair, row-tile pair, channel half) items:
 //   warps 0-3   expand 64 indicator bits per row into bf16 {0,1} and tcgen05.st them as the A
-//               operand into TMEM (A never touches shared memory); later the epilogue
-//   warp 4      TMA producer of B tiles [64 cells x 256 channels] (MN-major, SWIZZLE_128B)
-//   warp 5      MMA issuer, M=128 N=256 K=16, A from TMEM, fp32 accumulator of 256 TMEM columns
+//               operand into TMEM (A never touches shared memory)
+//   warps 4-7   epilogue of the previous item (double-buffered 128-column accumulators)
+//   warp 8      TMA producer of B tiles [64 cells x 128 channels] (MN-major, SWIZZLE_128B, multicast)
+//   warp 9      MMA issuer, M=128 N=128 K=16, A from TMEM
 #include "desc_common.cuh"
 #include "tc_ptx.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -84,6 +87,11 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
   sw += sw1;
 }
 
+// Persistent forward kernel.  Work item = (pair b, row-tile pair mp, column tile nt); the flattened item range is
+// split evenly over the clusters (one 2-CTA cluster per SM pair), so all SMs finish together instead of running
+// 2.16 waves of whole row tiles.  Within a cluster CTA rank r owns row tile 2*mp + r; A is reloaded only when
+// (b, mp) changes (items are contiguous in nt).  Per-item, per-warp partial sums go to
+// partials[((item*2 + rank)*8 + warp)*2 + {0,1}].
 template <int P, bool BITS>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -99,24 +107,20 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   uint8_t* sB = sA + Cfg::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::B_BYTES);
   uint64_t* a_full = bars;
-  uint64_t* b_full = bars + 1;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;
   uint64_t* b_empty = b_full + NSTAGE;
   uint64_t* t_full = b_empty + NSTAGE;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
-  double* red = reinterpret_cast<double*>(tmem_ptr + 2);  // 8 warps x 2
-  uint32_t* ballot_scratch = reinterpret_cast<uint32_t*>(red + 16);  // 8 warps x 32 words
+  uint32_t* ballot_scratch = tmem_ptr + 2;  // 8 warps x 32 words
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int MT = g.Nc_pad / BM, NT = g.Nc_pad / BN;
-  // Clusters of 2 CTAs own two row tiles of the same pair and share every B chunk: each CTA fetches half of the
-  // chunk and TMA-multicasts it into both shared memories (halves the L2 -> SM traffic that bounds this kernel).
-  const int MTE = (MT + 1) & ~1;  // row tiles per pair rounded up to the cluster size
-  const int b = blockIdx.x / MTE, mt = blockIdx.x % MTE;
-  const bool tile_valid = mt < MT;  // the odd tile out still takes part in the B multicast, its results are dropped
-  const int m0 = tile_valid ? mt * BM : 0;
-  const int row_base = b * g.Nc_pad;  // first packed row of this pair
+  const int MP = g.Nc_pad / (2 * BM), NT = g.Nc_pad / BN;  // Nc_pad is a multiple of 256
   const uint32_t cta_rank = tc::cluster_ctarank();
+  const int ncluster = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const long long T = (long long)g.B * MP * NT;
+  const int it0 = (int)(T * cid / ncluster), it1 = (int)(T * (cid + 1) / ncluster);
 
   if (warp == 8 && lane == 0) {
     tc::prefetch_tmap(&tmA_hi);
@@ -126,6 +130,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 9) {
     if (lane == 0) {
       tc::mbar_init(a_full, 1);
+      tc::mbar_init(a_empty, 1);
       for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 2); }  // 2 = both CTAs' MMAs
       for (int s = 0; s < 2; ++s) { tc::mbar_init(t_full + s, 1); tc::mbar_init(t_empty + s, 8); }
       tc::fence_barrier_init();
@@ -141,42 +146,54 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      tc::mbar_expect_tx(a_full, Cfg::A_BYTES);
-      for (int p = 0; p < P; ++p)
+      int prev_key = -1, stage_it = 0;
+      uint32_t a_empty_ph = 0;
+      for (int it = it0; it < it1; ++it) {
+        const int key = it / NT, nt = it - key * NT;  // key = b * MP + mp
+        const int b = key / MP, mp = key - b * MP;
+        const int row_base = b * g.Nc_pad;
+        if (key != prev_key) {
+          if (prev_key >= 0) { tc::mbar_wait(a_empty, a_empty_ph); a_empty_ph ^= 1; }  // MMAs on the old A rows are done
+          tc::mbar_expect_tx(a_full, Cfg::A_BYTES);
+          for (int p = 0; p < P; ++p)
+            for (int kc = 0; kc < NKC; ++kc)
+              tc::tma_load_2d(p == 0 ? &tmA_hi : &tmA_lo, a_full, sA + (p * NKC + kc) * CHUNK_BYTES, kc * KC,
+                              row_base + (2 * mp + (int)cta_rank) * BM);
+          prev_key = key;
+        }
         for (int kc = 0; kc < NKC; ++kc)
-          tc::tma_load_2d(p == 0 ? &tmA_hi : &tmA_lo, a_full, sA + (p * NKC + kc) * CHUNK_BYTES, kc * KC, row_base + m0);
-      int it = 0;
-      for (int nt = 0; nt < NT; ++nt)
-        for (int kc = 0; kc < NKC; ++kc)
-          for (int p = 0; p < P; ++p, ++it) {
-            int s = it % NSTAGE;
-            uint32_t ph = (it / NSTAGE) & 1;
+          for (int p = 0; p < P; ++p, ++stage_it) {
+            int s = stage_it % NSTAGE;
+            uint32_t ph = (stage_it / NSTAGE) & 1;
             tc::mbar_wait(b_empty + s, ph ^ 1);  // slot s is free in BOTH CTAs
             tc::mbar_expect_tx(b_full + s, BCHUNK_BYTES);
             // my half (128 of the 256 cells) of the chunk, written into both CTAs' slot s
             tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * BCHUNK_BYTES + cta_rank * (BCHUNK_BYTES / 2),
                                kc * KC, row_base + nt * BN + cta_rank * (BN / 2), (uint16_t)0x3);
           }
+      }
     }
     __syncwarp();
   } else if (warp == 9) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BN, 0, 0);
-      tc::mbar_wait(a_full, 0);
       const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
-      int it = 0;
-      for (int nt = 0; nt < NT; ++nt) {
-        int as = nt & 1;
-        uint32_t aph = (nt >> 1) & 1;
+      int prev_key = -1, stage_it = 0, tcount = 0;
+      uint32_t a_full_ph = 0;
+      for (int it = it0; it < it1; ++it, ++tcount) {
+        const int key = it / NT;
+        if (key != prev_key) { tc::mbar_wait(a_full, a_full_ph); a_full_ph ^= 1; prev_key = key; }
+        const int as = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
         tc::mbar_wait(t_empty + as, aph ^ 1);
         tc::fence_after_sync();
-        uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * BN;
         uint32_t first = 1;
         for (int kc = 0; kc < NKC; ++kc)
-          for (int p = 0; p < P; ++p, ++it) {
-            int s = it % NSTAGE;
-            uint32_t ph = (it / NSTAGE) & 1;
+          for (int p = 0; p < P; ++p, ++stage_it) {
+            int s = stage_it % NSTAGE;
+            uint32_t ph = (stage_it / NSTAGE) & 1;
             tc::mbar_wait(b_full + s, ph);
             tc::fence_after_sync();
             // B plane p (0 = hi, 1 = lo) meets A hi; B hi additionally meets A lo (lo*lo is dropped)
@@ -190,21 +207,27 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             tc::mma_commit_mc(b_empty + s, (uint16_t)0x3);  // tell both producers: this CTA is done with slot s
           }
         tc::mma_commit(t_full + as);  // accumulator tile complete
+        const int next_key = (it + 1 < it1) ? (it + 1) / NT : -2;
+        if (next_key != key) tc::mma_commit(a_empty);  // the A rows may be replaced once these MMAs have drained
       }
     }
     __syncwarp();
   } else {
     // ------------------------------ epilogue warps 0..7 ------------------------------
     const int q = warp & 3, half = warp >> 2;
-    const int row = m0 + q * 32 + lane;  // row inside the padded pair
     const int NW = g.Nc_pad / 32;
-    double su_d = 0.0, sw_d = 0.0;
-    for (int nt = 0; nt < NT; ++nt) {
-      int as = nt & 1;
-      uint32_t aph = (nt >> 1) & 1;
+    int tcount = 0;
+    for (int it = it0; it < it1; ++it, ++tcount) {
+      const int key = it / NT, nt = it - key * NT;
+      const int b = key / MP, mp = key - b * MP;
+      const int row_base = b * g.Nc_pad;
+      const int m0 = (2 * mp + (int)cta_rank) * BM;
+      const int row = m0 + q * 32 + lane;  // row inside the padded pair
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
       tc::mbar_wait(t_full + as, aph);
       tc::fence_after_sync();
-      float su = 0.f, sw = 0.f;
+      double su_d = 0.0, sw_d = 0.0;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int cbase = nt * BN + half * 128 + ch * 32;
@@ -213,12 +236,15 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         tc::tmem_ld_wait();
         const float* mvp = mv_pad + (size_t)row_base + cbase;
         uint32_t rowword, colword;
+        float su = 0.f, sw = 0.f;
         epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane);
-        if (BITS && tile_valid) {
+        su_d += (double)su;
+        sw_d += (double)sw;
+        if (BITS) {
           bitsR[((size_t)b * NW + cbase / 32) * g.Nc_pad + row] = rowword;
           bitsC[((size_t)b * NW + (m0 + q * 32) / 32) * g.Nc_pad + cbase + lane] = colword;
         }
-        if (dbgS && tile_valid && row < g.Nc) {
+        if (dbgS && row < g.Nc) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (cbase + j < g.Nc) dbgS[((size_t)b * g.Nc + row) * g.Nc + cbase + j] = __uint_as_float(v[j]);
@@ -228,22 +254,18 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(t_empty + as);
-      su_d += (double)su;
-      sw_d += (double)sw;
+      su_d = warp_sum_d(su_d);
+      sw_d = warp_sum_d(sw_d);
+      if (lane == 0) {
+        size_t slot = (((size_t)it * 2 + cta_rank) * 8 + warp) * 2;
+        partials[slot] = su_d;
+        partials[slot + 1] = sw_d;
+      }
     }
-    su_d = warp_sum_d(su_d);
-    sw_d = warp_sum_d(sw_d);
-    if (lane == 0) { red[warp * 2] = tile_valid ? su_d : 0.0; red[warp * 2 + 1] = tile_valid ? sw_d : 0.0; }
   }
 
   tc::fence_before_sync();
   tc::cluster_sync_all();  // nobody exits while the peer may still multicast into / arrive on this CTA
-  if (threadIdx.x == 0) {
-    double a = 0.0, c = 0.0;
-    for (int i = 0; i < 8; ++i) { a += red[2 * i]; c += red[2 * i + 1]; }
-    partials[2 * (size_t)blockIdx.x] = a;
-    partials[2 * (size_t)blockIdx.x + 1] = c;
-  }
   if (warp == 9) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
@@ -255,20 +277,24 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 // ------------------------------------------------------------------------------------------------
 constexpr int KT = 64;                       // cells (GEMM K) per stage
 constexpr int BG_BOX_BYTES = KT * 128;       // one [64 cells x 64 channels] box = 8 KB
-constexpr int BG_THREADS = 192;
+constexpr int BG_N = 128;                    // channels per work item (half of the descriptor)
+constexpr int BG_THREADS = 320;              // 4 expander warps, 4 epilogue warps, TMA producer, MMA issuer
 
 template <int P> struct BgCfg {
-  static constexpr int NS = (P == 1) ? 4 : 3;
-  static constexpr int STAGE_BYTES = P * 4 * BG_BOX_BYTES;  // 32 KB per plane
+  static constexpr int NS = (P == 1) ? 6 : 4;
+  static constexpr int STAGE_BYTES = P * 2 * BG_BOX_BYTES;  // P planes x two 64-channel boxes = 16 KB per plane
   static constexpr int SMEM = NS * STAGE_BYTES + BAR_BYTES + 1024;
 };
 
+// Persistent indicator GEMM.  Work item = (pair b, row-tile pair mp, channel half dh); flattened item range split
+// evenly over 2-CTA clusters.  The fp32 accumulator is double buffered in TMEM (2 x 128 columns), so the epilogue of
+// item i (warps 4-7: TMEM -> registers -> coalesced NCHW stores) overlaps the main loop of item i+1 (warps 0-3 expand
+// indicator bits into the TMEM A ring, warp 8 streams B through TMA multicast, warp 9 issues the MMAs).
 template <int P>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
-                         const int* __restrict__ plist, const float* __restrict__ pcoef,
-                         const float* __restrict__ possrc, int Nc, int Nc_pad, float* __restrict__ out) {
+                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale, int B, int Nc, int Nc_pad,
+                         float* __restrict__ out) {
   using Cfg = BgCfg<P>;
   constexpr int NS = Cfg::NS;
   extern __shared__ uint8_t smem_raw[];
@@ -278,27 +304,25 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   uint64_t* a_full = b_full + NS;
   uint64_t* s_free = a_full + NS;
   uint64_t* d_full = s_free + NS;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_full + 1);
+  uint64_t* d_empty = d_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int MT = Nc_pad / BM, NK = Nc_pad / KT, NW = Nc_pad / 32;
-  // 2-CTA clusters share every B tile through TMA multicast, exactly as in the forward kernel
-  const int MTE = (MT + 1) & ~1;
-  const int b = blockIdx.x / MTE, mt = blockIdx.x % MTE;
-  const bool tile_valid = mt < MT;
-  const int m0 = tile_valid ? mt * BM : 0;
-  const int row_base = b * Nc_pad;
+  const int MP = Nc_pad / (2 * BM), NK = Nc_pad / KT, NW = Nc_pad / 32;
   const uint32_t cta_rank = tc::cluster_ctarank();
-  constexpr uint32_t A_COL0 = 256;  // TMEM columns [0,256) accumulator, then NS x 32 columns of A
+  const int ncluster = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const long long T = (long long)B * MP * 2;
+  const int it0 = (int)(T * cid / ncluster), it1 = (int)(T * (cid + 1) / ncluster);
+  constexpr uint32_t A_COL0 = 256;  // TMEM: accumulators at columns [0,128) and [128,256), then NS x 32 columns of A
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tc::prefetch_tmap(&tmB_hi);
     if (P == 2) tc::prefetch_tmap(&tmB_lo);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(a_full + s, 128); tc::mbar_init(s_free + s, 2); }
-      tc::mbar_init(d_full, 1);
+      for (int s = 0; s < 2; ++s) { tc::mbar_init(d_full + s, 1); tc::mbar_init(d_empty + s, 4); }
       tc::fence_barrier_init();
     }
     __syncwarp();
@@ -309,108 +333,124 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      for (int kc = 0; kc < NK; ++kc) {
-        int s = kc % NS;
-        uint32_t ph = (kc / NS) & 1;
-        tc::mbar_wait(s_free + s, ph ^ 1);
-        tc::mbar_expect_tx(b_full + s, Cfg::STAGE_BYTES);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        for (int p = 0; p < P; ++p)
-          for (int dc = 0; dc < 4; ++dc)  // my 32 of the 64 cells of every box, multicast to both CTAs
-            tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s,
-                               st + (p * 4 + dc) * BG_BOX_BYTES + cta_rank * (BG_BOX_BYTES / 2), dc * 64,
-                               row_base + kc * KT + cta_rank * (KT / 2), (uint16_t)0x3);
+      int st_it = 0;
+      for (int it = it0; it < it1; ++it) {
+        const int key = it >> 1, dh = it & 1;
+        const int b = key / MP;
+        const int row_base = b * Nc_pad;
+        for (int kc = 0; kc < NK; ++kc, ++st_it) {
+          int s = st_it % NS;
+          uint32_t ph = (st_it / NS) & 1;
+          tc::mbar_wait(s_free + s, ph ^ 1);
+          tc::mbar_expect_tx(b_full + s, Cfg::STAGE_BYTES);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          for (int p = 0; p < P; ++p)
+            for (int dc = 0; dc < 2; ++dc)  // my 32 of the 64 cells of every box, multicast to both CTAs
+              tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s,
+                                 st + (p * 2 + dc) * BG_BOX_BYTES + cta_rank * (BG_BOX_BYTES / 2), dh * BG_N + dc * 64,
+                                 row_base + kc * KT + cta_rank * (KT / 2), (uint16_t)0x3);
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
+    // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, 256, 0, 1);  // A K-major (TMEM), B MN-major
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BG_N, 0, 1);  // A K-major (TMEM), B MN-major
       const uint32_t smem_u = tc::smem_u32(smem);
-      uint32_t first = 1;
-      for (int kc = 0; kc < NK; ++kc) {
-        int s = kc % NS;
-        uint32_t ph = (kc / NS) & 1;
-        tc::mbar_wait(b_full + s, ph);
-        tc::mbar_wait(a_full + s, ph);
+      int st_it = 0, tcount = 0;
+      for (int it = it0; it < it1; ++it, ++tcount) {
+        const int as = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        tc::mbar_wait(d_empty + as, aph ^ 1);
         tc::fence_after_sync();
-        for (int p = 0; p < P; ++p) {
-          // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B per step); 256 channels = four
-          // 64-wide blocks (LBO 8 KB); A advances 8 TMEM columns per step
-          uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * 4 * BG_BOX_BYTES, BG_BOX_BYTES, 1024);
-          tc::mma_ts_x4(tmem_base, tmem_base + A_COL0 + s * 32, db, idesc, first ? 0u : 1u);
-          first = 0;
+        const uint32_t d_tmem = tmem_base + as * BG_N;
+        uint32_t first = 1;
+        for (int kc = 0; kc < NK; ++kc, ++st_it) {
+          int s = st_it % NS;
+          uint32_t ph = (st_it / NS) & 1;
+          tc::mbar_wait(b_full + s, ph);
+          tc::mbar_wait(a_full + s, ph);
+          tc::fence_after_sync();
+          for (int p = 0; p < P; ++p) {
+            // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B per step); 128 channels = two
+            // 64-wide blocks (LBO 8 KB); A advances 8 TMEM columns per step
+            uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * 2 * BG_BOX_BYTES, BG_BOX_BYTES, 1024);
+            tc::mma_ts_x4(d_tmem, tmem_base + A_COL0 + s * 32, db, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          tc::mma_commit_mc(s_free + s, (uint16_t)0x3);
         }
-        tc::mma_commit_mc(s_free + s, (uint16_t)0x3);
+        tc::mma_commit(d_full + as);
       }
-      tc::mma_commit(d_full);
     }
     __syncwarp();
-  } else {
-    // warps 0..3: expand indicator bits -> bf16 A operand in TMEM
+  } else if (warp < 4) {
+    // ------------------------------ expanders: indicator bits -> bf16 A operand in TMEM ------------------------------
     const int q = warp;
-    const int row = m0 + q * 32 + lane;
-    for (int kc = 0; kc < NK; ++kc) {
-      int s = kc % NS;
-      uint32_t ph = (kc / NS) & 1;
-      uint32_t w0 = __ldg(bits + ((size_t)b * NW + kc * 2) * Nc_pad + row);
-      uint32_t w1 = __ldg(bits + ((size_t)b * NW + kc * 2 + 1) * Nc_pad + row);
-      tc::mbar_wait(s_free + s, ph ^ 1);
-      tc::fence_after_sync();
-      uint32_t r[32];
+    int st_it = 0;
+    for (int it = it0; it < it1; ++it) {
+      const int key = it >> 1;
+      const int b = key / MP, mp = key - b * MP;
+      const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
+      const uint32_t* brow = bits + (size_t)b * NW * Nc_pad + row;
+      for (int kc = 0; kc < NK; ++kc, ++st_it) {
+        int s = st_it % NS;
+        uint32_t ph = (st_it / NS) & 1;
+        uint32_t w0 = __ldg(brow + (size_t)(kc * 2) * Nc_pad);
+        uint32_t w1 = __ldg(brow + (size_t)(kc * 2 + 1) * Nc_pad);
+        tc::mbar_wait(s_free + s, ph ^ 1);
+        tc::fence_after_sync();
+        uint32_t r[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        r[i] = ((w0 >> (2 * i)) & 1u) * 0x3F80u + ((w0 >> (2 * i + 1)) & 1u) * 0x3F800000u;
-        r[16 + i] = ((w1 >> (2 * i)) & 1u) * 0x3F80u + ((w1 >> (2 * i + 1)) & 1u) * 0x3F800000u;
-      }
-      tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
-      tc::tmem_st_wait();
-      tc::fence_before_sync();
-      tc::mbar_arrive(a_full + s);
-    }
-    // epilogue: accumulator row of this thread -> out[b, d, row] (coalesced over rows)
-    tc::mbar_wait(d_full, 0);
-    tc::fence_after_sync();
-    const bool row_ok = tile_valid && row < Nc;
-    float rs = 1.f;
-    if (rowscale && row_ok) rs = rowscale[(size_t)row_base + row];
-    // sparse positive pairs of this row (and removal of their negative term), see desc_pos_coef_kernel
-    int npos = 0;
-    if (plist && row_ok) {
-#pragma unroll
-      for (int n = 0; n < DESC_MAXP; ++n)
-        if (plist[((size_t)row_base + row) * DESC_MAXP + n] >= 0) npos = n + 1;
-    }
-    const int nmax = __reduce_max_sync(0xffffffffu, npos);
-#pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      uint32_t v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, v);
-      tc::tmem_ld_wait();
-      if (row_ok) {
-        float val[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]) * rs;
-#pragma unroll 1
-        for (int n = 0; n < nmax; ++n) {
-          int pc = plist[((size_t)row_base + row) * DESC_MAXP + n];
-          if (pc < 0) continue;
-          float pf = pcoef[((size_t)row_base + row) * DESC_MAXP + n];
-          const float* ps = possrc + ((size_t)b * KD + ch * 32) * Nc + pc;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
+        for (int i = 0; i < 16; ++i) {
+          r[i] = ((w0 >> (2 * i)) & 1u) * 0x3F80u + ((w0 >> (2 * i + 1)) & 1u) * 0x3F800000u;
+          r[16 + i] = ((w1 >> (2 * i)) & 1u) * 0x3F80u + ((w1 >> (2 * i + 1)) & 1u) * 0x3F800000u;
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) out[((size_t)b * KD + ch * 32 + j) * Nc + row] = val[j];
+        tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        tc::mbar_arrive(a_full + s);
       }
+    }
+  } else {
+    // ------------------------------ epilogue warps 4..7 ------------------------------
+    const int q = warp & 3;
+    int tcount = 0;
+    for (int it = it0; it < it1; ++it, ++tcount) {
+      const int key = it >> 1, dh = it & 1;
+      const int b = key / MP, mp = key - b * MP;
+      const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
+      const bool row_ok = row < Nc;
+      float rs = 1.f;
+      if (rowscale && row_ok) rs = rowscale[(size_t)b * Nc_pad + row];
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      tc::mbar_wait(d_full + as, aph);
+      tc::fence_after_sync();
+#pragma unroll 1
+      for (int ch = 0; ch < BG_N / 32; ++ch) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BG_N + ch * 32, v);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+          float* o = out + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + row;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[(size_t)j * Nc] = __uint_as_float(v[j]) * rs;
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(d_empty + as);
     }
   }
 
   tc::fence_before_sync();
   tc::cluster_sync_all();
-  if (warp == 5) {
+  if (warp == 9) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
   }
@@ -479,8 +519,11 @@ int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
-// CTAs (= partial-sum slots) of the forward kernel: row tiles per pair rounded up to the cluster size 2
-extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) { return B * (((desc_nc_pad(Nc) / BM) + 1) & ~1); }
+// partial-sum slots of the forward kernel: one per (item, cluster rank, epilogue warp)
+extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) {
+  int ncp = desc_nc_pad(Nc);
+  return B * (ncp / (2 * BM)) * (ncp / BN) * 2 * 8;
+}
 
 // Ahi/Alo: packed planes of `descriptors`, Bhi/Blo: packed planes of `descriptors_warped`
 // ([B, Nc_pad, 256] bf16).  Alo == Blo == NULL selects single-pass bf16; otherwise bf16x3.
@@ -504,7 +547,10 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   if ((rc = make_plane_map(&mBh, Bhi, rows, BN / 2))) return rc;  // half boxes: each CTA of a cluster fetches one half
   if ((rc = make_plane_map(&mAl, Alo ? Alo : Ahi, rows, BM))) return rc;
   if ((rc = make_plane_map(&mBl, Blo ? Blo : Bhi, rows, BN / 2))) return rc;
-  int grid = ssp_desc_dense_tc_nblocks(B, g.Nc);
+  // persistent: one 2-CTA cluster per SM pair (or fewer when there is less work)
+  long long items = (long long)B * (g.Nc_pad / (2 * BM)) * (g.Nc_pad / BN);
+  int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
+  int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FWD(PP, BB)                                                                                   \
   do {                                                                                                       \
@@ -520,11 +566,13 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
 }
 
 // out[b, d, r] = rowscale[b, r] * sum_k bit(r, k) * (Bhi + Blo)[b, k, d]      (out is [B, 256, Nc] fp32)
+// plist / pcoef / possrc are accepted for ABI stability and must be NULL: the sparse positive pairs are applied by
+// ssp_desc_pos_apply after the GEMM.
 extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
                                      const int* plist, const float* pcoef, const float* possrc, int B, int Nc,
                                      float* out, void* stream) {
   SSP_REQUIRE(bits && Bhi && out, "ssp_desc_bits_gemm_tc: null pointer");
-  SSP_REQUIRE(!plist || (pcoef && possrc), "ssp_desc_bits_gemm_tc: plist needs pcoef and possrc");
+  SSP_REQUIRE(!plist && !pcoef && !possrc, "ssp_desc_bits_gemm_tc: positive-pair lists are applied by ssp_desc_pos_apply");
   SSP_REQUIRE(B > 0 && Nc > 0, "ssp_desc_bits_gemm_tc: bad sizes");
   SSP_REQUIRE((((uintptr_t)Bhi | (uintptr_t)Blo) & 15) == 0, "ssp_desc_bits_gemm_tc: operands must be 16-byte aligned");
   int Nc_pad = desc_nc_pad(Nc);
@@ -533,16 +581,18 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   int rc;
   if ((rc = make_plane_map(&mh, Bhi, rows, KT / 2))) return rc;  // half boxes (cluster multicast)
   if ((rc = make_plane_map(&ml, Blo ? Blo : Bhi, rows, KT / 2))) return rc;
-  int grid = B * (((Nc_pad / BM) + 1) & ~1);
+  long long items = (long long)B * (Nc_pad / (2 * BM)) * 2;
+  int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
+  int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
   if (Blo) {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, mh, ml, bits, rowscale, plist,
-                              pcoef, possrc, Nc, Nc_pad, out))) return rc;
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, mh, ml, bits, rowscale, B, Nc,
+                              Nc_pad, out))) return rc;
   } else {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, mh, ml, bits, rowscale, plist,
-                              pcoef, possrc, Nc, Nc_pad, out))) return rc;
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, mh, ml, bits, rowscale, B, Nc,
+                              Nc_pad, out))) return rc;
   }
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;
