@@ -293,8 +293,9 @@ template <int P> struct BgCfg {
 template <int P>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale, int B, int Nc, int Nc_pad,
-                         float* __restrict__ out) {
+                         const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
+                         const int* __restrict__ plist, const float* __restrict__ pcoef, const float* __restrict__ possrc,
+                         int B, int Nc, int Nc_pad, float* __restrict__ out) {
   using Cfg = BgCfg<P>;
   constexpr int NS = Cfg::NS;
   extern __shared__ uint8_t smem_raw[];
@@ -306,6 +307,12 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   uint64_t* d_full = s_free + NS;
   uint64_t* d_empty = d_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
+  // 4 indicator bits -> 4 bf16 {0,1} (two 32-bit TMEM columns); 16 entries x 8 B cover all 32 banks exactly once
+  uint2* lut = reinterpret_cast<uint2*>(tmem_ptr + 2);
+  if (threadIdx.x < 16) {
+    uint32_t x = threadIdx.x;
+    lut[x] = make_uint2((x & 1u) * 0x3F80u + ((x >> 1) & 1u) * 0x3F800000u, ((x >> 2) & 1u) * 0x3F80u + ((x >> 3) & 1u) * 0x3F800000u);
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MP = Nc_pad / (2 * BM), NK = Nc_pad / KT, NW = Nc_pad / 32;
@@ -406,9 +413,10 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
         tc::fence_after_sync();
         uint32_t r[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          r[i] = ((w0 >> (2 * i)) & 1u) * 0x3F80u + ((w0 >> (2 * i + 1)) & 1u) * 0x3F800000u;
-          r[16 + i] = ((w1 >> (2 * i)) & 1u) * 0x3F80u + ((w1 >> (2 * i + 1)) & 1u) * 0x3F800000u;
+        for (int i = 0; i < 8; ++i) {
+          uint2 e0 = lut[(w0 >> (4 * i)) & 15u], e1 = lut[(w1 >> (4 * i)) & 15u];
+          r[2 * i] = e0.x; r[2 * i + 1] = e0.y;
+          r[16 + 2 * i] = e1.x; r[16 + 2 * i + 1] = e1.y;
         }
         tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
         tc::tmem_st_wait();
@@ -427,6 +435,17 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       const bool row_ok = row < Nc;
       float rs = 1.f;
       if (rowscale && row_ok) rs = rowscale[(size_t)b * Nc_pad + row];
+      // sparse positive pairs of this row (and removal of their negative term, see desc_pos_coef_kernel): their
+      // gathers hide behind the next item's main loop because this epilogue runs on its own warps
+      const int* pl = plist ? plist + ((size_t)b * Nc_pad + row) * DESC_MAXP : nullptr;
+      const float* pcf = plist ? pcoef + ((size_t)b * Nc_pad + row) * DESC_MAXP : nullptr;
+      int npos = 0;
+      if (pl && row_ok) {
+#pragma unroll
+        for (int n = 0; n < DESC_MAXP; ++n)
+          if (pl[n] >= 0) npos = n + 1;
+      }
+      const int nmax = __reduce_max_sync(0xffffffffu, npos);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       tc::mbar_wait(d_full + as, aph);
@@ -437,9 +456,21 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BG_N + ch * 32, v);
         tc::tmem_ld_wait();
         if (row_ok) {
+          float val[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]) * rs;
+#pragma unroll 1
+          for (int n = 0; n < nmax; ++n) {
+            int pc = n < npos ? pl[n] : -1;
+            if (pc < 0) continue;
+            float pf = pcf[n];
+            const float* ps = possrc + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + pc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
+          }
           float* o = out + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + row;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[(size_t)j * Nc] = __uint_as_float(v[j]) * rs;
+          for (int j = 0; j < 32; ++j) o[(size_t)j * Nc] = val[j];
         }
       }
       tc::fence_before_sync();
@@ -566,13 +597,12 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
 }
 
 // out[b, d, r] = rowscale[b, r] * sum_k bit(r, k) * (Bhi + Blo)[b, k, d]      (out is [B, 256, Nc] fp32)
-// plist / pcoef / possrc are accepted for ABI stability and must be NULL: the sparse positive pairs are applied by
-// ssp_desc_pos_apply after the GEMM.
+//                + sum_n pcoef[b, r, n] * possrc[b, d, plist[b, r, n]]   (sparse positive pairs; plist may be NULL)
 extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
                                      const int* plist, const float* pcoef, const float* possrc, int B, int Nc,
                                      float* out, void* stream) {
   SSP_REQUIRE(bits && Bhi && out, "ssp_desc_bits_gemm_tc: null pointer");
-  SSP_REQUIRE(!plist && !pcoef && !possrc, "ssp_desc_bits_gemm_tc: positive-pair lists are applied by ssp_desc_pos_apply");
+  SSP_REQUIRE(!plist || (pcoef && possrc), "ssp_desc_bits_gemm_tc: plist needs pcoef and possrc");
   SSP_REQUIRE(B > 0 && Nc > 0, "ssp_desc_bits_gemm_tc: bad sizes");
   SSP_REQUIRE((((uintptr_t)Bhi | (uintptr_t)Blo) & 15) == 0, "ssp_desc_bits_gemm_tc: operands must be 16-byte aligned");
   int Nc_pad = desc_nc_pad(Nc);
@@ -587,12 +617,12 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (Blo) {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, mh, ml, bits, rowscale, B, Nc,
-                              Nc_pad, out))) return rc;
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, mh, ml, bits, rowscale, plist, pcoef,
+                              possrc, B, Nc, Nc_pad, out))) return rc;
   } else {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, mh, ml, bits, rowscale, B, Nc,
-                              Nc_pad, out))) return rc;
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, mh, ml, bits, rowscale, plist, pcoef,
+                              possrc, B, Nc, Nc_pad, out))) return rc;
   }
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;

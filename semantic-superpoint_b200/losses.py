@@ -223,27 +223,25 @@ class DescriptorLossFn(torch.autograd.Function):
             Slo = torch.empty_like(Shi) if split else None
         # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
         # dDw[b,:,c] = alpha[c] sum_r I[r,c] D[b,:,r]  + sum_n colcoef[c,n] D [b,:,colrow[c,n]]
-        # stream plan:  [pos_coef]      ||  [pack(alpha*Dw) -> GEMM dD]
-        #               [pos_apply dD]  ||  [GEMM dDw]          then pos_apply dDw
+        # tensor-core engines: the positive pairs are applied inside the GEMM epilogues (dedicated epilogue warps hide
+        # the gathers behind the next item's main loop); fp32 engine: one streaming apply kernel after the GEMMs.
+        # stream plan:  [pos_coef]  ||  [pack(alpha * Dw)]  ->  GEMM dD  ->  GEMM dDw
         with _Fork(dev) as f1:
             call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
                  ptr(mv_pad), ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(coefs[1]), stream_of(Dc))
         if tc_engine:
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
-            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, None, None, None, B, Nc, ptr(dD), st)
+            f1.join()
+            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc), B, Nc,
+                 ptr(dD), st)
+            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc), B, Nc,
+                 ptr(dDw), st)
         else:
             call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
-        f1.join()
-        with _Fork(dev) as f2:  # ordered after the dD GEMM and the coefficients
-            call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 1,
-                 ptr(dD), ptr(dDw), stream_of(Dc))
-        if tc_engine:
-            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), None, None, None, B, Nc, ptr(dDw), st)
-        else:
             call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
-        call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 2,
-             ptr(dD), ptr(dDw), st)
-        f2.join()
+            f1.join()
+            call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 0,
+                 ptr(dD), ptr(dDw), st)
         return dD, dDw, None, None, None, None, None, None, None, None
 
 
