@@ -19,9 +19,10 @@
 // (pair, row-tile pair, channel half) items:
 //   warps 0-3   expand 64 indicator bits per row into bf16 {0,1} and tcgen05.st them as the A
 //               operand into TMEM (A never touches shared memory)
-//   warps 4-7   epilogue of the previous item (double-buffered 128-column accumulators)
-//   warp 8      TMA producer of B tiles [64 cells x 128 channels] (MN-major, SWIZZLE_128B, multicast)
-//   warp 9      MMA issuer, M=128 N=128 K=16, A from TMEM
+//   warps 4-11  epilogue of the previous item (double-buffered 128-column accumulators), incl. the sparse
+//               positive-pair terms
+//   warp 12     TMA producer of B tiles [64 cells x 128 channels] (MN-major, SWIZZLE_128B, multicast)
+//   warp 13     MMA issuer, M=128 N=128 K=16, A from TMEM
 #include "desc_common.cuh"
 #include "tc_ptx.cuh"
 #include <algorithm>
@@ -278,7 +279,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 constexpr int KT = 64;                       // cells (GEMM K) per stage
 constexpr int BG_BOX_BYTES = KT * 128;       // one [64 cells x 64 channels] box = 8 KB
 constexpr int BG_N = 128;                    // channels per work item (half of the descriptor)
-constexpr int BG_THREADS = 320;              // 4 expander warps, 4 epilogue warps, TMA producer, MMA issuer
+constexpr int BG_THREADS = 448;              // warps 0-3 expanders, 4-11 epilogue, 12 TMA producer, 13 MMA issuer
 
 template <int P> struct BgCfg {
   static constexpr int NS = (P == 1) ? 6 : 4;
@@ -322,14 +323,14 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   const int it0 = (int)(T * cid / ncluster), it1 = (int)(T * (cid + 1) / ncluster);
   constexpr uint32_t A_COL0 = 256;  // TMEM: accumulators at columns [0,128) and [128,256), then NS x 32 columns of A
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     tc::prefetch_tmap(&tmB_hi);
     if (P == 2) tc::prefetch_tmap(&tmB_lo);
   }
-  if (warp == 9) {
+  if (warp == 13) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(a_full + s, 128); tc::mbar_init(s_free + s, 2); }
-      for (int s = 0; s < 2; ++s) { tc::mbar_init(d_full + s, 1); tc::mbar_init(d_empty + s, 4); }
+      for (int s = 0; s < 2; ++s) { tc::mbar_init(d_full + s, 1); tc::mbar_init(d_empty + s, 8); }
       tc::fence_barrier_init();
     }
     __syncwarp();
@@ -340,7 +341,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int st_it = 0;
@@ -363,7 +364,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BG_N, 0, 1);  // A K-major (TMEM), B MN-major
@@ -425,8 +426,9 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       }
     }
   } else {
-    // ------------------------------ epilogue warps 4..7 ------------------------------
-    const int q = warp & 3;
+    // ------------------------------ epilogue warps 4..11 ------------------------------
+    // two warps per TMEM lane quadrant, each draining two of the four 32-column chunks of the accumulator
+    const int q = warp & 3, chalf = (warp - 4) >> 2;
     int tcount = 0;
     for (int it = it0; it < it1; ++it, ++tcount) {
       const int key = it >> 1, dh = it & 1;
@@ -451,7 +453,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       tc::mbar_wait(d_full + as, aph);
       tc::fence_after_sync();
 #pragma unroll 1
-      for (int ch = 0; ch < BG_N / 32; ++ch) {
+      for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
         uint32_t v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BG_N + ch * 32, v);
         tc::tmem_ld_wait();
@@ -481,7 +483,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
 
   tc::fence_before_sync();
   tc::cluster_sync_all();
-  if (warp == 9) {
+  if (warp == 13) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
   }
