@@ -405,24 +405,37 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       const int b = key / MP, mp = key - b * MP;
       const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
       const uint32_t* brow = bits + (size_t)b * NW * Nc_pad + row;
-      for (int kc = 0; kc < NK; ++kc, ++st_it) {
-        int s = st_it % NS;
-        uint32_t ph = (st_it / NS) & 1;
-        uint32_t w0 = __ldg(brow + (size_t)(kc * 2) * Nc_pad);
-        uint32_t w1 = __ldg(brow + (size_t)(kc * 2 + 1) * Nc_pad);
-        tc::mbar_wait(s_free + s, ph ^ 1);
-        tc::fence_after_sync();
-        uint32_t r[32];
+      // indicator words are fetched four stages (8 words) ahead: the loads of group g+1 are in flight while group g
+      // is expanded, so the HBM/L2 latency of the bit matrix never sits on the per-stage critical path
+      uint32_t cur[8], nxt[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint2 e0 = lut[(w0 >> (4 * i)) & 15u], e1 = lut[(w1 >> (4 * i)) & 15u];
-          r[2 * i] = e0.x; r[2 * i + 1] = e0.y;
-          r[16 + 2 * i] = e1.x; r[16 + 2 * i + 1] = e1.y;
+      for (int u = 0; u < 8; ++u) cur[u] = __ldg(brow + (size_t)u * Nc_pad);
+      for (int kc0 = 0; kc0 < NK; kc0 += 4) {  // NK = Nc_pad / 64 is a multiple of 4
+        if (kc0 + 4 < NK) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) nxt[u] = __ldg(brow + (size_t)((kc0 + 4) * 2 + u) * Nc_pad);
         }
-        tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
-        tc::tmem_st_wait();
-        tc::fence_before_sync();
-        tc::mbar_arrive(a_full + s);
+#pragma unroll
+        for (int u = 0; u < 4; ++u, ++st_it) {
+          int s = st_it % NS;
+          uint32_t ph = (st_it / NS) & 1;
+          const uint32_t w0 = cur[2 * u], w1 = cur[2 * u + 1];
+          tc::mbar_wait(s_free + s, ph ^ 1);
+          tc::fence_after_sync();
+          uint32_t r[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint2 e0 = lut[(w0 >> (4 * i)) & 15u], e1 = lut[(w1 >> (4 * i)) & 15u];
+            r[2 * i] = e0.x; r[2 * i + 1] = e0.y;
+            r[16 + 2 * i] = e1.x; r[16 + 2 * i + 1] = e1.y;
+          }
+          tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
+          tc::tmem_st_wait();
+          tc::fence_before_sync();
+          tc::mbar_arrive(a_full + s);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
       }
     }
   } else {
