@@ -291,8 +291,9 @@ def run_ours(args):
         "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
         "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
         "ssp_desc_pos_coef": ("hbm", 8.0 * B * NC * 16 * 4),
-        "ssp_detector_loss_fwd": ("hbm", B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
-        "ssp_detector_loss_bwd": ("hbm", B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+        "ssp_detector_loss_fwd_pair": ("hbm", 2 * B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+        "ssp_detector_loss_bwd_pair": ("hbm", 2 * B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+        "ssp_desc_pack2": ("hbm", 2 * B * NC * DCH * 4 * 2.0),
     }
     bound_tbl["ssp_desc_pos_apply"] = ("hbm", 2.0 * 3.0 * B * NC * DCH * 4)
     # the roofline is reported for the dominant KERNEL of the dense contraction / its data movement

@@ -57,6 +57,15 @@ int ssp_detector_loss_fwd(const float* semi /*[B,65,Hc,Wc]*/, const float* targe
                           int Wc, int fused2d, float* out3, void* ws, size_t ws_bytes, void* stream);
 int ssp_detector_loss_bwd(const float* semi, const float* target, const float* mask, int B, int Hc, int Wc,
                           int fused2d, const float* fwd_out3, const float* gout /*[1]*/, float* dsemi, void* stream);
+/* both losses of a training pair (image, warped image) in one launch; ws = 2 regions of ws_bytes rounded up to 16;
+ * cellmask1 (optional, [B,Hc,Wc]) receives getMasks() of problem 1 as a by-product */
+int ssp_detector_loss_fwd_pair(const float* semi0, const float* target0, const float* mask0, const float* semi1,
+                               const float* target1, const float* mask1, int B, int Hc, int Wc, int fused2d,
+                               float* out3_0, float* out3_1, float* cellmask1, void* ws, size_t ws_bytes, void* stream);
+int ssp_detector_loss_bwd_pair(const float* semi0, const float* target0, const float* mask0, const float* semi1,
+                               const float* target1, const float* mask1, int B, int Hc, int Wc, int fused2d,
+                               const float* fwd0, const float* fwd1, const float* gout0, const float* gout1,
+                               float* dsemi0, float* dsemi1, void* stream);
 
 /* ---- a6: flattenDetection (utils/utils.py:515-560) ---- */
 int ssp_flatten_detection(const float* semi /*[N,65,Hc,Wc]*/, int N, int Hc, int Wc, float* heat /*[N,1,8Hc,8Wc]*/,
@@ -97,6 +106,8 @@ int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* mv_pad
                             float* dbgS /*[B,Nc,Nc] or NULL*/, void* stream);
 int ssp_desc_pack(const float* src /*[B,Dch,Nc]*/, const float* scale /*[B,Nc_pad] or NULL*/, int B, int Dch, int Nc,
                   void* hi /*bf16 [B,Nc_pad,Dch]*/, void* lo /*or NULL*/, void* stream);
+int ssp_desc_pack2(const float* src0, const float* src1 /*or NULL*/, const float* scale, int B, int Dch, int Nc, void* hi0,
+                   void* lo0, void* hi1, void* lo1, void* stream);
 int ssp_desc_dense_tc_nblocks(int B, int Nc);
 int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
                           int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,

@@ -33,6 +33,8 @@ SIGNATURES = {
     "ssp_detector_loss_ws_bytes": (_Z, [_I, _I, _I]),
     "ssp_detector_loss_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "ssp_detector_loss_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ssp_detector_loss_fwd_pair": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "ssp_detector_loss_bwd_pair": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "ssp_flatten_detection": (_I, [_P, _I, _I, _I, _P, _P]),
     "ssp_combine_heatmap": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ssp_nms_ws_bytes": (_Z, [_I, _I, _I, _I]),
@@ -46,6 +48,7 @@ SIGNATURES = {
     "ssp_desc_dense_simt_nblocks": (_I, [_I, _I]),
     "ssp_desc_dense_fwd_simt": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "ssp_desc_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "ssp_desc_pack2": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
     "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P]),

@@ -438,9 +438,14 @@ extern "C" int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const
 // ----------------------------------------------------------------------------------------------
 #define PK_CELLS 32
 __global__ void __launch_bounds__(256)
-desc_pack_kernel(const float* __restrict__ src, const float* __restrict__ scale, int Dch, int Nc, int Nc_pad,
-                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+desc_pack_kernel(const float* __restrict__ src0, const float* __restrict__ src1, const float* __restrict__ scale,
+                 int Dch, int Nc, int Nc_pad, __nv_bfloat16* __restrict__ hi0, __nv_bfloat16* __restrict__ lo0,
+                 __nv_bfloat16* __restrict__ hi1, __nv_bfloat16* __restrict__ lo1) {
   extern __shared__ float tile[];  // [PK_CELLS][Dch + 1]
+  // blockIdx.z selects one of up to two tensors packed by the same launch
+  const float* __restrict__ src = blockIdx.z ? src1 : src0;
+  __nv_bfloat16* __restrict__ hi = blockIdx.z ? hi1 : hi0;
+  __nv_bfloat16* __restrict__ lo = blockIdx.z ? lo1 : lo0;
   int b = blockIdx.y;
   int c0 = blockIdx.x * PK_CELLS;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -465,16 +470,22 @@ desc_pack_kernel(const float* __restrict__ src, const float* __restrict__ scale,
   }
 }
 
-extern "C" int ssp_desc_pack(const float* src, const float* scale, int B, int Dch, int Nc, void* hi, void* lo,
-                             void* stream) {
-  SSP_REQUIRE(src && hi, "ssp_desc_pack: null pointer");
+// Packs one (src1 == NULL) or two tensors in one launch; `scale` applies to both.
+extern "C" int ssp_desc_pack2(const float* src0, const float* src1, const float* scale, int B, int Dch, int Nc, void* hi0,
+                              void* lo0, void* hi1, void* lo1, void* stream) {
+  SSP_REQUIRE(src0 && hi0 && (!src1 || hi1), "ssp_desc_pack: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0, "ssp_desc_pack: bad sizes");
   int Nc_pad = desc_nc_pad(Nc);
   size_t smem = (size_t)PK_CELLS * (Dch + 1) * sizeof(float);
   SSP_REQUIRE(smem <= 48 * 1024, "ssp_desc_pack: descriptor dim %d too large", Dch);
-  dim3 grid(Nc_pad / PK_CELLS, B);
-  desc_pack_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, scale, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi,
-                                                              (__nv_bfloat16*)lo);
+  dim3 grid(Nc_pad / PK_CELLS, B, src1 ? 2 : 1);
+  desc_pack_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src0, src1, scale, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi0,
+                                                              (__nv_bfloat16*)lo0, (__nv_bfloat16*)hi1, (__nv_bfloat16*)lo1);
   SSP_CUDA_CHECK_LAUNCH("desc_pack_kernel");
   return SSP_OK;
+}
+
+extern "C" int ssp_desc_pack(const float* src, const float* scale, int B, int Dch, int Nc, void* hi, void* lo,
+                             void* stream) {
+  return ssp_desc_pack2(src, nullptr, scale, B, Dch, Nc, hi, lo, nullptr, nullptr, stream);
 }

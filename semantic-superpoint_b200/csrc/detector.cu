@@ -225,13 +225,35 @@ __device__ __forceinline__ void det_target(DetShared& sh, const float* __restric
   }
 }
 
+// One launch serves up to two independent losses (image and warped image of a training pair): blockIdx.y selects
+// the problem.  Halves the number of launches / latency chains of the loss step.
+struct DetProblem {
+  const float* semi;
+  const float* target;
+  const float* mask;
+  double* partials;
+  unsigned int* counter;
+  float* out;          // forward: out3; backward: dsemi
+  float* cellmask;     // forward only, optional: per-cell mask product [B,Hc,Wc] (= getMasks), else nullptr
+  const float* fwd_out;  // backward only
+  const float* gout;     // backward only
+};
+struct DetProblems {
+  DetProblem p[2];
+};
+
 // FUSED2D = 0: target [B,65,Hc,Wc] and mask [B,Hc,Wc] are given (reference call signature).
 // FUSED2D = 1: target/mask are built on the fly from labels_2D / mask_2D [B,1,H,W].
 template <int FUSED2D>
 __global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
-detector_loss_fwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
-                         const float* __restrict__ mask, int B, int Hc, int Wc, double* __restrict__ partials,
-                         unsigned int* __restrict__ counter, float* __restrict__ out) {
+detector_loss_fwd_kernel(const __grid_constant__ DetProblems probs, int B, int Hc, int Wc) {
+  const DetProblem& pr = probs.p[blockIdx.y];
+  const float* __restrict__ semi = pr.semi;
+  const float* __restrict__ target = pr.target;
+  const float* __restrict__ mask = pr.mask;
+  double* __restrict__ partials = pr.partials;
+  unsigned int* __restrict__ counter = pr.counter;
+  float* __restrict__ out = pr.out;
   __shared__ DetShared sh;
   int Nc = Hc * Wc;
   int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -250,6 +272,7 @@ detector_loss_fwd_kernel(const float* __restrict__ semi, const float* __restrict
   if (valid && grp == 0) {
     acc[0] = (double)(bce * mk);
     acc[1] = (double)mk;
+    if (pr.cellmask) pr.cellmask[cell] = mk;
   }
   double tot[2];
   if (block_reduce_publish<2>(acc, partials, counter, tot)) {
@@ -265,9 +288,14 @@ detector_loss_fwd_kernel(const float* __restrict__ semi, const float* __restrict
 // d semi = gout * mask/den * softmax_bwd( (p - t) / max(p (1-p), 1e-12) )
 template <int FUSED2D>
 __global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
-detector_loss_bwd_kernel(const float* __restrict__ semi, const float* __restrict__ target,
-                         const float* __restrict__ mask, int B, int Hc, int Wc, const float* __restrict__ fwd_out,
-                         const float* __restrict__ gout, float* __restrict__ dsemi) {
+detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int Hc, int Wc) {
+  const DetProblem& pr = probs.p[blockIdx.y];
+  const float* __restrict__ semi = pr.semi;
+  const float* __restrict__ target = pr.target;
+  const float* __restrict__ mask = pr.mask;
+  const float* __restrict__ fwd_out = pr.fwd_out;
+  const float* __restrict__ gout = pr.gout;
+  float* __restrict__ dsemi = pr.out;
   __shared__ DetShared sh;
   int Nc = Hc * Wc;
   int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -302,44 +330,90 @@ extern "C" size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc) {
   return 16 + nblk * 2 * sizeof(double);
 }
 
+static int det_check(const char* who, const float* semi, const float* target, const float* mask, int B, int Hc, int Wc,
+                     int fused2d) {
+  SSP_REQUIRE(semi && target && mask, "%s: null pointer", who);
+  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "%s: bad sizes B=%d Hc=%d Wc=%d", who, B, Hc, Wc);
+  if (fused2d)
+    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0, "%s: 2-D label/mask pointers must be 16-byte aligned", who);
+  return SSP_OK;
+}
+
+// Forward of one (semi1 == NULL) or two losses in one launch.  ws holds one region of ssp_detector_loss_ws_bytes per
+// problem.  cellmask1 (optional) receives the per-cell mask product of problem 1 (the descriptor loss's mask_valid).
+extern "C" int ssp_detector_loss_fwd_pair(const float* semi0, const float* target0, const float* mask0,
+                                          const float* semi1, const float* target1, const float* mask1, int B, int Hc,
+                                          int Wc, int fused2d, float* out3_0, float* out3_1, float* cellmask1, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  int rc;
+  if ((rc = det_check("ssp_detector_loss_fwd", semi0, target0, mask0, B, Hc, Wc, fused2d))) return rc;
+  int np = semi1 ? 2 : 1;
+  if (np == 2 && (rc = det_check("ssp_detector_loss_fwd", semi1, target1, mask1, B, Hc, Wc, fused2d))) return rc;
+  SSP_REQUIRE(out3_0 && ws && (np == 1 || out3_1), "ssp_detector_loss_fwd: null pointer");
+  size_t per = (ssp_detector_loss_ws_bytes(B, Hc, Wc) + 15) / 16 * 16;
+  SSP_REQUIRE(ws_bytes >= per * np, "ssp_detector_loss_fwd: workspace too small");
+  SSP_REQUIRE(((uintptr_t)ws & 15) == 0, "ssp_detector_loss_fwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  DetProblems pb = {};
+  for (int i = 0; i < np; ++i) {
+    char* w = (char*)ws + per * i;
+    pb.p[i].semi = i ? semi1 : semi0;
+    pb.p[i].target = i ? target1 : target0;
+    pb.p[i].mask = i ? mask1 : mask0;
+    pb.p[i].counter = (unsigned int*)w;
+    pb.p[i].partials = (double*)(w + 16);
+    pb.p[i].out = i ? out3_1 : out3_0;
+    pb.p[i].cellmask = i ? cellmask1 : nullptr;
+    SSP_CUDA_CALL(cudaMemsetAsync(w, 0, 16, st));
+  }
+  dim3 grid(ssp_ceil_div(B * Hc * Wc, DET_CELLS), np);
+  if (fused2d)
+    detector_loss_fwd_kernel<1><<<grid, 128, 0, st>>>(pb, B, Hc, Wc);
+  else
+    detector_loss_fwd_kernel<0><<<grid, 128, 0, st>>>(pb, B, Hc, Wc);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_fwd_kernel");
+  return SSP_OK;
+}
+
 extern "C" int ssp_detector_loss_fwd(const float* semi, const float* target, const float* mask, int B, int Hc,
                                      int Wc, int fused2d, float* out3, void* ws, size_t ws_bytes, void* stream) {
-  SSP_REQUIRE(semi && target && mask && out3 && ws, "ssp_detector_loss_fwd: null pointer");
-  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_fwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
-  SSP_REQUIRE(ws_bytes >= ssp_detector_loss_ws_bytes(B, Hc, Wc), "ssp_detector_loss_fwd: workspace too small");
-  SSP_REQUIRE(((uintptr_t)ws & 15) == 0, "ssp_detector_loss_fwd: workspace must be 16-byte aligned");
-  if (fused2d)
-    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
-                "ssp_detector_loss_fwd: 2-D label/mask pointers must be 16-byte aligned");
+  return ssp_detector_loss_fwd_pair(semi, target, mask, nullptr, nullptr, nullptr, B, Hc, Wc, fused2d, out3, nullptr,
+                                    nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ssp_detector_loss_bwd_pair(const float* semi0, const float* target0, const float* mask0,
+                                          const float* semi1, const float* target1, const float* mask1, int B, int Hc,
+                                          int Wc, int fused2d, const float* fwd0, const float* fwd1, const float* gout0,
+                                          const float* gout1, float* dsemi0, float* dsemi1, void* stream) {
+  int rc;
+  if ((rc = det_check("ssp_detector_loss_bwd", semi0, target0, mask0, B, Hc, Wc, fused2d))) return rc;
+  int np = semi1 ? 2 : 1;
+  if (np == 2 && (rc = det_check("ssp_detector_loss_bwd", semi1, target1, mask1, B, Hc, Wc, fused2d))) return rc;
+  SSP_REQUIRE(fwd0 && gout0 && dsemi0 && (np == 1 || (fwd1 && gout1 && dsemi1)), "ssp_detector_loss_bwd: null pointer");
+  DetProblems pb = {};
+  for (int i = 0; i < np; ++i) {
+    pb.p[i].semi = i ? semi1 : semi0;
+    pb.p[i].target = i ? target1 : target0;
+    pb.p[i].mask = i ? mask1 : mask0;
+    pb.p[i].out = i ? dsemi1 : dsemi0;
+    pb.p[i].fwd_out = i ? fwd1 : fwd0;
+    pb.p[i].gout = i ? gout1 : gout0;
+  }
+  dim3 grid(ssp_ceil_div(B * Hc * Wc, DET_CELLS), np);
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned int* counter = (unsigned int*)ws;
-  double* partials = (double*)((char*)ws + 16);
-  SSP_CUDA_CALL(cudaMemsetAsync(counter, 0, 16, st));
-  int nblk = ssp_ceil_div(B * Hc * Wc, DET_CELLS);
   if (fused2d)
-    detector_loss_fwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
+    detector_loss_bwd_kernel<1><<<grid, 128, 0, st>>>(pb, B, Hc, Wc);
   else
-    detector_loss_fwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, partials, counter, out3);
-  SSP_CUDA_CHECK_LAUNCH("detector_loss_fwd_kernel");
+    detector_loss_bwd_kernel<0><<<grid, 128, 0, st>>>(pb, B, Hc, Wc);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_bwd_kernel");
   return SSP_OK;
 }
 
 extern "C" int ssp_detector_loss_bwd(const float* semi, const float* target, const float* mask, int B, int Hc,
                                      int Wc, int fused2d, const float* fwd_out3, const float* gout, float* dsemi,
                                      void* stream) {
-  SSP_REQUIRE(semi && target && mask && fwd_out3 && gout && dsemi, "ssp_detector_loss_bwd: null pointer");
-  SSP_REQUIRE(B > 0 && Hc > 0 && Wc > 0, "ssp_detector_loss_bwd: bad sizes B=%d Hc=%d Wc=%d", B, Hc, Wc);
-  if (fused2d)
-    SSP_REQUIRE((((uintptr_t)target | (uintptr_t)mask) & 15) == 0,
-                "ssp_detector_loss_bwd: 2-D label/mask pointers must be 16-byte aligned");
-  int nblk = ssp_ceil_div(B * Hc * Wc, DET_CELLS);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (fused2d)
-    detector_loss_bwd_kernel<1><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
-  else
-    detector_loss_bwd_kernel<0><<<nblk, 128, 0, st>>>(semi, target, mask, B, Hc, Wc, fwd_out3, gout, dsemi);
-  SSP_CUDA_CHECK_LAUNCH("detector_loss_bwd_kernel");
-  return SSP_OK;
+  return ssp_detector_loss_bwd_pair(semi, target, mask, nullptr, nullptr, nullptr, B, Hc, Wc, fused2d, fwd_out3, nullptr, gout,
+                                    nullptr, dsemi, nullptr, stream);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -106,6 +106,53 @@ class DetectorLossFn(torch.autograd.Function):
         return dsemi, None, None, None, None
 
 
+class DetectorLossPairFn(torch.autograd.Function):
+    """Both detector losses of a training pair (image, warped image) in ONE launch each way, plus getMasks() of the
+    warped mask as a by-product (it is the descriptor loss's mask_valid).  Returns (loss, loss_warp, cell_mask_warp)."""
+
+    @staticmethod
+    def forward(ctx, semi, target, mask, semi_w, target_w, mask_w, fused2d, dist_group=None):
+        _lib.require_cuda(semi, semi_w)
+        dev = semi.device
+        x0, t0, m0 = f32c(semi.detach(), dev), f32c(target.detach(), dev), f32c(mask.detach(), dev)
+        x1, t1, m1 = f32c(semi_w.detach(), dev), f32c(target_w.detach(), dev), f32c(mask_w.detach(), dev)
+        B, C, Hc, Wc = x0.shape
+        if C != 65 or x1.shape != x0.shape:
+            raise RuntimeError("detector_loss: inputs must be two [B,65,Hc,Wc] tensors of the same shape")
+        n2d = B * Hc * Wc * 64
+        for t, m in ((t0, m0), (t1, m1)):
+            ok = (t.numel() == n2d and m.numel() == n2d) if fused2d else (t.shape == x0.shape and m.numel() == B * Hc * Wc)
+            if not ok:
+                raise RuntimeError("detector_loss: target / mask shapes do not match the logits")
+        out = torch.empty((2, 3), dtype=torch.float32, device=dev)
+        cellmask = torch.empty((B, Hc, Wc), dtype=torch.float32, device=dev)
+        per = (_lib.load().ssp_detector_loss_ws_bytes(B, Hc, Wc) + 15) // 16 * 16
+        ws = torch.empty((2 * per,), dtype=torch.uint8, device=dev)
+        call("ssp_detector_loss_fwd_pair", ptr(x0), ptr(t0), ptr(m0), ptr(x1), ptr(t1), ptr(m1), B, Hc, Wc,
+             1 if fused2d else 0, ptr(out[0]), ptr(out[1]), ptr(cellmask), ptr(ws), 2 * per, stream_of(x0))
+        if dist_group is not None:
+            from .dist import globalize_detector
+            globalize_detector(out[0], dist_group)
+            globalize_detector(out[1], dist_group)
+        ctx.save_for_backward(x0, t0, m0, x1, t1, m1, out)
+        ctx.fused2d = fused2d
+        ctx.mark_non_differentiable(cellmask)
+        return out[0, 0], out[1, 0], cellmask
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g0, g1, _gm):
+        x0, t0, m0, x1, t1, m1, out = ctx.saved_tensors
+        B, C, Hc, Wc = x0.shape
+        dev = x0.device
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g = torch.stack([(a if a is not None else zero).reshape(()).to(torch.float32) for a in (g0, g1)]).contiguous()
+        d0, d1 = torch.empty_like(x0), torch.empty_like(x1)
+        call("ssp_detector_loss_bwd_pair", ptr(x0), ptr(t0), ptr(m0), ptr(x1), ptr(t1), ptr(m1), B, Hc, Wc,
+             1 if ctx.fused2d else 0, ptr(out[0]), ptr(out[1]), ptr(g[0:1]), ptr(g[1:2]), ptr(d0), ptr(d1), stream_of(x0))
+        return d0, None, None, d1, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 def _nc_pad(nc):
     return (nc + 255) // 256 * 256
@@ -173,8 +220,7 @@ class DescriptorLossFn(torch.autograd.Function):
             call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
                  ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
         else:
-            call("ssp_desc_pack", ptr(Dc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), st)
-            call("ssp_desc_pack", ptr(Dwc), None, B, Dch, Nc, ptr(Bhi), ptr(Blo), st)
+            call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
             call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
                  ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             planes = (Ahi, Alo)

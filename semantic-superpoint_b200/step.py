@@ -14,27 +14,17 @@ def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2
     """Returns dict(loss, loss_det, loss_det_warp, loss_desc, positive_dist, negative_dist).
 
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc   (uniform weighting, Train_model_heatmap_all.py:361-365)
-    side_stream: run the two detector losses (forward and, through autograd, backward) on this stream so that their
-    HBM-bound kernels overlap the tensor-core descriptor kernels (used by GraphedLossStep, where buffer lifetimes are
-    static; in eager mode the caller must keep the inputs alive until the streams are joined).
+    side_stream: unused (kept for compatibility).
     """
-    if side_stream is not None:
-        cur = torch.cuda.current_stream()
-        side_stream.wait_stream(cur)
-        with torch.cuda.stream(side_stream):
-            loss_det = U.detector_loss_2d(semi, labels_2D, mask_2D, dist_group=dist_group)
-            loss_det_warp = U.detector_loss_2d(semi_warp, warped_labels, mask_warp_2D, dist_group=dist_group)
-    else:
-        loss_det = U.detector_loss_2d(semi, labels_2D, mask_2D, dist_group=dist_group)
-        loss_det_warp = U.detector_loss_2d(semi_warp, warped_labels, mask_warp_2D, dist_group=dist_group)
-    mask_desc = U.getMasks(mask_warp_2D, 8, device=semi.device).unsqueeze(1)
+    # both detector losses in one launch each way; getMasks(mask_warp_2D) comes out of the same kernel
+    loss_det, loss_det_warp, mask_cells = U.detector_loss_pair_2d(semi, labels_2D, mask_2D, semi_warp, warped_labels,
+                                                                  mask_warp_2D, dist_group=dist_group)
+    mask_desc = mask_cells.unsqueeze(1)
     kw = {"dist_group": dist_group}
     if engine is not None:
         kw["engine"] = engine
     loss_desc, _mask, pos, neg = U.descriptor_loss(desc, desc_warp, mat_H, mask_valid=mask_desc, device=semi.device,
                                                    lamda_d=lamda_d, descriptor_dist=descriptor_dist, **kw)
-    if side_stream is not None:
-        torch.cuda.current_stream().wait_stream(side_stream)
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc
     return {"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
             "positive_dist": pos, "negative_dist": neg}
@@ -69,8 +59,6 @@ class GraphedLossStep(object):
 
     def __init__(self, example, overlap=True, **kw):
         self.kw = kw
-        if overlap and kw.get("dist_group") is None:
-            self.kw["side_stream"] = torch.cuda.Stream()
         self.static = {k: example[k].detach().clone() for k in self.IN_KEYS}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import call, f32c, ptr, stream_of
-from .losses import DescriptorLossFn, DetectorLossFn, LazyPairMask, get_descriptor_engine
+from .losses import DescriptorLossFn, DetectorLossFn, DetectorLossPairFn, LazyPairMask, get_descriptor_engine
 
 __all__ = [
     "warp_points", "filter_points", "warp_points_filter", "warp_keypoints", "inv_warp_image_batch", "inv_warp_image",
@@ -277,6 +277,13 @@ def detector_loss_2d(semi, labels_2D, mask_2D, dist_group=None):
     """Fused labels2Dto3D(add_dustbin=True) + getMasks + detector_loss from the 2-D maps (one kernel)."""
     _lib.require_cuda(semi)
     return DetectorLossFn.apply(semi, labels_2D, mask_2D, True, dist_group)
+
+
+def detector_loss_pair_2d(semi, labels_2D, mask_2D, semi_warp, warped_labels, mask_warp_2D, dist_group=None):
+    """Both detector losses of a training pair from the 2-D maps in one launch each way.
+    Returns (loss_det, loss_det_warp, mask_3D_flattened of the warped mask [B,Hc,Wc])."""
+    _lib.require_cuda(semi, semi_warp)
+    return DetectorLossPairFn.apply(semi, labels_2D, mask_2D, semi_warp, warped_labels, mask_warp_2D, True, dist_group)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -132,6 +132,17 @@ def test_detector_loss(golden):
         close(semi_f.grad, g[grad_k], atol=1e-7)
 
 
+def test_detector_loss_pair(golden):
+    """Both losses of a training pair in one launch == the two single-loss launches == the reference."""
+    g = golden("detector")
+    a = cu(g["semi"]).requires_grad_(True)
+    b = cu(g["semi2"]).requires_grad_(True)
+    la, lb, cm = S.detector_loss_pair_2d(a, cu(g["lab_bin"]), cu(g["mask2d"]), b, cu(g["lab_soft"]), cu(g["mask2d"]))
+    close(la, g["loss"]); close(lb, g["loss2"]); close(cm, g["mask3d"], atol=0)
+    (la + 2.5 * lb).backward()
+    close(a.grad, g["dsemi"], atol=1e-7); close(b.grad, g["dsemi2"], atol=1e-7)
+
+
 def test_detector_loss_240x320():
     B = 4
     semi = synth.pseudo_normal((B, 65, 30, 40), 7) * 2
