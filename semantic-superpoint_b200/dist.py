@@ -37,13 +37,49 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class DeferredExchange(object):
+    """Launches the tiny all-reduces asynchronously and applies their fix-ups later, so that the exchange of one loss
+    overlaps the kernels of the next (the reductions only gate the final loss values and the backward scales).
+    Pass an instance as `dist_group`; call finish() before the losses are used."""
+
+    def __init__(self, group=True):
+        self.group = group
+        self.pending = []
+
+    def all_reduce(self, sums, fixup):
+        work = tdist.all_reduce(sums, op=tdist.ReduceOp.SUM, group=_group(self.group), async_op=True)
+        self.pending.append((work, fixup))
+
+    def finish(self):
+        for work, fixup in self.pending:
+            work.wait()
+            fixup()
+        self.pending = []
+
+
+def _reduce(sums, group, fixup):
+    if isinstance(group, DeferredExchange):
+        group.all_reduce(sums, fixup)
+    else:
+        tdist.all_reduce(sums, op=tdist.ReduceOp.SUM, group=_group(group))
+        fixup()
+
+
+def _world(group):
+    g = group.group if isinstance(group, DeferredExchange) else group
+    return tdist.get_world_size(_group(g))
+
+
 def globalize_detector(out3, group):
     """out3 = [loss, numerator, sum(mask) + 1e-5] of the local shard -> same triple for the global batch."""
     sums = torch.stack((out3[1], out3[2] - 1e-5))
-    tdist.all_reduce(sums, op=tdist.ReduceOp.SUM, group=_group(group))
-    out3[1] = sums[0]
-    out3[2] = sums[1] + 1e-5
-    out3[0] = out3[1] / out3[2]
+
+    def fixup():
+        out3[1] = sums[0]
+        out3[2] = sums[1] + 1e-5
+        out3[0] = out3[1] / out3[2]
+
+    _reduce(sums, group, fixup)
     return out3
 
 
@@ -51,12 +87,15 @@ def globalize_descriptor(out8, B_local, Hc, Wc, group):
     """out8 = [loss, pos, neg, norm, num_loss, num_pos, num_neg, sum(mask_valid)] of the local shard -> global batch.
     norm_global = B_global * (sum_global(mask_valid) + 1) * Hc * Wc  (utils/utils.py:886-887)."""
     sums = out8[4:8].clone()
-    tdist.all_reduce(sums, op=tdist.ReduceOp.SUM, group=_group(group))
-    world = tdist.get_world_size(_group(group))
-    norm = float(B_local * world) * (sums[3] + 1.0) * float(Hc * Wc)
-    out8[3] = norm
-    out8[0:3] = sums[0:3] / norm
-    out8[4:8] = sums
+    world = _world(group)
+
+    def fixup():
+        norm = float(B_local * world) * (sums[3] + 1.0) * float(Hc * Wc)
+        out8[3] = norm
+        out8[0:3] = sums[0:3] / norm
+        out8[4:8] = sums
+
+    _reduce(sums, group, fixup)
     return out8
 
 

@@ -90,14 +90,16 @@ class DetectorLossFn(torch.autograd.Function):
         if dist_group is not None:
             from .dist import globalize_detector
             globalize_detector(out3, dist_group)
-        ctx.save_for_backward(x, t, m, out3)
+        ctx.save_for_backward(x, t, m)
+        ctx.out3 = out3  # attribute, not a saved tensor: a deferred exchange patches it in place after forward
         ctx.fused2d = fused2d
         return out3[0]
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout):
-        x, t, m, out3 = ctx.saved_tensors
+        x, t, m = ctx.saved_tensors
+        out3 = ctx.out3
         B, C, Hc, Wc = x.shape
         g = f32c(gout.reshape(1), x.device)
         dsemi = torch.empty_like(x)
@@ -134,7 +136,8 @@ class DetectorLossPairFn(torch.autograd.Function):
             from .dist import globalize_detector
             globalize_detector(out[0], dist_group)
             globalize_detector(out[1], dist_group)
-        ctx.save_for_backward(x0, t0, m0, x1, t1, m1, out)
+        ctx.save_for_backward(x0, t0, m0, x1, t1, m1)
+        ctx.out = out  # see DetectorLossFn
         ctx.fused2d = fused2d
         ctx.mark_non_differentiable(cellmask)
         return out[0, 0], out[1, 0], cellmask
@@ -142,7 +145,8 @@ class DetectorLossPairFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g0, g1, _gm):
-        x0, t0, m0, x1, t1, m1, out = ctx.saved_tensors
+        x0, t0, m0, x1, t1, m1 = ctx.saved_tensors
+        out = ctx.out
         B, C, Hc, Wc = x0.shape
         dev = x0.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
@@ -234,8 +238,9 @@ class DescriptorLossFn(torch.autograd.Function):
             globalize_descriptor(out8, B, Hc, Wc, dist_group)
 
         if need_grad:
-            ctx.save_for_backward(Dc, Dwc, mv_pad, out8, bitsR, bitsC, lists_i, lists_f,
+            ctx.save_for_backward(Dc, Dwc, mv_pad, bitsR, bitsC, lists_i, lists_f,
                                   *( [planes[0]] + ([planes[1]] if planes[1] is not None else []) if planes else []))
+            ctx.out8 = out8  # see DetectorLossFn
         ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
         ctx.mark_non_differentiable(wpts)
         return out8[0], out8[1], out8[2], wpts
@@ -244,7 +249,8 @@ class DescriptorLossFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g_loss, g_pos, g_neg, _g_wpts):
         saved = ctx.saved_tensors
-        Dc, Dwc, mv_pad, out8, bitsR, bitsC, lists_i, lists_f = saved[:8]
+        Dc, Dwc, mv_pad, bitsR, bitsC, lists_i, lists_f = saved[:7]
+        out8 = ctx.out8
         B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, split = ctx.meta
         dev = Dc.device
         Nc = Hc * Wc
@@ -263,8 +269,8 @@ class DescriptorLossFn(torch.autograd.Function):
         dDw = torch.empty_like(Dwc)
         tc_engine = engine != "fp32"
         if tc_engine:
-            Ahi = saved[8]
-            Alo = saved[9] if split else None
+            Ahi = saved[7]
+            Alo = saved[8] if split else None
             Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Slo = torch.empty_like(Shi) if split else None
         # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]

@@ -16,6 +16,10 @@ def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc   (uniform weighting, Train_model_heatmap_all.py:361-365)
     side_stream: unused (kept for compatibility).
     """
+    # multi-GPU: the global-normaliser all-reduces are launched asynchronously and overlap the following kernels
+    if dist_group is not None:
+        from .dist import DeferredExchange
+        dist_group = DeferredExchange(dist_group)
     # both detector losses in one launch each way; getMasks(mask_warp_2D) comes out of the same kernel
     loss_det, loss_det_warp, mask_cells = U.detector_loss_pair_2d(semi, labels_2D, mask_2D, semi_warp, warped_labels,
                                                                   mask_warp_2D, dist_group=dist_group)
@@ -25,6 +29,8 @@ def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2
         kw["engine"] = engine
     loss_desc, _mask, pos, neg = U.descriptor_loss(desc, desc_warp, mat_H, mask_valid=mask_desc, device=semi.device,
                                                    lamda_d=lamda_d, descriptor_dist=descriptor_dist, **kw)
+    if dist_group is not None:
+        dist_group.finish()
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc
     return {"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
             "positive_dist": pos, "negative_dist": neg}

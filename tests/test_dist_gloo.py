@@ -29,7 +29,7 @@ def _inputs():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as tdist
-    from ssp_b200.dist import globalize_descriptor, globalize_detector, init_from_env, shard_range
+    from ssp_b200.dist import DeferredExchange, globalize_descriptor, globalize_detector, init_from_env, shard_range
     init_from_env(backend="gloo")
     Hs, D, Dw, mv, semi, lab, m3 = _inputs()
     lo, hi = shard_range(B, rank, world)
@@ -42,6 +42,15 @@ def _worker(rank, world, port, q):
     den = np.float32(m3[lo:hi].sum() + 1e-5)
     out3 = torch.tensor([ld, ld * den, den], dtype=torch.float32)
     globalize_detector(out3, True)
+    # the deferred (asynchronous) exchange used by step.loss_step must give the same numbers
+    ex = DeferredExchange(True)
+    out8d = torch.tensor([l, p, n, norm, l * norm, p * norm, n * norm, mv[lo:hi].sum()], dtype=torch.float32)
+    out3d = torch.tensor([ld, ld * den, den], dtype=torch.float32)
+    globalize_detector(out3d, ex)
+    globalize_descriptor(out8d, hi - lo, HC, WC, ex)
+    assert len(ex.pending) == 2
+    ex.finish()
+    assert torch.equal(out8d, out8) and torch.equal(out3d, out3)
     q.put((rank, out8.numpy().copy(), out3.numpy().copy()))
     tdist.barrier()
     tdist.destroy_process_group()
