@@ -70,30 +70,37 @@ def _world(group):
     return tdist.get_world_size(_group(g))
 
 
-def globalize_detector(out3, group):
-    """out3 = [loss, numerator, sum(mask) + 1e-5] of the local shard -> same triple for the global batch."""
+def globalize_detector(out3, group, after=None):
+    """out3 = [loss, numerator, sum(mask) + 1e-5] of the local shard -> same triple for the global batch.
+    `after` (optional callable) runs once the global values are in place (immediately, or at DeferredExchange.finish)."""
     sums = torch.stack((out3[1], out3[2] - 1e-5))
 
     def fixup():
-        out3[1] = sums[0]
-        out3[2] = sums[1] + 1e-5
-        out3[0] = out3[1] / out3[2]
+        with torch.no_grad():
+            out3[1] = sums[0]
+            out3[2] = sums[1] + 1e-5
+            out3[0] = out3[1] / out3[2]
+            if after is not None:
+                after()
 
     _reduce(sums, group, fixup)
     return out3
 
 
-def globalize_descriptor(out8, B_local, Hc, Wc, group):
+def globalize_descriptor(out8, B_local, Hc, Wc, group, after=None):
     """out8 = [loss, pos, neg, norm, num_loss, num_pos, num_neg, sum(mask_valid)] of the local shard -> global batch.
     norm_global = B_global * (sum_global(mask_valid) + 1) * Hc * Wc  (utils/utils.py:886-887)."""
     sums = out8[4:8].clone()
     world = _world(group)
 
     def fixup():
-        norm = float(B_local * world) * (sums[3] + 1.0) * float(Hc * Wc)
-        out8[3] = norm
-        out8[0:3] = sums[0:3] / norm
-        out8[4:8] = sums
+        with torch.no_grad():
+            norm = float(B_local * world) * (sums[3] + 1.0) * float(Hc * Wc)
+            out8[3] = norm
+            out8[0:3] = sums[0:3] / norm
+            out8[4:8] = sums
+            if after is not None:
+                after()
 
     _reduce(sums, group, fixup)
     return out8

@@ -87,13 +87,16 @@ class DetectorLossFn(torch.autograd.Function):
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         call("ssp_detector_loss_fwd", ptr(x), ptr(t), ptr(m), B, Hc, Wc, 1 if fused2d else 0, ptr(out3), ptr(ws),
              nbytes, stream_of(x))
-        if dist_group is not None:
-            from .dist import globalize_detector
-            globalize_detector(out3, dist_group)
         ctx.save_for_backward(x, t, m)
         ctx.out3 = out3  # attribute, not a saved tensor: a deferred exchange patches it in place after forward
         ctx.fused2d = fused2d
-        return out3[0]
+        if dist_group is None:
+            return out3[0]
+        # multi-GPU: the returned scalar is its own tensor (not a view of out3), refreshed when the exchange completes
+        from .dist import globalize_detector
+        res = out3[0].clone()
+        globalize_detector(out3, dist_group, after=lambda: res.copy_(out3[0]))
+        return res
 
     @staticmethod
     @once_differentiable
@@ -132,15 +135,17 @@ class DetectorLossPairFn(torch.autograd.Function):
         ws = torch.empty((2 * per,), dtype=torch.uint8, device=dev)
         call("ssp_detector_loss_fwd_pair", ptr(x0), ptr(t0), ptr(m0), ptr(x1), ptr(t1), ptr(m1), B, Hc, Wc,
              1 if fused2d else 0, ptr(out[0]), ptr(out[1]), ptr(cellmask), ptr(ws), 2 * per, stream_of(x0))
-        if dist_group is not None:
-            from .dist import globalize_detector
-            globalize_detector(out[0], dist_group)
-            globalize_detector(out[1], dist_group)
         ctx.save_for_backward(x0, t0, m0, x1, t1, m1)
         ctx.out = out  # see DetectorLossFn
         ctx.fused2d = fused2d
         ctx.mark_non_differentiable(cellmask)
-        return out[0, 0], out[1, 0], cellmask
+        if dist_group is None:
+            return out[0, 0], out[1, 0], cellmask
+        from .dist import globalize_detector
+        r0, r1 = out[0, 0].clone(), out[1, 0].clone()
+        globalize_detector(out[0], dist_group, after=lambda: r0.copy_(out[0, 0]))
+        globalize_detector(out[1], dist_group, after=lambda: r1.copy_(out[1, 0]))
+        return r0, r1, cellmask
 
     @staticmethod
     @once_differentiable
@@ -233,9 +238,16 @@ class DescriptorLossFn(torch.autograd.Function):
         if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
             raise RuntimeError("descriptor_loss: %d positive pairs overflowed the per-column lists" % int(colcnt[B * Ncp]))
         call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(out8), st)
+        res = None
         if dist_group is not None:
             from .dist import globalize_descriptor
-            globalize_descriptor(out8, B, Hc, Wc, dist_group)
+            res = [out8[i].clone() for i in range(3)]  # own tensors (not views), refreshed when the exchange completes
+
+            def refresh():
+                for i in range(3):
+                    res[i].copy_(out8[i])
+
+            globalize_descriptor(out8, B, Hc, Wc, dist_group, after=refresh)
 
         if need_grad:
             ctx.save_for_backward(Dc, Dwc, mv_pad, bitsR, bitsC, lists_i, lists_f,
@@ -243,6 +255,8 @@ class DescriptorLossFn(torch.autograd.Function):
             ctx.out8 = out8  # see DetectorLossFn
         ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
         ctx.mark_non_differentiable(wpts)
+        if res is not None:
+            return res[0], res[1], res[2], wpts
         return out8[0], out8[1], out8[2], wpts
 
     @staticmethod
