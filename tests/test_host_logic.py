@@ -93,3 +93,33 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF), reason="reference checkout only exists in the authoring container")
+def test_signatures_match_live_reference_and_dropin_binds():
+    """Where the reference is available: same parameter names / defaults as its own callables, and install() binds over
+    the real `utils.utils` module (then restores it)."""
+    import importlib
+    import inspect
+    import sys
+    sys.path.insert(0, REF)
+    try:
+        RU = importlib.import_module("utils.utils")
+        for name in S.dropin.UTILS_NAMES:
+            ref_sig, our_sig = inspect.signature(getattr(RU, name)), inspect.signature(getattr(S.utils, name))
+            ref_p = [(p.name, p.default) for p in ref_sig.parameters.values() if p.kind != p.VAR_KEYWORD]
+            our_p = [(p.name, p.default) for p in our_sig.parameters.values() if p.kind != p.VAR_KEYWORD]
+            assert our_p[:len(ref_p)] == ref_p, name  # ours may only append optional extras
+            assert all(d is not inspect.Parameter.empty for _, d in our_p[len(ref_p):]), name
+        orig = RU.descriptor_loss
+        bound = S.dropin.install(utils_module=RU)
+        assert RU.descriptor_loss is S.utils.descriptor_loss and len(bound) >= len(S.dropin.UTILS_NAMES)
+        S.dropin.uninstall()
+        assert RU.descriptor_loss is orig
+    finally:
+        sys.path.remove(REF)
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[m]
