@@ -171,49 +171,64 @@ extern "C" int ssp_inv_warp_image(const float* img, int B, int C, int H, int W, 
 // ----------------------------------------------------------------------------------------------
 // a3: compute_valid_mask = nearest-warp of an all-ones image, then cv2.erode with an explicit
 // structuring element (taps that fall outside the image are ignored = cv2's default +inf border).
-// Fused: a 32x32 output tile computes the raw in-bounds predicate for tile+halo into shared memory
+// Fused: a 32x32 output tile computes the raw in-bounds predicate for tile+halo into shared memory (bit packed)
 // and takes the min over the kernel taps there; nothing but the final mask touches HBM.
 // ----------------------------------------------------------------------------------------------
 #define VM_TILE 32
+// Rows of the tile + halo are packed into 64-bit words (bit = column) by warp ballots; the erosion of one output
+// pixel is then kh shift / and / compare steps against the per-row masks of the structuring element instead of
+// kh*kw byte reads.  Needs VM_TILE + kw - 1 <= 64, i.e. kw <= 33 (erosion radius <= 16).
 __global__ void __launch_bounds__(256)
 valid_mask_kernel(int H, int W, const float* __restrict__ Hinv, const float* __restrict__ xs,
                   const float* __restrict__ ys, const uint8_t* __restrict__ kern, int kh, int kw, int ax, int ay,
                   float* __restrict__ out) {
-  extern __shared__ uint8_t raw[];  // (VM_TILE + kh - 1) x (VM_TILE + kw - 1), 1 = valid or outside image
+  __shared__ unsigned long long rowbits[VM_TILE + 64];  // one word per tile+halo row, 1 = valid or outside the image
+  __shared__ unsigned long long kmask[64];              // structuring element rows
   __shared__ float h[9];
-  int b = blockIdx.z;
-  int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   if (tid < 9) h[tid] = Hinv[b * 9 + tid];
+  if (tid < kh) {
+    unsigned long long m = 0ull;
+    for (int kx = 0; kx < kw; ++kx) m |= (unsigned long long)(kern[tid * kw + kx] != 0) << kx;
+    kmask[tid] = m;
+  }
   __syncthreads();
-  int ph = kh > 0 ? kh - 1 : 0, pw = kw > 0 ? kw - 1 : 0;
-  int th = VM_TILE + ph, tw = VM_TILE + pw;
-  int y0 = blockIdx.y * VM_TILE - (kh > 0 ? ay : 0);
-  int x0 = blockIdx.x * VM_TILE - (kw > 0 ? ax : 0);
-  for (int i = tid; i < th * tw; i += 256) {
-    int yy = y0 + i / tw, xx = x0 + i % tw;
-    uint8_t v = 1;  // outside the image: ignored by the erosion
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      float ix, iy;
-      src_coord(h, __ldg(xs + xx), __ldg(ys + yy), H, W, ix, iy);
-      float rx = rintf(ix), ry = rintf(iy);
-      v = (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H) ? 1 : 0;
+  const int ph = kh > 0 ? kh - 1 : 0, pw = kw > 0 ? kw - 1 : 0;
+  const int th = VM_TILE + ph, tw = VM_TILE + pw;
+  const int y0 = blockIdx.y * VM_TILE - (kh > 0 ? ay : 0);
+  const int x0 = blockIdx.x * VM_TILE - (kw > 0 ? ax : 0);
+  for (int r = wrp; r < th; r += 8) {
+    const int yy = y0 + r;
+    unsigned long long word = 0ull;
+    for (int half = 0; half * 32 < tw; ++half) {
+      const int c = half * 32 + lane, xx = x0 + c;
+      bool v = true;  // outside the image (or beyond the halo): ignored by the erosion
+      if (c < tw && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        float ix, iy;
+        src_coord(h, __ldg(xs + xx), __ldg(ys + yy), H, W, ix, iy);
+        float rx = rintf(ix), ry = rintf(iy);
+        v = (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H);
+      }
+      word |= (unsigned long long)__ballot_sync(0xffffffffu, v) << (32 * half);
     }
-    raw[i] = v;
+    if (lane == 0) rowbits[r] = word;
   }
   __syncthreads();
   for (int i = tid; i < VM_TILE * VM_TILE; i += 256) {
-    int ly = i / VM_TILE, lx = i % VM_TILE;
-    int y = blockIdx.y * VM_TILE + ly, x = blockIdx.x * VM_TILE + lx;
+    const int ly = i / VM_TILE, lx = i % VM_TILE;
+    const int y = blockIdx.y * VM_TILE + ly, x = blockIdx.x * VM_TILE + lx;
     if (y >= H || x >= W) continue;
-    uint8_t m = 1;
+    bool m = true;
     if (kh > 0 && kw > 0) {
-      for (int ky = 0; ky < kh; ++ky)
-        for (int kx = 0; kx < kw; ++kx)
-          if (kern[ky * kw + kx]) m &= raw[(ly + ky) * tw + (lx + kx)];
+      for (int ky = 0; ky < kh; ++ky) {
+        const unsigned long long km = kmask[ky];
+        m = m && (((rowbits[ly + ky] >> lx) & km) == km);
+      }
     } else {
-      m = raw[ly * tw + lx];
+      m = (rowbits[ly] >> lx) & 1ull;
     }
-    out[((size_t)b * H + y) * W + x] = (float)m;
+    out[((size_t)b * H + y) * W + x] = m ? 1.f : 0.f;
   }
 }
 
@@ -221,13 +236,12 @@ extern "C" int ssp_valid_mask(int B, int H, int W, const float* Hinv, const floa
                               const uint8_t* kern, int kh, int kw, int ax, int ay, float* out, void* stream) {
   SSP_REQUIRE(Hinv && xs && ys && out, "ssp_valid_mask: null pointer");
   SSP_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "ssp_valid_mask: bad sizes B=%d H=%d W=%d", B, H, W);
-  SSP_REQUIRE((kh == 0 && kw == 0) || (kern && kh > 0 && kw > 0 && kh <= 64 && kw <= 64 && ax >= 0 && ax < kw &&
+  SSP_REQUIRE((kh == 0 && kw == 0) || (kern && kh > 0 && kw > 0 && kh <= 33 && kw <= 33 && ax >= 0 && ax < kw &&
                                        ay >= 0 && ay < kh),
               "ssp_valid_mask: bad structuring element kh=%d kw=%d anchor=(%d,%d)", kh, kw, ax, ay);
   dim3 block(32, 8);
   dim3 grid(ssp_ceil_div(W, VM_TILE), ssp_ceil_div(H, VM_TILE), B);
-  size_t smem = (size_t)(VM_TILE + (kh > 0 ? kh - 1 : 0)) * (VM_TILE + (kw > 0 ? kw - 1 : 0));
-  valid_mask_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(H, W, Hinv, xs, ys, kern, kh, kw, ax, ay, out);
+  valid_mask_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, Hinv, xs, ys, kern, kh, kw, ax, ay, out);
   SSP_CUDA_CHECK_LAUNCH("valid_mask_kernel");
   return SSP_OK;
 }
