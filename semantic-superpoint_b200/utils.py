@@ -22,6 +22,7 @@ __all__ = [
 ]
 
 _grid_cache = {}
+_stencil_cache = {}
 
 
 def _cuda_device(device, *tensors):
@@ -218,8 +219,12 @@ def compute_valid_mask(image_shape, inv_homography, device="cpu", erosion_radius
     out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     kern_t, kh, kw = None, 0, 0
     if kernel is None and erosion_radius > 0:
-        kernel = ellipse_kernel(erosion_radius)
-    if kernel is not None and kernel.size > 0:
+        key = ("ellipse", int(erosion_radius), str(dev))  # device copy of the structuring element, made once
+        if key not in _stencil_cache:
+            k = ellipse_kernel(erosion_radius)
+            _stencil_cache[key] = (torch.from_numpy(k).to(dev), k.shape)
+        kern_t, (kh, kw) = _stencil_cache[key]
+    elif kernel is not None and kernel.size > 0:
         kernel = np.ascontiguousarray(kernel, dtype=np.uint8)
         kh, kw = kernel.shape
         kern_t = torch.from_numpy(kernel).to(dev)
@@ -334,7 +339,6 @@ def combine_heatmap_batch(heatmap, inv_homographies, mask_2D):
 # ------------------------------------------------------------------------------------------------
 # a8 / a9  keypoint extraction
 # ------------------------------------------------------------------------------------------------
-_stencil_cache = {}
 
 
 def _cheb_stencil(R, dev):
