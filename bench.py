@@ -303,8 +303,15 @@ def run_ours(args):
         achieved, peak, unit = work / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
     else:
         achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+    # DRAM traffic of that kernel from the committed ncu --set full capture of this same command (per launch)
+    traffic = None
+    kern_of = {"ssp_desc_bits_gemm_tc": "desc_bits_gemm_tc_kernel", "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
+               "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel"}
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if top in kern_of and os.path.exists(tpath) and args.engine == "bf16x3":
+        traffic = json.load(open(tpath)).get(kern_of[top], {}).get("dram_bytes_per_launch")
     roofline = {"kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
+                "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
                 "us_per_launch": shares[top]["us_per_call"],
                 "note": "algorithmic 2*Nc^2*256 flop per pair x 32 pairs per launch; bf16x3 issues 3 (fwd) / 2 (bwd) MMAs per "
                         "algorithmic MAC, so its ceiling is 1/3 (1/2) of the bf16 peak"}
