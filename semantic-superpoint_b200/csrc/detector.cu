@@ -141,60 +141,33 @@ __device__ __forceinline__ float bce_term(float p, float t) {
 }
 
 struct DetShared {
-  float red[DET_GROUPS][DET_CELLS];
+  float red[3][DET_GROUPS][DET_CELLS];
 };
 
 // combine one value per channel group into the per-cell total (fixed order 0..3), all threads get it
 template <typename Op>
 __device__ __forceinline__ float det_combine(DetShared& sh, float v, int lane, int grp, Op op) {
   __syncthreads();
-  sh.red[grp][lane] = v;
+  sh.red[0][grp][lane] = v;
   __syncthreads();
-  return op(op(sh.red[0][lane], sh.red[1][lane]), op(sh.red[2][lane], sh.red[3][lane]));
+  return op(op(sh.red[0][0][lane], sh.red[0][1][lane]), op(sh.red[0][2][lane], sh.red[0][3][lane]));
 }
 
-// loads this thread's 16 (+1) logits, returns softmax probabilities p[0..15], pd = dustbin probability (grp 3)
-__device__ __forceinline__ void det_softmax(DetShared& sh, const float* __restrict__ semi_cell, size_t Nc, bool valid,
-                                            int lane, int grp, float (&p)[DET_CPG], float& pd) {
-  float m = -INFINITY;
-  pd = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) {
-    p[c] = valid ? __ldg(semi_cell + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
-    m = fmaxf(m, p[c]);
-  }
-  if (grp == 3) {
-    pd = valid ? __ldg(semi_cell + (size_t)64 * Nc) : 0.f;
-    m = fmaxf(m, pd);
-  }
-  m = det_combine(sh, m, lane, grp, [](float a, float b) { return fmaxf(a, b); });
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) {
-    p[c] = expf(p[c] - m);
-    s += p[c];
-  }
-  if (grp == 3) {
-    pd = expf(pd - m);
-    s += pd;
-  }
-  s = det_combine(sh, s, lane, grp, [](float a, float b) { return a + b; });
-#pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) p[c] = p[c] / s;
-  pd = pd / s;
-}
-
-// target / mask of this thread's channels.  FUSED2D: built from the 2-D maps with the reference's dustbin rule.
+// Everything a thread needs, loaded up front so that all global loads of a cell are in flight together:
+// 16 (+1) logits, 16 (+1) target values (raw 2-D labels when FUSED2D) and the mask (partial product when FUSED2D).
 template <int FUSED2D>
-__device__ __forceinline__ void det_target(DetShared& sh, const float* __restrict__ target, const float* __restrict__ mask,
-                                           int b, int ij, int cell, int Hc, int Wc, bool valid, int lane, int grp,
-                                           float (&t)[DET_CPG], float& td, float& mk) {
-  int Nc = Hc * Wc;
+__device__ __forceinline__ void det_load(const float* __restrict__ semi_cell, const float* __restrict__ target,
+                                         const float* __restrict__ mask, int b, int ij, int cell, int Hc, int Wc, bool valid,
+                                         int grp, float (&x)[DET_CPG], float& xd, float (&t)[DET_CPG], float& td, float& mk) {
+  const size_t Nc = (size_t)Hc * Wc;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) x[c] = valid ? __ldg(semi_cell + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
+  xd = (valid && grp == 3) ? __ldg(semi_cell + (size_t)64 * Nc) : -INFINITY;
   td = 0.f;
   if (FUSED2D) {
     int H = Hc * CELL, W = Wc * CELL;
     int y0 = (ij / Wc) * CELL + 2 * grp, x0 = (ij % Wc) * CELL;
-    float mp = 1.f, ls = 0.f;
+    mk = 1.f;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
       float4 a = make_float4(0, 0, 0, 0), c4 = a, ma = make_float4(1, 1, 1, 1), mb = ma;
@@ -205,12 +178,49 @@ __device__ __forceinline__ void det_target(DetShared& sh, const float* __restric
       }
       t[dy * 8 + 0] = a.x; t[dy * 8 + 1] = a.y; t[dy * 8 + 2] = a.z; t[dy * 8 + 3] = a.w;
       t[dy * 8 + 4] = c4.x; t[dy * 8 + 5] = c4.y; t[dy * 8 + 6] = c4.z; t[dy * 8 + 7] = c4.w;
-      mp *= ma.x * ma.y * ma.z * ma.w * mb.x * mb.y * mb.z * mb.w;
+      mk *= ma.x * ma.y * ma.z * ma.w * mb.x * mb.y * mb.z * mb.w;
     }
+  } else {
+    mk = valid ? __ldg(mask + cell) : 0.f;
+    const float* tp = target + (size_t)b * NCH * Nc + ij;
 #pragma unroll
-    for (int c = 0; c < DET_CPG; ++c) ls += t[c];
-    mk = det_combine(sh, mp, lane, grp, [](float a, float b) { return a * b; });
-    float s = det_combine(sh, ls, lane, grp, [](float a, float b) { return a + b; });
+    for (int c = 0; c < DET_CPG; ++c) t[c] = valid ? __ldg(tp + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
+    if (grp == 3) td = valid ? __ldg(tp + (size_t)64 * Nc) : 0.f;
+  }
+}
+
+// softmax probabilities p (in place of the logits), normalised targets and the cell mask: two barrier rounds
+// (max; then exp-sum, label-sum and mask-product together).
+template <int FUSED2D>
+__device__ __forceinline__ void det_prepare(DetShared& sh, int lane, int grp, float (&p)[DET_CPG], float& pd,
+                                            float (&t)[DET_CPG], float& td, float& mk) {
+  float m = pd;  // -inf unless this thread owns the dustbin channel
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) m = fmaxf(m, p[c]);
+  m = det_combine(sh, m, lane, grp, [](float a, float b) { return fmaxf(a, b); });
+  float se = 0.f, ls = 0.f;
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) {
+    p[c] = expf(p[c] - m);
+    se += p[c];
+    ls += t[c];
+  }
+  if (grp == 3) {
+    pd = expf(pd - m);
+    se += pd;
+  }
+  __syncthreads();
+  sh.red[0][grp][lane] = se;
+  sh.red[1][grp][lane] = ls;
+  sh.red[2][grp][lane] = mk;
+  __syncthreads();
+  se = (sh.red[0][0][lane] + sh.red[0][1][lane]) + (sh.red[0][2][lane] + sh.red[0][3][lane]);
+#pragma unroll
+  for (int c = 0; c < DET_CPG; ++c) p[c] = p[c] / se;
+  pd = pd / se;
+  if (FUSED2D) {
+    float s = (sh.red[1][0][lane] + sh.red[1][1][lane]) + (sh.red[1][2][lane] + sh.red[1][3][lane]);
+    mk = (sh.red[2][0][lane] * sh.red[2][1][lane]) * (sh.red[2][2][lane] * sh.red[2][3][lane]);
     // dustbin: d = 1 - sum; d < 1 -> 0; all 65 channels divided by their sum   [utils/utils.py:431-439]
     float dust = 1.f - s;
     if (dust < 1.f) dust = 0.f;
@@ -218,12 +228,6 @@ __device__ __forceinline__ void det_target(DetShared& sh, const float* __restric
 #pragma unroll
     for (int c = 0; c < DET_CPG; ++c) t[c] = t[c] / dn;
     td = dust / dn;
-  } else {
-    mk = valid ? __ldg(mask + cell) : 0.f;
-    const float* tp = target + (size_t)b * NCH * Nc + ij;
-#pragma unroll
-    for (int c = 0; c < DET_CPG; ++c) t[c] = valid ? __ldg(tp + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
-    if (grp == 3) td = valid ? __ldg(tp + (size_t)64 * Nc) : 0.f;
   }
 }
 
@@ -263,8 +267,8 @@ detector_loss_fwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
   bool valid = cell < B * Nc;
   int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
   float p[DET_CPG], t[DET_CPG], pd, td, mk;
-  det_softmax(sh, semi + (size_t)b * NCH * Nc + ij, Nc, valid, lane, grp, p, pd);
-  det_target<FUSED2D>(sh, target, mask, b, ij, cell, Hc, Wc, valid, lane, grp, t, td, mk);
+  det_load<FUSED2D>(semi + (size_t)b * NCH * Nc + ij, target, mask, b, ij, cell, Hc, Wc, valid, grp, p, pd, t, td, mk);
+  det_prepare<FUSED2D>(sh, lane, grp, p, pd, t, td, mk);
   float bce = 0.f;
 #pragma unroll
   for (int c = 0; c < DET_CPG; ++c) bce += bce_term(p[c], t[c]);
@@ -305,8 +309,8 @@ detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
   bool valid = cell < B * Nc;
   int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
   float p[DET_CPG], t[DET_CPG], pd, td, mk;
-  det_softmax(sh, semi + (size_t)b * NCH * Nc + ij, Nc, valid, lane, grp, p, pd);
-  det_target<FUSED2D>(sh, target, mask, b, ij, cell, Hc, Wc, valid, lane, grp, t, td, mk);
+  det_load<FUSED2D>(semi + (size_t)b * NCH * Nc + ij, target, mask, b, ij, cell, Hc, Wc, valid, grp, p, pd, t, td, mk);
+  det_prepare<FUSED2D>(sh, lane, grp, p, pd, t, td, mk);
   float scale = __ldg(gout) * mk / __ldg(fwd_out + 2);
   float dot = 0.f, dpd = 0.f;
 #pragma unroll
