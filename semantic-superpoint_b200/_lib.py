@@ -97,7 +97,7 @@ def check(rc, what):
 
 # kernels launched per entry point (memsets / copies not counted); the NMS drivers launch init + >= 2 rounds +
 # compact + rank, counted at their minimum
-KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4}
+KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2}
 kernel_count = 0
 _prof = None
 

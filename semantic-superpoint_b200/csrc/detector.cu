@@ -258,8 +258,6 @@ detector_loss_fwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
   const float* __restrict__ target = pr.target;
   const float* __restrict__ mask = pr.mask;
   double* __restrict__ partials = pr.partials;
-  unsigned int* __restrict__ counter = pr.counter;
-  float* __restrict__ out = pr.out;
   __shared__ DetShared sh;
   int Nc = Hc * Wc;
   int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -280,14 +278,34 @@ detector_loss_fwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
     acc[1] = (double)mk;
     if (pr.cellmask) pr.cellmask[cell] = mk;
   }
-  double tot[2];
-  if (block_reduce_publish<2>(acc, partials, counter, tot)) {
-    float num = (float)tot[0];
-    float den = (float)tot[1] + 1e-5f;
-    out[0] = num / den;  // loss
-    out[1] = num;
-    out[2] = den;
-    *counter = 0;
+  // per-block partials; a one-block-per-problem finalize kernel sums them in index order (deterministic, and no
+  // same-address atomics: 2400 serialized atomicAdds cost more than the whole streaming pass)
+  __shared__ double shd[32];
+  double r0 = block_sum_d(acc[0], shd);
+  double r1 = block_sum_d(acc[1], shd);
+  if (threadIdx.x == 0) {
+    partials[2 * (size_t)blockIdx.x] = r0;
+    partials[2 * (size_t)blockIdx.x + 1] = r1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+detector_loss_finalize_kernel(const __grid_constant__ DetProblems probs, int nblk) {
+  const DetProblem& pr = probs.p[blockIdx.x];
+  __shared__ double shd[32];
+  double a = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    a += pr.partials[2 * (size_t)i];
+    c += pr.partials[2 * (size_t)i + 1];
+  }
+  a = block_sum_d(a, shd);
+  c = block_sum_d(c, shd);
+  if (threadIdx.x == 0) {
+    float num = (float)a;
+    float den = (float)c + 1e-5f;
+    pr.out[0] = num / den;  // loss
+    pr.out[1] = num;
+    pr.out[2] = den;
   }
 }
 
@@ -370,7 +388,6 @@ extern "C" int ssp_detector_loss_fwd_pair(const float* semi0, const float* targe
     pb.p[i].partials = (double*)(w + 16);
     pb.p[i].out = i ? out3_1 : out3_0;
     pb.p[i].cellmask = i ? cellmask1 : nullptr;
-    SSP_CUDA_CALL(cudaMemsetAsync(w, 0, 16, st));
   }
   dim3 grid(ssp_ceil_div(B * Hc * Wc, DET_CELLS), np);
   if (fused2d)
@@ -378,6 +395,8 @@ extern "C" int ssp_detector_loss_fwd_pair(const float* semi0, const float* targe
   else
     detector_loss_fwd_kernel<0><<<grid, 128, 0, st>>>(pb, B, Hc, Wc);
   SSP_CUDA_CHECK_LAUNCH("detector_loss_fwd_kernel");
+  detector_loss_finalize_kernel<<<np, 256, 0, st>>>(pb, (int)grid.x);
+  SSP_CUDA_CHECK_LAUNCH("detector_loss_finalize_kernel");
   return SSP_OK;
 }
 
