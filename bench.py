@@ -320,6 +320,11 @@ def run_ours(args):
     extra = {}
     if not args.no_adapt:
         extra = bench_adaptation(torch, S, dev, rank, world, sdist, barrier)
+    if not args.no_semantic:
+        try:
+            extra.update(bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, args.steps))
+        except Exception as e:  # auxiliary measurement: never lose the headline line to it
+            extra["with_semantic_head"] = {"error": repr(e)}
 
     if rank == 0:
         cpu = cpu_baseline(8, 2) if world == 1 and not args.no_cpu else None
@@ -347,6 +352,37 @@ def run_ours(args):
         torch.cuda.synchronize()
         sys.stderr.flush()
         os._exit(0)  # skip NCCL / graph teardown: destroying a process group with captured collectives can hang
+
+
+def bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, steps):
+    """Same loss step with the semantic head of the SSp configuration added: two cross entropies over
+    133 classes whose x8 bilinear upsample is fused into the loss (inputs: the 1/8-resolution head outputs + int64 label
+    maps).  Reported next to the headline, which stays the five north-star pieces."""
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    B = dsets[0]["semi"].shape[0]
+    sets = []
+    for d in dsets:
+        e = dict(d)
+        e["sem_pred"] = torch.randn((B, 133, HC, WC), device=dev, generator=gen) * 2
+        e["sem_warp_pred"] = torch.randn((B, 133, HC, WC), device=dev, generator=gen) * 2
+        e["sem"] = torch.randint(0, 134, (B, H_IMG, W_IMG), device=dev, generator=gen)
+        e["warped_sem"] = torch.randint(0, 134, (B, H_IMG, W_IMG), device=dev, generator=gen)
+        sets.append(e)
+    graphs = [S.step.GraphedLossStep(e, dist_group=group) for e in sets]
+    for i in range(3):
+        graphs[i % len(graphs)].replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = graphs[i % len(graphs)].replay()
+    e1.record()
+    barrier()
+    ms = sdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    return {"with_semantic_head": {"pairs_per_s": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                                   "loss": float(out["loss"]), "loss_sem": float(out["loss_sem"]),
+                                   "workload": "detector x2 + descriptor + semantic CE x2 (133 classes, fused x8 upsample), fwd+bwd"}}
 
 
 def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, images_per_step=4, steps=6):
@@ -392,6 +428,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph-multi", action="store_true", help="(default now) kept for compatibility")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-semantic", action="store_true", help="skip the auxiliary step timing with the semantic head")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

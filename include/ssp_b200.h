@@ -136,6 +136,27 @@ int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo
                           const int* plist, const float* pcoef, const float* possrc /*[B,256,Nc]*/, int B, int Nc,
                           float* out /*[B,256,Nc]*/, void* stream);
 
+/* ---- semantic head: cross entropy with ignore_index, optionally fused with the x8 bilinear upsample ------------
+ * (not part of the five north-star pieces, same boundary.)
+ * Replaces Train_model_heatmap_all.py:181-193 (sem_loss = nn.CrossEntropyLoss(ignore_index=133)) and, for the
+ * _up8 entry points, also models/SuperPointNet_gauss2_ssmall.py:90 (F.interpolate(sem, x_hw, "bilinear",
+ * align_corners=False)): the [B,C,H,W] logits never exist.
+ * labels: int64 [B,H,W]; values outside [0,C) other than ignore_index are not counted (the reference asserts).
+ * out3 = { loss = sum / count (NaN when nothing is counted), sum, count }.  ws: ssp_sem_ce_ws_bytes(), 8-byte aligned. */
+size_t ssp_sem_ce_ws_bytes(int B, int C, int H, int W, int upsampled);
+int ssp_sem_ce_fwd(const float* logits /*[B,C,H,W]*/, const long long* labels, int B, int C, int H, int W,
+                   int ignore_index, float* lse2 /*[B,H,W] log2-domain log-sum-exp, kept for the backward*/,
+                   float* out3, void* ws, size_t ws_bytes, void* stream);
+int ssp_sem_ce_bwd(const float* logits, const long long* labels, const float* lse2, int B, int C, int H, int W,
+                   int ignore_index, const float* out3, const float* gout /*device scalar*/,
+                   float* dlogits /*[B,C,H,W]*/, void* stream);
+/* logits_lr [B,C,Hc,Wc], labels [B,8Hc,8Wc], 2 <= C <= 256.  gsum (optional, [B,C,Hc,Wc]) receives the un-normalised
+ * gradient sum_pixels w(pixel,cell) (softmax - onehot); ssp_sem_ce_up8_bwd scales it by gout / count. */
+int ssp_sem_ce_up8(const float* logits_lr, const long long* labels, int B, int C, int Hc, int Wc, int ignore_index,
+                   float* gsum, float* out3, void* ws, size_t ws_bytes, void* stream);
+int ssp_sem_ce_up8_bwd(const float* gsum, const float* out3, const float* gout, int B, int C, int Hc, int Wc,
+                       float* dlogits /*[B,C,Hc,Wc]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -414,3 +414,71 @@ def descriptor_dots(descriptors, descriptors_warped):
     Dw = np.asarray(descriptors_warped, dtype=np.float64)
     B, Dch = D.shape[:2]
     return np.einsum("bdi,bdj->bij", D.reshape(B, Dch, -1), Dw.reshape(B, Dch, -1))
+
+
+# ------------------------------------------------------------------------------------------------
+# semantic head: x8 bilinear upsample + cross entropy  
+# ------------------------------------------------------------------------------------------------
+def _upsample_axis(n_in, n_out):
+    """F.interpolate(mode="bilinear", align_corners=False) source indices / weights along one axis
+    (torch area_pixel_compute_source_index: src = (dst + 0.5) * in/out - 0.5, clamped below at 0)."""
+    scale = f32(n_in) / f32(n_out)
+    src = np.maximum((np.arange(n_out, dtype=f32) + f32(0.5)) * scale - f32(0.5), f32(0))
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    i1 = np.minimum(i0 + 1, n_in - 1)
+    lam = (src - i0.astype(f32)).astype(np.float64)
+    return i0, i1, lam
+
+
+def upsample_bilinear(x, out_hw):
+    """models/SuperPointNet_gauss2_ssmall.py:90  F.interpolate(sem, x_hw, mode="bilinear", align_corners=False).
+    x [B,C,h,w] -> [B,C,H,W] (float64)."""
+    x = np.asarray(x, dtype=np.float64)
+    H, W = out_hw
+    y0, y1, ly = _upsample_axis(x.shape[2], H)
+    x0, x1, lx = _upsample_axis(x.shape[3], W)
+    rows = x[:, :, y0, :] * (1 - ly)[None, None, :, None] + x[:, :, y1, :] * ly[None, None, :, None]
+    return rows[:, :, :, x0] * (1 - lx) + rows[:, :, :, x1] * lx
+
+
+def upsample_bilinear_adjoint(g, in_hw):
+    """Transpose of upsample_bilinear: gradient [B,C,H,W] -> [B,C,h,w]."""
+    g = np.asarray(g, dtype=np.float64)
+    B, C, H, W = g.shape
+    h, w = in_hw
+    y0, y1, ly = _upsample_axis(h, H)
+    x0, x1, lx = _upsample_axis(w, W)
+    cols = np.zeros((B, C, H, w))
+    np.add.at(cols, (slice(None), slice(None), slice(None), x0), g * (1 - lx))
+    np.add.at(cols, (slice(None), slice(None), slice(None), x1), g * lx)
+    out = np.zeros((B, C, h, w))
+    np.add.at(out, (slice(None), slice(None), y0, slice(None)), cols * (1 - ly)[None, None, :, None])
+    np.add.at(out, (slice(None), slice(None), y1, slice(None)), cols * ly[None, None, :, None])
+    return out
+
+
+def sem_loss(pred, label, ignore_index=133, grad=False, gout=1.0):
+    """Train_model_heatmap_all.py:181-193  nn.CrossEntropyLoss(ignore_index=133)(pred [B,C,H,W], label [B,H,W]):
+    mean over the non-ignored pixels of -log_softmax(pred)[label]; nothing counted -> NaN (gradient 0).
+    If pred's spatial size differs from label's it is first upsampled like the model's last line does
+    (SuperPointNet_gauss2_ssmall.py:90) and the gradient is returned with respect to the low-res logits."""
+    pred = np.asarray(pred, dtype=np.float64)
+    label = np.asarray(label).astype(np.int64)
+    lowres = pred.shape[2:] != label.shape[1:]
+    full = upsample_bilinear(pred, label.shape[1:]) if lowres else pred
+    m = full.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(full - m).sum(axis=1))
+    valid = label != ignore_index
+    safe = np.where(valid, label, 0)
+    picked = np.take_along_axis(full, safe[:, None], axis=1)[:, 0]
+    n = int(valid.sum())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        loss = f32(np.where(valid, lse - picked, 0.0).sum() / n) if n else f32(np.nan)
+    if not grad:
+        return loss
+    g = np.exp(full - lse[:, None])
+    np.put_along_axis(g, safe[:, None], np.take_along_axis(g, safe[:, None], axis=1) - 1.0, axis=1)
+    g = g * valid[:, None] * (gout / n if n else 0.0)
+    if lowres:
+        g = upsample_bilinear_adjoint(g, pred.shape[2:])
+    return loss, g.astype(f32)

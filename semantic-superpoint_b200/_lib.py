@@ -58,6 +58,11 @@ SIGNATURES = {
     "ssp_desc_pos_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "ssp_sem_ce_ws_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "ssp_sem_ce_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "ssp_sem_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ssp_sem_ce_up8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "ssp_sem_ce_up8_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -97,7 +102,8 @@ def check(rc, what):
 
 # kernels launched per entry point (memsets / copies not counted); the NMS drivers launch init + >= 2 rounds +
 # compact + rank, counted at their minimum
-KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2}
+KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2,
+                    "ssp_sem_ce_fwd": 2, "ssp_sem_ce_up8": 2}
 kernel_count = 0
 _prof = None
 

@@ -12,34 +12,6 @@
 #define CELL 8
 #define NCH 65
 
-// ---- deterministic two-level reduction: per-block partials -> last block sums in index order ----
-template <int NV>
-__device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double* __restrict__ partials,
-                                                     unsigned int* __restrict__ counter, double (&total)[NV]) {
-  __shared__ double sh[32];
-  __shared__ bool is_last;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double r = block_sum_d(v[i], sh);
-    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * NV + i] = r;
-  }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned int done = atomicAdd(counter, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return false;
-  __threadfence();
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double a = 0.0;
-    for (unsigned int j = threadIdx.x; j < gridDim.x; j += blockDim.x) a += partials[(size_t)j * NV + i];
-    total[i] = block_sum_d(a, sh);
-  }
-  return threadIdx.x == 0;
-}
-
 // ----------------------------------------------------------------------------------------------
 // labels2Dto3D: pixel-unshuffle(8) (+ dustbin + normalisation)
 // ----------------------------------------------------------------------------------------------
@@ -131,14 +103,26 @@ extern "C" int ssp_cell_mask(const float* mask2d, int B, int H, int W, float* ou
 #define DET_GROUPS 4
 #define DET_CPG 16  // channels per group
 
-__device__ __forceinline__ float bce_term(float p, float t) {
-  // nn.BCELoss: log terms clamped at -100.  __logf (MUFU.LG2 based, abs. error ~2^-21.4 for arguments in (0, 2)) keeps
-  // the 65-term cell sum within 1e-6 relative of the libm version at a fifth of the instructions; the kernel is
-  // issue-bound on the 130 logarithms per cell otherwise.
-  float lp = fmaxf(__logf(p), -100.f);
-  float lq = fmaxf(__logf(1.f - p), -100.f);
-  return -(t * lp + (1.f - t) * lq);
+// MUFU-level transcendental helpers.  The loss needs 65 exponentials and 130 logarithms per cell; with libm expf /
+// logf / IEEE divisions the kernels were instruction-bound (1700 SASS instructions per thread, ncu issue-active 63 %,
+// 29 % of the HBM roofline).  ex2.approx / lg2.approx are accurate to 2 ulp, far inside the 1e-4 parity tolerance.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#define DET_LOG2E 1.4426950408889634f
+#define DET_LN2 0.6931471805599453f
 
 struct DetShared {
   float red[3][DET_GROUPS][DET_CELLS];
@@ -159,10 +143,11 @@ template <int FUSED2D>
 __device__ __forceinline__ void det_load(const float* __restrict__ semi_cell, const float* __restrict__ target,
                                          const float* __restrict__ mask, int b, int ij, int cell, int Hc, int Wc, bool valid,
                                          int grp, float (&x)[DET_CPG], float& xd, float (&t)[DET_CPG], float& td, float& mk) {
-  const size_t Nc = (size_t)Hc * Wc;
+  const int Nc = Hc * Wc;  // 32-bit channel offsets: one IMAD.WIDE per load instead of a 64-bit multiply chain
+  const float* __restrict__ sp = semi_cell + (size_t)(grp * DET_CPG) * Nc;
 #pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) x[c] = valid ? __ldg(semi_cell + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
-  xd = (valid && grp == 3) ? __ldg(semi_cell + (size_t)64 * Nc) : -INFINITY;
+  for (int c = 0; c < DET_CPG; ++c) x[c] = valid ? __ldg(sp + c * Nc) : 0.f;
+  xd = (valid && grp == 3) ? __ldg(sp + DET_CPG * Nc) : -INFINITY;
   td = 0.f;
   if (FUSED2D) {
     int H = Hc * CELL, W = Wc * CELL;
@@ -182,32 +167,41 @@ __device__ __forceinline__ void det_load(const float* __restrict__ semi_cell, co
     }
   } else {
     mk = valid ? __ldg(mask + cell) : 0.f;
-    const float* tp = target + (size_t)b * NCH * Nc + ij;
+    const float* __restrict__ tp = target + (size_t)b * NCH * Nc + ij + (size_t)(grp * DET_CPG) * Nc;
 #pragma unroll
-    for (int c = 0; c < DET_CPG; ++c) t[c] = valid ? __ldg(tp + (size_t)(grp * DET_CPG + c) * Nc) : 0.f;
-    if (grp == 3) td = valid ? __ldg(tp + (size_t)64 * Nc) : 0.f;
+    for (int c = 0; c < DET_CPG; ++c) t[c] = valid ? __ldg(tp + c * Nc) : 0.f;
+    if (grp == 3) td = valid ? __ldg(tp + DET_CPG * Nc) : 0.f;
   }
 }
 
-// softmax probabilities p (in place of the logits), normalised targets and the cell mask: two barrier rounds
-// (max; then exp-sum, label-sum and mask-product together).
+// Softmax of the cell in the log2 domain, normalised targets and the cell mask: two barrier rounds (max; then
+// exp-sum, label-sum and mask-product together).  On return
+//   v[c]  = (x_c - max) * log2(e)      (pd likewise for the dustbin channel of group 3)
+//   e[c]  = 2^v[c]                     (ed)
+//   inv_se = 1 / sum_c e_c,  lnse = ln(sum_c e_c)   ->  p_c = e_c * inv_se,  ln p_c = v_c * ln2 - lnse
+//   t[c]  = target / (sum + dustbin)   (FUSED2D; already normalised otherwise),  mk = cell mask
 template <int FUSED2D>
-__device__ __forceinline__ void det_prepare(DetShared& sh, int lane, int grp, float (&p)[DET_CPG], float& pd,
-                                            float (&t)[DET_CPG], float& td, float& mk) {
-  float m = pd;  // -inf unless this thread owns the dustbin channel
+__device__ __forceinline__ void det_prepare(DetShared& sh, int lane, int grp, float (&v)[DET_CPG], float& vd,
+                                            float (&e)[DET_CPG], float& ed, float (&t)[DET_CPG], float& td, float& mk,
+                                            float& inv_se, float& lnse) {
+  float m = vd;  // -inf unless this thread owns the dustbin channel
 #pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) m = fmaxf(m, p[c]);
+  for (int c = 0; c < DET_CPG; ++c) m = fmaxf(m, v[c]);
   m = det_combine(sh, m, lane, grp, [](float a, float b) { return fmaxf(a, b); });
+  const float ms = m * DET_LOG2E;
   float se = 0.f, ls = 0.f;
 #pragma unroll
   for (int c = 0; c < DET_CPG; ++c) {
-    p[c] = expf(p[c] - m);
-    se += p[c];
+    v[c] = fmaf(v[c], DET_LOG2E, -ms);
+    e[c] = fast_ex2(v[c]);
+    se += e[c];
     ls += t[c];
   }
+  ed = 0.f;
   if (grp == 3) {
-    pd = expf(pd - m);
-    se += pd;
+    vd = fmaf(vd, DET_LOG2E, -ms);
+    ed = fast_ex2(vd);
+    se += ed;
   }
   __syncthreads();
   sh.red[0][grp][lane] = se;
@@ -215,9 +209,8 @@ __device__ __forceinline__ void det_prepare(DetShared& sh, int lane, int grp, fl
   sh.red[2][grp][lane] = mk;
   __syncthreads();
   se = (sh.red[0][0][lane] + sh.red[0][1][lane]) + (sh.red[0][2][lane] + sh.red[0][3][lane]);
-#pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) p[c] = p[c] / se;
-  pd = pd / se;
+  inv_se = 1.f / se;
+  lnse = fast_lg2(se) * DET_LN2;
   if (FUSED2D) {
     float s = (sh.red[1][0][lane] + sh.red[1][1][lane]) + (sh.red[1][2][lane] + sh.red[1][3][lane]);
     mk = (sh.red[2][0][lane] * sh.red[2][1][lane]) * (sh.red[2][2][lane] * sh.red[2][3][lane]);
@@ -225,10 +218,22 @@ __device__ __forceinline__ void det_prepare(DetShared& sh, int lane, int grp, fl
     float dust = 1.f - s;
     if (dust < 1.f) dust = 0.f;
     float dn = s + dust;
+    float inv_dn = 1.f / dn;
+    if (dn != 1.f) {  // block-uniform in the common case (binary labels: empty cell or one keypoint)
 #pragma unroll
-    for (int c = 0; c < DET_CPG; ++c) t[c] = t[c] / dn;
-    td = dust / dn;
+      for (int c = 0; c < DET_CPG; ++c) t[c] = t[c] * inv_dn;
+    }
+    td = dust * inv_dn;
   }
+}
+
+// BCE of one channel given e = 2^v: -(t ln p + (1-t) ln(1-p)), both logarithms clamped at -100 like nn.BCELoss.
+// ln p is taken from the logits (v ln2 - ln se), so only ln(1-p) costs a MUFU.
+__device__ __forceinline__ float bce_term(float v, float e, float t, float inv_se, float lnse) {
+  float p = e * inv_se;
+  float lp = fmaxf(fmaf(v, DET_LN2, -lnse), -100.f);
+  float lq = fmaxf(fast_lg2(1.f - p) * DET_LN2, -100.f);
+  return fmaf(t, lq - lp, -lq);
 }
 
 // One launch serves up to two independent losses (image and warped image of a training pair): blockIdx.y selects
@@ -264,28 +269,25 @@ detector_loss_fwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
   int cell = blockIdx.x * DET_CELLS + lane;
   bool valid = cell < B * Nc;
   int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
-  float p[DET_CPG], t[DET_CPG], pd, td, mk;
-  det_load<FUSED2D>(semi + (size_t)b * NCH * Nc + ij, target, mask, b, ij, cell, Hc, Wc, valid, grp, p, pd, t, td, mk);
-  det_prepare<FUSED2D>(sh, lane, grp, p, pd, t, td, mk);
+  float v[DET_CPG], e[DET_CPG], t[DET_CPG], vd, ed, td, mk, inv_se, lnse;
+  det_load<FUSED2D>(semi + (size_t)b * NCH * Nc + ij, target, mask, b, ij, cell, Hc, Wc, valid, grp, v, vd, t, td, mk);
+  det_prepare<FUSED2D>(sh, lane, grp, v, vd, e, ed, t, td, mk, inv_se, lnse);
   float bce = 0.f;
 #pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) bce += bce_term(p[c], t[c]);
-  if (grp == 3) bce += bce_term(pd, td);
+  for (int c = 0; c < DET_CPG; ++c) bce += bce_term(v[c], e[c], t[c], inv_se, lnse);
+  if (grp == 3) bce += bce_term(vd, ed, td, inv_se, lnse);
   bce = det_combine(sh, bce, lane, grp, [](float a, float b) { return a + b; });
-  double acc[2] = {0.0, 0.0};
-  if (valid && grp == 0) {
-    acc[0] = (double)(bce * mk);
-    acc[1] = (double)mk;
-    if (pr.cellmask) pr.cellmask[cell] = mk;
-  }
-  // per-block partials; a one-block-per-problem finalize kernel sums them in index order (deterministic, and no
-  // same-address atomics: 2400 serialized atomicAdds cost more than the whole streaming pass)
-  __shared__ double shd[32];
-  double r0 = block_sum_d(acc[0], shd);
-  double r1 = block_sum_d(acc[1], shd);
-  if (threadIdx.x == 0) {
-    partials[2 * (size_t)blockIdx.x] = r0;
-    partials[2 * (size_t)blockIdx.x + 1] = r1;
+  // per-block partials (32 cells, summed in fp32 by warp 0); a one-block-per-problem finalize kernel adds them in
+  // double, in index order: deterministic, and no same-address atomics.
+  if (grp == 0) {
+    float num = valid ? bce * mk : 0.f, den = valid ? mk : 0.f;
+    if (valid && pr.cellmask) pr.cellmask[cell] = mk;
+    num = warp_sum(num);
+    den = warp_sum(den);
+    if (lane == 0) {
+      partials[2 * (size_t)blockIdx.x] = (double)num;
+      partials[2 * (size_t)blockIdx.x + 1] = (double)den;
+    }
   }
 }
 
@@ -326,27 +328,32 @@ detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
   int cell = blockIdx.x * DET_CELLS + lane;
   bool valid = cell < B * Nc;
   int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
-  float p[DET_CPG], t[DET_CPG], pd, td, mk;
-  det_load<FUSED2D>(semi + (size_t)b * NCH * Nc + ij, target, mask, b, ij, cell, Hc, Wc, valid, grp, p, pd, t, td, mk);
-  det_prepare<FUSED2D>(sh, lane, grp, p, pd, t, td, mk);
-  float scale = __ldg(gout) * mk / __ldg(fwd_out + 2);
-  float dot = 0.f, dpd = 0.f;
+  float v[DET_CPG], e[DET_CPG], t[DET_CPG], vd, ed, td, mk, inv_se, lnse;
+  det_load<FUSED2D>(semi + (size_t)b * NCH * Nc + ij, target, mask, b, ij, cell, Hc, Wc, valid, grp, v, vd, t, td, mk);
+  det_prepare<FUSED2D>(sh, lane, grp, v, vd, e, ed, t, td, mk, inv_se, lnse);
+  // g_c = dBCE/dp_c = (p - t) / max(p (1 - p), 1e-12);  d semi_c = scale * p_c * (g_c - sum_k p_k g_k)
+  float dot = 0.f, gd = 0.f;
 #pragma unroll
   for (int c = 0; c < DET_CPG; ++c) {
-    float dp = scale * (p[c] - t[c]) / fmaxf((1.f - p[c]) * p[c], 1e-12f);
-    t[c] = dp;
-    dot += p[c] * dp;
+    float p = e[c] * inv_se;
+    float g = (p - t[c]) * fast_rcp(fmaxf((1.f - p) * p, 1e-12f));
+    e[c] = p;
+    t[c] = g;
+    dot = fmaf(p, g, dot);
   }
   if (grp == 3) {
-    dpd = scale * (pd - td) / fmaxf((1.f - pd) * pd, 1e-12f);
-    dot += pd * dpd;
+    float p = ed * inv_se;
+    gd = (p - td) * fast_rcp(fmaxf((1.f - p) * p, 1e-12f));
+    ed = p;
+    dot = fmaf(p, gd, dot);
   }
   dot = det_combine(sh, dot, lane, grp, [](float a, float b) { return a + b; });
   if (!valid) return;
-  float* o = dsemi + (size_t)b * NCH * Nc + ij;
+  const float scale = __ldg(gout) * mk / __ldg(fwd_out + 2);
+  float* __restrict__ o = dsemi + (size_t)b * NCH * Nc + ij + (size_t)(grp * DET_CPG) * Nc;
 #pragma unroll
-  for (int c = 0; c < DET_CPG; ++c) o[(size_t)(grp * DET_CPG + c) * Nc] = p[c] * (t[c] - dot);
-  if (grp == 3) o[(size_t)64 * Nc] = pd * (dpd - dot);
+  for (int c = 0; c < DET_CPG; ++c) o[c * Nc] = (e[c] * scale) * (t[c] - dot);
+  if (grp == 3) o[DET_CPG * Nc] = (ed * scale) * (gd - dot);
 }
 
 extern "C" size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc) {

@@ -87,6 +87,21 @@ def globalize_detector(out3, group, after=None):
     return out3
 
 
+def globalize_semantic(out3, group, after=None):
+    """out3 = [loss, sum, count] of the local shard -> global batch (mean over every counted pixel of every rank)."""
+    sums = out3[1:3].clone()
+
+    def fixup():
+        with torch.no_grad():
+            out3[1:3] = sums
+            out3[0] = sums[0] / sums[1]
+            if after is not None:
+                after()
+
+    _reduce(sums, group, fixup)
+    return out3
+
+
 def globalize_descriptor(out8, B_local, Hc, Wc, group, after=None):
     """out8 = [loss, pos, neg, norm, num_loss, num_pos, num_neg, sum(mask_valid)] of the local shard -> global batch.
     norm_global = B_global * (sum_global(mask_valid) + 1) * Hc * Wc  (utils/utils.py:886-887)."""

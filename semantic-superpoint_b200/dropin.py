@@ -32,7 +32,7 @@ def _bind(obj, name, fn, bound):
 
 def install(utils_module=None, trainer_class=None, frontend_class=None, export_module=None):
     """Patch `utils.utils` (imported from sys.path unless given) and, when passed, the trainer class
-    (`Train_model_heatmap_all`: detector_loss, getMasks), the inference front-end class
+    (`Train_model_heatmap_all`: detector_loss, getMasks, sem_loss), the inference front-end class
     (`SuperPointFrontend_torch`: getPtsFromHeatmap, nms_fast) and the `export` module (combine_heatmap)."""
     bound = []
     if utils_module is None:
@@ -44,6 +44,7 @@ def install(utils_module=None, trainer_class=None, frontend_class=None, export_m
               lambda self, input, target, mask=None, loss_type="softmax": _u.detector_loss(input, target, mask, loss_type), bound)
         _bind(trainer_class, "getMasks",
               lambda self, mask_2D, cell_size, device="cpu": _u.getMasks(mask_2D, cell_size, device), bound)
+        _bind(trainer_class, "sem_loss", lambda self, pred, label, device="cpu": _u.sem_loss(pred, label, device), bound)
     if frontend_class is not None:
         _bind(frontend_class, "getPtsFromHeatmap",
               lambda self, heatmap: _u.getPtsFromHeatmap(heatmap, self.conf_thresh, self.nms_dist), bound)

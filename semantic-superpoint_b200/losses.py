@@ -111,6 +111,69 @@ class DetectorLossFn(torch.autograd.Function):
         return dsemi, None, None, None, None
 
 
+class SemanticLossFn(torch.autograd.Function):
+    """Cross entropy of the semantic head with ignore_index (Train_model_heatmap_all.py:181-193).
+
+    pred [B,C,H,W] at the label resolution -> streaming softmax-CE kernels.
+    pred [B,C,H/8,W/8] (the head output before the model's F.interpolate, SuperPointNet_gauss2_ssmall.py:90) -> the x8
+    bilinear upsample is fused into the loss and its backward; the full-resolution logits never exist.
+    With dist_group the mean runs over the counted pixels of the GLOBAL batch (sum and count are all-reduced)."""
+
+    @staticmethod
+    def forward(ctx, pred, label, ignore_index, dist_group=None):
+        _lib.require_cuda(pred)
+        dev = pred.device
+        x = f32c(pred.detach(), dev)
+        lab = label.detach().to(device=dev, dtype=torch.int64).contiguous()
+        if x.dim() != 4 or lab.dim() != 3 or lab.shape[0] != x.shape[0]:
+            raise RuntimeError("sem_loss: expected pred [B,C,h,w] and label [B,H,W], got %s and %s"
+                               % (tuple(pred.shape), tuple(label.shape)))
+        B, C, h, w = x.shape
+        H, W = lab.shape[1:]
+        up = (h, w) != (H, W)
+        if up and (H != 8 * h or W != 8 * w):
+            raise RuntimeError("sem_loss: pred %dx%d must match the label size %dx%d or be exactly 1/8 of it" % (h, w, H, W))
+        out3 = torch.empty((3,), dtype=torch.float32, device=dev)
+        nbytes = _lib.load().ssp_sem_ce_ws_bytes(B, C, H, W, 1 if up else 0)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        need_grad = ctx.needs_input_grad[0]
+        if up:
+            gsum = torch.empty_like(x) if need_grad else None
+            call("ssp_sem_ce_up8", ptr(x), ptr(lab), B, C, h, w, int(ignore_index), ptr(gsum), ptr(out3), ptr(ws), nbytes,
+                 stream_of(x))
+            ctx.saved = (gsum,)
+        else:
+            lse2 = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+            call("ssp_sem_ce_fwd", ptr(x), ptr(lab), B, C, H, W, int(ignore_index), ptr(lse2), ptr(out3), ptr(ws), nbytes,
+                 stream_of(x))
+            ctx.saved = (x, lab, lse2)
+        ctx.up, ctx.shape, ctx.ignore = up, (B, C, h, w), int(ignore_index)
+        ctx.out3 = out3  # attribute, see DetectorLossFn
+        if dist_group is None:
+            return out3[0]
+        from .dist import globalize_semantic
+        res = out3[0].clone()
+        globalize_semantic(out3, dist_group, after=lambda: res.copy_(out3[0]))
+        return res
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        B, C, h, w = ctx.shape
+        out3 = ctx.out3
+        g = f32c(gout.reshape(1), out3.device)
+        if ctx.up:
+            (gsum,) = ctx.saved
+            d = torch.empty_like(gsum)
+            call("ssp_sem_ce_up8_bwd", ptr(gsum), ptr(out3), ptr(g), B, C, h, w, ptr(d), stream_of(d))
+        else:
+            x, lab, lse2 = ctx.saved
+            d = torch.empty_like(x)
+            call("ssp_sem_ce_bwd", ptr(x), ptr(lab), ptr(lse2), B, C, h, w, ctx.ignore, ptr(out3), ptr(g), ptr(d),
+                 stream_of(d))
+        return d, None, None, None
+
+
 class DetectorLossPairFn(torch.autograd.Function):
     """Both detector losses of a training pair (image, warped image) in ONE launch each way, plus getMasks() of the
     warped mask as a by-product (it is the descriptor loss's mask_valid).  Returns (loss, loss_warp, cell_mask_warp)."""

@@ -1,6 +1,7 @@
 """The two hot loops of the reference, expressed over the kernels (no backbone: heads' outputs come in).
 
-loss_step          = Train_model_heatmap_all.train_val_sample lines 295-350 (detector loss x2 + descriptor loss)
+loss_step          = Train_model_heatmap_all.train_val_sample lines 295-365 (detector loss x2 + descriptor loss,
+                     optionally the two semantic cross entropies of the SSp configuration)
 adaptation_step    = export.export_detector_homoAdapt_gpu lines 304-323 (flatten -> aggregate -> NMS -> top-k)
 Both are free of host synchronisation except the final keypoint read-back of adaptation_step.
 """
@@ -10,10 +11,14 @@ from . import utils as U
 
 
 def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2D, mask_warp_2D, mat_H,
-              lamda_d=250, descriptor_dist=4, lambda_loss=1.0, engine=None, dist_group=None, side_stream=None):
-    """Returns dict(loss, loss_det, loss_det_warp, loss_desc, positive_dist, negative_dist).
+              lamda_d=250, descriptor_dist=4, lambda_loss=1.0, engine=None, dist_group=None, side_stream=None,
+              sem_pred=None, sem=None, sem_warp_pred=None, warped_sem=None):
+    """Returns dict(loss, loss_det, loss_det_warp, loss_desc, positive_dist, negative_dist[, loss_sem, loss_sem_warp]).
 
-    loss = loss_det + loss_det_warp + lambda_loss * loss_desc   (uniform weighting, Train_model_heatmap_all.py:361-365)
+    loss = loss_det + loss_det_warp [+ loss_sem + loss_sem_warp] + lambda_loss * loss_desc
+    (uniform weighting, Train_model_heatmap_all.py:361-365).  The semantic terms (config data.semantic, :304,:320-324)
+    are added when sem_pred / sem (and the warped twins) are given; sem_pred may be the full-resolution logits or the
+    1/8-resolution head output (fused upsample, see utils.sem_loss).
     side_stream: unused (kept for compatibility).
     """
     # multi-GPU: the global-normaliser all-reduces are launched asynchronously and overlap the following kernels
@@ -29,11 +34,18 @@ def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2
         kw["engine"] = engine
     loss_desc, _mask, pos, neg = U.descriptor_loss(desc, desc_warp, mat_H, mask_valid=mask_desc, device=semi.device,
                                                    lamda_d=lamda_d, descriptor_dist=descriptor_dist, **kw)
+    out = {}
+    if sem_pred is not None:
+        out["loss_sem"] = U.sem_loss(sem_pred, sem, dist_group=dist_group)
+        out["loss_sem_warp"] = U.sem_loss(sem_warp_pred, warped_sem, dist_group=dist_group)
     if dist_group is not None:
         dist_group.finish()
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc
-    return {"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
-            "positive_dist": pos, "negative_dist": neg}
+    if sem_pred is not None:
+        loss = loss + out["loss_sem"] + out["loss_sem_warp"]
+    out.update({"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
+                "positive_dist": pos, "negative_dist": neg})
+    return out
 
 
 @torch.no_grad()
@@ -62,9 +74,13 @@ class GraphedLossStep(object):
     scalars and the four gradients) live in static buffers that the next replay overwrites."""
 
     IN_KEYS = ("semi", "semi_warp", "desc", "desc_warp", "labels_2D", "warped_labels", "mask_2D", "mask_warp_2D", "mat_H")
+    SEM_KEYS = ("sem_pred", "sem_warp_pred", "sem", "warped_sem")  # optional: SSp configuration
 
     def __init__(self, example, overlap=True, **kw):
         self.kw = kw
+        self.semantic = "sem_pred" in example
+        if self.semantic:
+            self.IN_KEYS = self.IN_KEYS + self.SEM_KEYS
         self.static = {k: example[k].detach().clone() for k in self.IN_KEYS}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -79,9 +95,13 @@ class GraphedLossStep(object):
 
     def _run(self):
         s = self.static
-        leaves = [s[k].detach().requires_grad_(True) for k in ("semi", "semi_warp", "desc", "desc_warp")]
+        names = ("semi", "semi_warp", "desc", "desc_warp") + (("sem_pred", "sem_warp_pred") if self.semantic else ())
+        leaves = [s[k].detach().requires_grad_(True) for k in names]
+        kw = dict(self.kw)
+        if self.semantic:
+            kw.update(sem_pred=leaves[4], sem=s["sem"], sem_warp_pred=leaves[5], warped_sem=s["warped_sem"])
         out = loss_step(leaves[0], leaves[1], leaves[2], leaves[3], s["labels_2D"], s["warped_labels"], s["mask_2D"],
-                        s["mask_warp_2D"], s["mat_H"], **self.kw)
+                        s["mask_warp_2D"], s["mat_H"], **kw)
         out["loss"].backward()
         res = {k: v.detach() for k, v in out.items()}
         res["grads"] = [l.grad for l in leaves]

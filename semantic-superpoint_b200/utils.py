@@ -12,7 +12,8 @@ import torch
 
 from . import _lib
 from ._lib import call, f32c, ptr, stream_of
-from .losses import DescriptorLossFn, DetectorLossFn, DetectorLossPairFn, LazyPairMask, get_descriptor_engine
+from .losses import (DescriptorLossFn, DetectorLossFn, DetectorLossPairFn, LazyPairMask, SemanticLossFn,
+                     get_descriptor_engine)
 
 __all__ = [
     "warp_points", "filter_points", "warp_points_filter", "warp_keypoints", "inv_warp_image_batch", "inv_warp_image",
@@ -289,6 +290,17 @@ def detector_loss_pair_2d(semi, labels_2D, mask_2D, semi_warp, warped_labels, ma
     Returns (loss_det, loss_det_warp, mask_3D_flattened of the warped mask [B,Hc,Wc])."""
     _lib.require_cuda(semi, semi_warp)
     return DetectorLossPairFn.apply(semi, labels_2D, mask_2D, semi_warp, warped_labels, mask_warp_2D, True, dist_group)
+
+
+def sem_loss(pred, label, device="cpu", ignore_index=133, dist_group=None):
+    """reference: Train_model_heatmap_all.py:181-193 (method sem_loss(self, pred, label, device)):
+    nn.CrossEntropyLoss(ignore_index=133)(pred, label).
+
+    pred [B,C,H,W] (what the unmodified model returns) or the head output BEFORE the model's final F.interpolate,
+    [B,C,H/8,W/8] (models/SuperPointNet_gauss2_ssmall.py:86-90): then the x8 bilinear upsample is fused into the loss and
+    the [B,133,H,W] logits are never materialised.  label [B,H,W] integer."""
+    _lib.require_cuda(pred)
+    return SemanticLossFn.apply(pred, label, int(ignore_index), dist_group)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -68,7 +68,49 @@ def save(name, **arrays):
     print("%-28s %8.1f KB" % (name, os.path.getsize(path) / 1024))
 
 
+def gen_semantic():
+    """semantic head.  The low-res logits are captured at convSout of the UNMODIFIED reference model
+    (models/SuperPointNet_gauss2_ssmall.py:86-91), its own forward upsamples them, and the trainer's sem_loss
+    (Train_model_heatmap_all.py:181-193) is the loss; a second case feeds larger synthetic logits through the same
+    two reference lines (F.interpolate + sem_loss)."""
+    import torch.nn.functional as F
+    from models.SuperPointNet_gauss2_ssmall import SuperPointNet_gauss2_ssmall
+    t = torch.from_numpy
+    Tcls = ref_trainer_class()
+    torch.manual_seed(3)
+    net = SuperPointNet_gauss2_ssmall()
+    net.train()
+    grabbed = {}
+
+    def hook(_m, _i, out):
+        out.retain_grad()
+        grabbed["lr"] = out
+
+    net.convSout.register_forward_hook(hook)
+    img = t(synth.uniform((2, 1, 32, 48), 101))
+    out = net(img)
+    sem = out["sem"]
+    sem.retain_grad()
+    lab = (synth.uniform((2, 32, 48), 102) * 134).astype(np.int64)      # 0..133, 133 = ignore_index
+    lab[0, :5, :] = 133
+    loss = Tcls.sem_loss(None, sem, t(lab), "cpu")
+    loss.backward()
+    # larger logits, odd borders exercised by a 3 x 5 cell map
+    lr2 = t(synth.pseudo_normal((1, 133, 3, 5), 103) * 4).requires_grad_(True)
+    full2 = F.interpolate(lr2, (24, 40), mode="bilinear", align_corners=False)
+    full2.retain_grad()
+    lab2 = (synth.uniform((1, 24, 40), 104) * 140).astype(np.int64).clip(0, 133)
+    loss2 = Tcls.sem_loss(None, full2, t(lab2), "cpu")
+    (loss2 * 0.7).backward()
+    save("semantic", lr=grabbed["lr"].detach().numpy(), full_sample=sem.detach().numpy()[:, ::7], label=lab, loss=loss.detach().numpy(),
+         dlr=grabbed["lr"].grad.numpy(), dfull_sample=sem.grad.numpy()[:, ::9, ::5, ::7],
+         lr2=lr2.detach().numpy(), label2=lab2, loss2=loss2.detach().numpy(), dlr2=lr2.grad.numpy(), g2=np.float32(0.7),
+         dfull2_sample=full2.grad.numpy()[:, ::9, ::3, ::5])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "semantic":
+        return gen_semantic()
     torch.manual_seed(0)
     t = torch.from_numpy
 
@@ -198,6 +240,8 @@ def main():
     # utils/loss_functions/sparse_loss.py:345 "pos should be 0")
     rI = run_desc(D, D.copy(), np.eye(3, dtype=np.float32)[None], np.ones((1, 1, 30, 40), np.float32), (1.0, 0.0, 0.0))
     save("desc_identity", loss=rI["loss"], pos=rI["pos"], neg=rI["neg"])
+
+    gen_semantic()
 
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:
         json.dump({"torch": torch.__version__, "numpy": np.__version__, "cv2": cv2.__version__,

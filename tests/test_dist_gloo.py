@@ -26,10 +26,18 @@ def _inputs():
     return Hs, D, Dw, mv, semi, lab, m3
 
 
+def _sem_inputs():
+    rng = np.random.default_rng(8)
+    lab = rng.integers(0, 134, (B, HC * 8, WC * 8))
+    lab[0, :20] = 133  # uneven counts across the two shards
+    return synth.pseudo_normal((B, 133, HC, WC), 9) * 2, lab
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as tdist
-    from ssp_b200.dist import DeferredExchange, globalize_descriptor, globalize_detector, init_from_env, shard_range
+    from ssp_b200.dist import (DeferredExchange, globalize_descriptor, globalize_detector, globalize_semantic, init_from_env,
+                               shard_range)
     init_from_env(backend="gloo")
     Hs, D, Dw, mv, semi, lab, m3 = _inputs()
     lo, hi = shard_range(B, rank, world)
@@ -51,7 +59,13 @@ def _worker(rank, world, port, q):
     assert len(ex.pending) == 2
     ex.finish()
     assert torch.equal(out8d, out8) and torch.equal(out3d, out3)
-    q.put((rank, out8.numpy().copy(), out3.numpy().copy()))
+    # semantic cross entropy: mean over the counted pixels of the global batch
+    sl, slab = _sem_inputs()
+    ls = O.sem_loss(sl[lo:hi], slab[lo:hi])
+    cnt = np.float32((slab[lo:hi] != 133).sum())
+    outs = torch.tensor([ls, ls * cnt, cnt], dtype=torch.float32)
+    globalize_semantic(outs, True)
+    q.put((rank, out8.numpy().copy(), out3.numpy().copy(), outs.numpy().copy()))
     tdist.barrier()
     tdist.destroy_process_group()
 
@@ -68,7 +82,10 @@ def test_global_normalisers_world2():
     Hs, D, Dw, mv, semi, lab, m3 = _inputs()
     l, _, p, n = O.descriptor_loss(D, Dw, Hs, mv)
     ld = O.detector_loss(semi, lab, m3)
-    for rank, out8, out3 in res:
+    sl, slab = _sem_inputs()
+    for rank, out8, out3, outs in res:
+        np.testing.assert_allclose(outs[0], O.sem_loss(sl, slab), rtol=1e-5)
+        np.testing.assert_allclose(outs[2], (slab != 133).sum())
         np.testing.assert_allclose(out8[:3], [l, p, n], rtol=1e-5)
         np.testing.assert_allclose(out8[3], B * (mv.sum() + 1) * HC * WC, rtol=1e-6)
         np.testing.assert_allclose(out3[0], ld, rtol=1e-5)

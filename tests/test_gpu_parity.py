@@ -358,6 +358,102 @@ def test_descriptor_other_channel_count():
 
 
 # ------------------------------------------------------------------ boundary behaviour
+# ------------------------------------------------------------------ 8f rank 1: semantic head
+def _sem_check(lr, lab, ignore=133, gout=1.0, full=False):
+    """CUDA sem_loss (fused x8 upsample, or full resolution when full=True) against the oracle, loss and gradient."""
+    if full:
+        pred = O.upsample_bilinear(lr, lab.shape[1:]).astype(np.float32)
+    else:
+        pred = lr
+    ref, dref = O.sem_loss(pred, lab, ignore_index=ignore, grad=True, gout=gout)
+    x = cu(pred).requires_grad_(True)
+    loss = S.utils.sem_loss(x, cu(lab), DEV, ignore_index=ignore)
+    (loss * gout).backward()
+    if np.isnan(ref):
+        assert torch.isnan(loss).item() and float(x.grad.abs().max()) == 0.0
+        return
+    close(loss, ref)
+    close(x.grad, dref, atol=1e-4 * max(np.abs(dref).max(), 1e-30))
+
+
+def test_sem_loss_golden(golden):
+    g = golden("semantic")
+    for lr_k, lab_k, loss_k, d_k, gout in (("lr", "label", "loss", "dlr", 1.0), ("lr2", "label2", "loss2", "dlr2", 0.7)):
+        x = cu(g[lr_k]).requires_grad_(True)
+        loss = S.utils.sem_loss(x, cu(g[lab_k]), DEV)          # fused upsample: pred is 1/8 of the label size
+        close(loss, g[loss_k])
+        (loss * gout).backward()
+        close(x.grad, g[d_k], atol=1e-4 * np.abs(g[d_k]).max())
+        _sem_check(g[lr_k], g[lab_k], gout=gout, full=True)     # full-resolution kernels on the upsampled logits
+    with torch.no_grad():                                       # no-grad forward (validation): GRAD=false kernel
+        close(S.utils.sem_loss(cu(g["lr"]), cu(g["label"]), DEV), g["loss"])
+
+
+def test_sem_loss_shapes_and_edges():
+    rng = np.random.default_rng(5)
+    for (B, C, hc, wc) in ((2, 133, 30, 40), (1, 133, 47, 155), (1, 7, 3, 13), (2, 64, 5, 11), (1, 256, 2, 2), (1, 2, 1, 1)):
+        lr = (synth.pseudo_normal((B, C, hc, wc), 11 + C) * 3).astype(np.float32)
+        lab = rng.integers(0, C + 1, (B, hc * 8, wc * 8)).astype(np.int64)   # C = ignore_index here
+        lab[:, : hc * 2, : wc * 3] = C
+        _sem_check(lr, lab, ignore=C, gout=1.3)
+        if B * C * hc * wc < 200000:
+            _sem_check(lr, lab, ignore=C, gout=1.3, full=True)
+    # nothing counted: loss NaN, gradient 0 (torch's mean over nothing)
+    lr = synth.pseudo_normal((1, 133, 4, 5), 3).astype(np.float32)
+    _sem_check(lr, np.full((1, 32, 40), 133, np.int64))
+    _sem_check(lr, np.full((1, 32, 40), 133, np.int64), full=True)
+    # logit spread far beyond the fp32 exponent range between neighbouring cells: the shift bound underflows and the
+    # per-pixel exact path takes over
+    big = synth.pseudo_normal((1, 133, 4, 5), 4).astype(np.float32)
+    big[0, :, ::2, ::2] *= 120.0
+    lab = rng.integers(0, 133, (1, 32, 40)).astype(np.int64)
+    _sem_check(big, lab)
+    # int32 labels and a CPU label tensor are accepted (converted), CPU logits are not
+    x = cu(lr).requires_grad_(True)
+    l = S.utils.sem_loss(x, torch.from_numpy(lab.astype(np.int32)), DEV)
+    close(l, O.sem_loss(lr, lab))
+    with pytest.raises(RuntimeError):
+        S.utils.sem_loss(torch.from_numpy(lr), torch.from_numpy(lab))
+    with pytest.raises(RuntimeError):
+        S.utils.sem_loss(cu(lr), cu(lab[:, :30]))               # neither the label size nor 1/8 of it
+
+
+def test_loss_step_semantic():
+    """SSp configuration: detector x2 + descriptor + semantic x2 (BASELINE configs[1]) through loss_step and the graph."""
+    B = 2
+    rng = np.random.default_rng(9)
+    ex = {"semi": cu(synth.pseudo_normal((B, 65, 30, 40), 1)), "semi_warp": cu(synth.pseudo_normal((B, 65, 30, 40), 2)),
+          "desc": cu(synth.unit_descriptors(B, 256, 30, 40, 3, smooth=0.3)),
+          "desc_warp": cu(synth.unit_descriptors(B, 256, 30, 40, 4, smooth=0.3)),
+          "labels_2D": cu(synth.keypoint_labels(B, 240, 320, 5)), "warped_labels": cu(synth.keypoint_labels(B, 240, 320, 6)),
+          "mask_2D": cu(np.ones((B, 1, 240, 320), np.float32))}
+    Hs, Hinv = homographies(B, 31)
+    ex["mask_warp_2D"] = cu(O.compute_valid_mask((240, 320), Hinv, 3)[:, None])
+    ex["mat_H"] = cu(Hs)
+    base = S.step.loss_step(ex["semi"], ex["semi_warp"], ex["desc"], ex["desc_warp"], ex["labels_2D"], ex["warped_labels"],
+                            ex["mask_2D"], ex["mask_warp_2D"], ex["mat_H"])
+    sp, spw = synth.pseudo_normal((B, 133, 30, 40), 7) * 2, synth.pseudo_normal((B, 133, 30, 40), 8) * 2
+    sem, semw = rng.integers(0, 134, (B, 240, 320)), rng.integers(0, 134, (B, 240, 320))
+    ex.update(sem_pred=cu(sp), sem_warp_pred=cu(spw), sem=cu(sem), warped_sem=cu(semw))
+    r1, d1 = O.sem_loss(sp, sem, grad=True)
+    r2, d2 = O.sem_loss(spw, semw, grad=True)
+    leaves = {k: ex[k].clone().requires_grad_(True) for k in ("semi", "semi_warp", "desc", "desc_warp", "sem_pred", "sem_warp_pred")}
+    out = S.step.loss_step(leaves["semi"], leaves["semi_warp"], leaves["desc"], leaves["desc_warp"], ex["labels_2D"],
+                           ex["warped_labels"], ex["mask_2D"], ex["mask_warp_2D"], ex["mat_H"], sem_pred=leaves["sem_pred"],
+                           sem=ex["sem"], sem_warp_pred=leaves["sem_warp_pred"], warped_sem=ex["warped_sem"])
+    out["loss"].backward()
+    close(out["loss_sem"], r1); close(out["loss_sem_warp"], r2)
+    close(out["loss"], float(base["loss"]) + float(r1) + float(r2))
+    close(leaves["sem_pred"].grad, d1, atol=1e-4 * np.abs(d1).max())
+    close(leaves["sem_warp_pred"].grad, d2, atol=1e-4 * np.abs(d2).max())
+    graphed = S.step.GraphedLossStep(ex)
+    res = graphed(ex)
+    torch.cuda.synchronize()
+    close(res["loss"], out["loss"], rtol=1e-5)
+    assert len(res["grads"]) == 6
+    close(res["grads"][4], d1, atol=1e-4 * np.abs(d1).max())
+
+
 def test_abi_errors():
     from ssp_b200 import _lib
     lib = _lib.load()

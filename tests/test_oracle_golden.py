@@ -115,3 +115,19 @@ def test_descriptor_identity_kat(golden):
     loss, _, pos, neg = O.descriptor_loss(D, D.copy(), np.eye(3)[None], np.ones((1, 1, 30, 40), np.float32))
     close(pos, g["pos"], atol=1e-7); close(neg, g["neg"]); close(loss, g["loss"])
     assert abs(float(pos)) < 1e-6
+
+
+def test_semantic_head(golden):
+    """x8 bilinear upsample (reference model forward) + CrossEntropyLoss(ignore_index=133)."""
+    g = golden("semantic")
+    close(O.upsample_bilinear(g["lr"], g["label"].shape[1:])[:, ::7], g["full_sample"], atol=1e-6)
+    for lr_k, lab_k, loss_k, d_k, ds_k, gout in (("lr", "label", "loss", "dlr", "dfull_sample", 1.0),
+                                                 ("lr2", "label2", "loss2", "dlr2", "dfull2_sample", float(g["g2"]))):
+        loss, d = O.sem_loss(g[lr_k], g[lab_k], grad=True, gout=gout)
+        close(loss, g[loss_k], rtol=1e-5)
+        close(d, g[d_k], atol=1e-4 * np.abs(g[d_k]).max())
+        full = O.upsample_bilinear(g[lr_k], g[lab_k].shape[1:])
+        loss_f, d_f = O.sem_loss(full, g[lab_k], grad=True, gout=gout)   # full-resolution entry of the same oracle
+        close(loss_f, g[loss_k], rtol=1e-5)
+        sy, sx = (5, 7) if lr_k == "lr" else (3, 5)
+        close(d_f[:, ::9, ::sy, ::sx], g[ds_k], atol=1e-4 * np.abs(g[ds_k]).max())
