@@ -17,3 +17,4 @@ for f in sys.argv[1:]:
     if 'clocks' in d: print('  clocks', d['clocks'])
     if 'homography_adaptation' in d: print('  adapt', d['homography_adaptation']['value'])
     if 'cpu_baseline' in d: print('  cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
+    if 'with_semantic_head' in d: print('  semantic', d['with_semantic_head'])

@@ -77,17 +77,21 @@ __device__ __forceinline__ void pos_window(float wx, float wy, float dist, int H
 //     column (partner row, dot)
 // partials: 4 doubles per block = { pos_unweighted, pos_weighted, negcorr_unweighted, negcorr_weighted }
 // ----------------------------------------------------------------------------------------------
+// Latency chain per block (the kernel is latency-bound: 1280 blocks of short dependent steps): geometry scan ->
+// one round of loads covering TWO partners per row (rows have 0.8 partners on average, rarely more than 2) -> one
+// shared-memory combine -> list stores / slot atomics fired by warp 0 without anybody waiting on them -> warp-level
+// reduction of the four partial sums.
 #define POS_ROWS 32
 #define POS_DG 8
-__global__ void __launch_bounds__(POS_ROWS * POS_DG)
+#define POS_CH 16  // channels per thread and chunk (3 x 16 independent loads in flight)
+__global__ void __launch_bounds__(POS_ROWS * POS_DG, 2)
 desc_pos_fwd_kernel(const float* __restrict__ D, const float* __restrict__ Dw, const float2* __restrict__ wpts,
                     const float* __restrict__ mv_pad, DescGeom g, double* __restrict__ partials,
                     int* __restrict__ rowcol, float* __restrict__ rowdot, int* __restrict__ colcnt,
                     int* __restrict__ colrow, float* __restrict__ coldot) {
   __shared__ int scol[POS_ROWS][DESC_MAXP];
   __shared__ int scnt[POS_ROWS];
-  __shared__ float spart[POS_DG][POS_ROWS];
-  __shared__ double sh[32];
+  __shared__ float spart[2][POS_DG][POS_ROWS];
   __shared__ int smax;
   const int b = blockIdx.y, lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
   const int r = blockIdx.x * POS_ROWS + lane;
@@ -108,63 +112,81 @@ desc_pos_fwd_kernel(const float* __restrict__ D, const float* __restrict__ Dw, c
         }
     }
     scnt[lane] = cnt;
-    if (r < g.Nc_pad)
-      for (int n = 0; n < DESC_MAXP; ++n) rowcol[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n] = n < cnt ? scol[lane][n] : -1;
-    atomicMax(&smax, cnt);
+    if (r < g.Nc_pad) {
+      int4* rc = reinterpret_cast<int4*>(rowcol + ((size_t)b * g.Nc_pad + r) * DESC_MAXP);
+#pragma unroll
+      for (int n = 0; n < DESC_MAXP; n += 4)
+        rc[n / 4] = make_int4(n < cnt ? scol[lane][n] : -1, n + 1 < cnt ? scol[lane][n + 1] : -1,
+                              n + 2 < cnt ? scol[lane][n + 2] : -1, n + 3 < cnt ? scol[lane][n + 3] : -1);
+    }
+    if (cnt) atomicMax(&smax, cnt);
   }
   __syncthreads();
   const int nmax = smax;
+  const int cnt = scnt[lane];
   const int dper = (g.Dch + POS_DG - 1) / POS_DG;
   const int d0 = dg * dper, d1 = min(g.Dch, d0 + dper);
-  const float* Db = D + (size_t)b * g.Dch * g.Nc + r;
-  const float* Dwb = Dw + (size_t)b * g.Dch * g.Nc;
+  const float* __restrict__ Db = D + (size_t)b * g.Dch * g.Nc + r;
+  const float* __restrict__ Dwb = Dw + (size_t)b * g.Dch * g.Nc;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int n = 0; n < nmax; ++n) {
-    bool has = n < scnt[lane];
-    int c = has ? scol[lane][n] : 0;
-    float part = 0.f;
-    if (has) {
-      for (int db = d0; db < d1; db += 32) {  // 64 independent loads in flight per thread
-        float a[32], w[32];
+  for (int n0 = 0; n0 < nmax; n0 += 2) {
+    const bool has0 = n0 < cnt, has1 = n0 + 1 < cnt;
+    const int c0 = has0 ? scol[lane][n0] : 0, c1 = has1 ? scol[lane][n0 + 1] : 0;
+    float part0 = 0.f, part1 = 0.f;
+    if (has0) {
+      for (int db = d0; db < d1; db += POS_CH) {
+        float a[POS_CH], w0[POS_CH], w1[POS_CH];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < POS_CH; ++i) {
           bool ok = db + i < d1;
           a[i] = ok ? __ldg(Db + (size_t)(db + i) * g.Nc) : 0.f;
-          w[i] = ok ? __ldg(Dwb + (size_t)(db + i) * g.Nc + c) : 0.f;
+          w0[i] = ok ? __ldg(Dwb + (size_t)(db + i) * g.Nc + c0) : 0.f;
+          w1[i] = (ok && has1) ? __ldg(Dwb + (size_t)(db + i) * g.Nc + c1) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) part = fmaf(a[i], w[i], part);
+        for (int i = 0; i < POS_CH; ++i) {
+          part0 = fmaf(a[i], w0[i], part0);
+          part1 = fmaf(a[i], w1[i], part1);
+        }
       }
     }
-    spart[dg][lane] = part;
+    if (n0) __syncthreads();  // warp 0 has consumed the previous round
+    spart[0][dg][lane] = part0;
+    spart[1][dg][lane] = part1;
     __syncthreads();
-    if (dg == 0 && has) {
-      float dot = 0.f;
+    if (dg == 0) {
 #pragma unroll
-      for (int q = 0; q < POS_DG; ++q) dot += spart[q][lane];
-      float mv = mv_pad[(size_t)b * g.Nc_pad + c];
-      float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
-      float negc = fmaxf(dot - g.mneg, 0.f);
-      acc[0] += (double)pos;
-      acc[1] += (double)(pos * mv);
-      acc[2] += (double)negc;
-      acc[3] += (double)(negc * mv);
-      rowdot[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n] = dot;
-      int slot = atomicAdd(colcnt + (size_t)b * g.Nc_pad + c, 1);
-      if (slot < DESC_MAXP) {
-        colrow[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = r;
-        coldot[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = dot;
-      } else {
-        atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, 1);  // overflow counter
+      for (int j = 0; j < 2; ++j) {
+        if (!(j ? has1 : has0)) continue;
+        const int c = j ? c1 : c0;
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < POS_DG; ++q) dot += spart[j][q][lane];
+        float mv = mv_pad[(size_t)b * g.Nc_pad + c];
+        float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
+        float negc = fmaxf(dot - g.mneg, 0.f);
+        acc[0] += (double)pos;
+        acc[1] += (double)(pos * mv);
+        acc[2] += (double)negc;
+        acc[3] += (double)(negc * mv);
+        rowdot[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n0 + j] = dot;
+        int slot = atomicAdd(colcnt + (size_t)b * g.Nc_pad + c, 1);
+        if (slot < DESC_MAXP) {
+          colrow[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = r;
+          coldot[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = dot;
+        } else {
+          atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, 1);  // overflow counter
+        }
       }
     }
-    __syncthreads();
   }
-  size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  if (dg == 0) {  // only warp 0 holds sums
+    size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double v = block_sum_d(acc[i], sh);
-    if (threadIdx.x == 0) partials[4 * blk + i] = v;
+    for (int i = 0; i < 4; ++i) {
+      double v = warp_sum_d(acc[i]);
+      if (lane == 0) partials[4 * blk + i] = v;
+    }
   }
 }
 
@@ -211,11 +233,34 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
   __shared__ double sh[32];
   double pu = 0, pw = 0, nu = 0, nw = 0, sm = 0;
   double cu = 0, cw = 0;  // negative-hinge contribution of the positive pairs, contained in the dense sums
-  for (int i = threadIdx.x; i < npos; i += blockDim.x) {
-    pu += pos_part[4 * i]; pw += pos_part[4 * i + 1]; cu += pos_part[4 * i + 2]; cw += pos_part[4 * i + 3];
+  // the loops are a chain of L2 round trips per thread unless several loads are in flight: batches of 4 vector loads
+  {
+    const double2* p2 = reinterpret_cast<const double2*>(pos_part);  // {pos_u, pos_w}, {negcorr_u, negcorr_w}
+    for (int i0 = threadIdx.x; i0 < npos; i0 += 4 * blockDim.x) {
+      double2 a[4], c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int i = i0 + u * blockDim.x;
+        bool ok = i < npos;
+        a[u] = ok ? p2[2 * (size_t)i] : make_double2(0.0, 0.0);
+        c[u] = ok ? p2[2 * (size_t)i + 1] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { pu += a[u].x; pw += a[u].y; cu += c[u].x; cw += c[u].y; }
+    }
+    const double2* n2 = reinterpret_cast<const double2*>(neg_part);
+    for (int i0 = threadIdx.x; i0 < nneg; i0 += 8 * blockDim.x) {
+      double2 a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        int i = i0 + u * blockDim.x;
+        a[u] = i < nneg ? n2[i] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { nu += a[u].x; nw += a[u].y; }
+    }
+    for (int i = threadIdx.x; i < nmv; i += blockDim.x) sm += mv_part[i];
   }
-  for (int i = threadIdx.x; i < nneg; i += blockDim.x) { nu += neg_part[2 * i]; nw += neg_part[2 * i + 1]; }
-  for (int i = threadIdx.x; i < nmv; i += blockDim.x) sm += mv_part[i];
   pu = block_sum_d(pu, sh);
   pw = block_sum_d(pw, sh);
   nu = block_sum_d(nu, sh);
@@ -243,6 +288,7 @@ extern "C" int ssp_desc_finalize(const double* pos_part, int npos, const double*
                                  const double* mv_part, int nmv, int B, int Hc, int Wc, float* out4, void* stream) {
   SSP_REQUIRE(pos_part && neg_part && mv_part && out4, "ssp_desc_finalize: null pointer");
   SSP_REQUIRE(npos >= 0 && nneg >= 0 && nmv >= 0 && B > 0 && Hc > 0 && Wc > 0, "ssp_desc_finalize: bad sizes");
+  SSP_REQUIRE((((uintptr_t)pos_part | (uintptr_t)neg_part) & 15) == 0, "ssp_desc_finalize: partial-sum arrays must be 16-byte aligned");
   desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_part, nmv, B, Hc, Wc, out4);
   SSP_CUDA_CHECK_LAUNCH("desc_finalize_kernel");
   return SSP_OK;

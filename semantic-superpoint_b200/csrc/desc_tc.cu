@@ -26,6 +26,7 @@
 #include "desc_common.cuh"
 #include "tc_ptx.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -281,8 +282,10 @@ constexpr int BG_BOX_BYTES = KT * 128;       // one [64 cells x 64 channels] box
 constexpr int BG_N = 128;                    // channels per work item (half of the descriptor)
 constexpr int BG_THREADS = 448;              // warps 0-3 expanders, 4-11 epilogue, 12 TMA producer, 13 MMA issuer
 
-template <int P> struct BgCfg {
-  static constexpr int NS = (P == 1) ? 6 : 4;
+// NS_ = depth of the B (TMA) / A (TMEM) stage ring.  P = 2: 32 KB per stage, 4 stages = 128 KB (default) or 6 = 192 KB;
+// P = 1: 16 KB per stage, 6 (default) or 8.  The TMEM A ring needs 256 + 32 * NS columns <= 512, i.e. NS <= 8.
+template <int P, int NS_> struct BgCfg {
+  static constexpr int NS = NS_;
   static constexpr int STAGE_BYTES = P * 2 * BG_BOX_BYTES;  // P planes x two 64-channel boxes = 16 KB per plane
   static constexpr int SMEM = NS * STAGE_BYTES + BAR_BYTES + 1024;
 };
@@ -291,14 +294,15 @@ template <int P> struct BgCfg {
 // evenly over 2-CTA clusters.  The fp32 accumulator is double buffered in TMEM (2 x 128 columns), so the epilogue of
 // item i (warps 4-7: TMEM -> registers -> coalesced NCHW stores) overlaps the main loop of item i+1 (warps 0-3 expand
 // indicator bits into the TMEM A ring, warp 8 streams B through TMA multicast, warp 9 issues the MMAs).
-template <int P>
+template <int P, int NS_>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                          const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
                          const int* __restrict__ plist, const float* __restrict__ pcoef, const float* __restrict__ possrc,
                          int B, int Nc, int Nc_pad, float* __restrict__ out) {
-  using Cfg = BgCfg<P>;
+  using Cfg = BgCfg<P, NS_>;
   constexpr int NS = Cfg::NS;
+  static_assert(256 + 32 * NS <= 512, "TMEM A ring does not fit");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
@@ -630,15 +634,17 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
   int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
-  if (Blo) {
-    if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, mh, ml, bits, rowscale, plist, pcoef,
-                              possrc, B, Nc, Nc_pad, out))) return rc;
-  } else {
-    if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, mh, ml, bits, rowscale, plist, pcoef,
-                              possrc, B, Nc, Nc_pad, out))) return rc;
-  }
+  // ring depth: SSP_BG_NS=deep selects the deeper stage ring (6 x 32 KB for the split engine, 8 x 16 KB single pass)
+  static const bool deep = [] { const char* e = getenv("SSP_BG_NS"); return e && e[0] == 'd'; }();
+#define LAUNCH_BG(PP, NN)                                                                                             \
+  do {                                                                                                                \
+    if ((rc = set_smem(desc_bits_gemm_tc_kernel<PP, NN>, BgCfg<PP, NN>::SMEM))) return rc;                            \
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<PP, NN>, grid, BG_THREADS, BgCfg<PP, NN>::SMEM, st, mh, ml, bits, \
+                              rowscale, plist, pcoef, possrc, B, Nc, Nc_pad, out))) return rc;                        \
+  } while (0)
+  if (Blo) { if (deep) LAUNCH_BG(2, 6); else LAUNCH_BG(2, 4); }
+  else     { if (deep) LAUNCH_BG(1, 8); else LAUNCH_BG(1, 6); }
+#undef LAUNCH_BG
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;
 }
