@@ -353,61 +353,117 @@ __device__ __forceinline__ float pos_coef(float dot, float mv, const float* __re
   return -lamda * ind * (g3[0] * mv + g3[1]) / norm;
 }
 
-__global__ void desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowdot,
-                                     const int* __restrict__ colcnt, int* __restrict__ colrow,
-                                     const float* __restrict__ coldot, const uint32_t* __restrict__ bitsR,
-                                     const float* __restrict__ mv_pad, const float* __restrict__ alpha,
-                                     const float* __restrict__ g3, const float* __restrict__ out8, int Nc_pad,
-                                     float lamda, float mpos, float* __restrict__ rowcoef, float* __restrict__ colcoef) {
+// N = number of list slots handled (4: vector loads, the common case; DESC_MAXP: any list).  Lists are filled front to
+// back, so a row list with slot 3 empty / a column count <= 4 is complete within the first 4 slots.
+template <int N>
+__device__ __forceinline__ void pos_coef_rows(const int* __restrict__ rowcol, const float* __restrict__ rowdot, size_t base,
+                                              int b, int cell, int Nc_pad, int NW, const uint32_t* __restrict__ bitsR,
+                                              const float* __restrict__ mv_pad, const float* __restrict__ alpha,
+                                              const float* __restrict__ g3, float norm, float lamda, float mpos,
+                                              float* __restrict__ rowcoef) {
+  int cc[N];
+  float dd[N], cf[N];
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    int4 c4 = *reinterpret_cast<const int4*>(rowcol + base + n);
+    float4 d4 = *reinterpret_cast<const float4*>(rowdot + base + n);
+    cc[n] = c4.x; cc[n + 1] = c4.y; cc[n + 2] = c4.z; cc[n + 3] = c4.w;
+    dd[n] = d4.x; dd[n + 1] = d4.y; dd[n + 2] = d4.z; dd[n + 3] = d4.w;
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    float coef = 0.f;
+    int c = cc[n];
+    if (c >= 0) {
+      coef = pos_coef(dd[n], mv_pad[(size_t)b * Nc_pad + c], g3, norm, lamda, mpos);
+      uint32_t w = bitsR[((size_t)b * NW + (c >> 5)) * Nc_pad + cell];
+      if ((w >> (c & 31)) & 1u) coef -= alpha[(size_t)b * Nc_pad + c];
+    }
+    cf[n] = coef;
+  }
+#pragma unroll
+  for (int n = 0; n < N; n += 4)
+    *reinterpret_cast<float4*>(rowcoef + base + n) = make_float4(cf[n], cf[n + 1], cf[n + 2], cf[n + 3]);
+}
+
+template <int N>
+__device__ __forceinline__ void pos_coef_cols(int cnt, int* __restrict__ colrow, const float* __restrict__ coldot, size_t base,
+                                              int b, int cell, int Nc_pad, int NW, const uint32_t* __restrict__ bitsR,
+                                              float mv, float al, const float* __restrict__ g3, float norm, float lamda,
+                                              float mpos, float* __restrict__ colcoef) {
+  int rr[N];
+  float dd[N];
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    int4 r4 = *reinterpret_cast<const int4*>(colrow + base + n);
+    float4 d4 = *reinterpret_cast<const float4*>(coldot + base + n);
+    int rv[4] = {r4.x, r4.y, r4.z, r4.w};
+    float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      rr[n + u] = n + u < cnt ? rv[u] : 0x7fffffff;  // slots past the count were never written
+      dd[n + u] = n + u < cnt ? dv[u] : 0.f;
+    }
+  }
+  // sort by row index: deterministic summation order whatever order the forward's atomics handed out the slots in
+#pragma unroll
+  for (int i = 1; i < N; ++i)
+#pragma unroll
+    for (int j = N - 1; j >= 1; --j)
+      if (j >= i && rr[j] < rr[j - 1]) {
+        int t = rr[j]; rr[j] = rr[j - 1]; rr[j - 1] = t;
+        float u = dd[j]; dd[j] = dd[j - 1]; dd[j - 1] = u;
+      }
+  float cf[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    cf[n] = 0.f;
+    if (n < cnt) {
+      int r = rr[n];
+      float coef = pos_coef(dd[n], mv, g3, norm, lamda, mpos);
+      uint32_t w = bitsR[((size_t)b * NW + (cell >> 5)) * Nc_pad + r];
+      if ((w >> (cell & 31)) & 1u) coef -= al;
+      cf[n] = coef;
+    } else {
+      rr[n] = -1;
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    *reinterpret_cast<int4*>(colrow + base + n) = make_int4(rr[n], rr[n + 1], rr[n + 2], rr[n + 3]);
+    *reinterpret_cast<float4*>(colcoef + base + n) = make_float4(cf[n], cf[n + 1], cf[n + 2], cf[n + 3]);
+  }
+  // the consumers scan all DESC_MAXP slots of a list for entries >= 0
+#pragma unroll
+  for (int n = N; n < DESC_MAXP; n += 4) *reinterpret_cast<int4*>(colrow + base + n) = make_int4(-1, -1, -1, -1);
+}
+
+__global__ void __launch_bounds__(128)
+desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowdot,
+                     const int* __restrict__ colcnt, int* __restrict__ colrow,
+                     const float* __restrict__ coldot, const uint32_t* __restrict__ bitsR,
+                     const float* __restrict__ mv_pad, const float* __restrict__ alpha,
+                     const float* __restrict__ g3, const float* __restrict__ out8, int Nc_pad,
+                     float lamda, float mpos, float* __restrict__ rowcoef, float* __restrict__ colcoef) {
   int b = blockIdx.y;
   int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= Nc_pad) return;
   const int NW = Nc_pad / 32;
   const float norm = out8[3];
   size_t base = ((size_t)b * Nc_pad + cell) * DESC_MAXP;
-  // row list of cell = r
-#pragma unroll
-  for (int n = 0; n < DESC_MAXP; ++n) {
-    int c = rowcol[base + n];
-    float coef = 0.f;
-    if (c >= 0) {
-      coef = pos_coef(rowdot[base + n], mv_pad[(size_t)b * Nc_pad + c], g3, norm, lamda, mpos);
-      uint32_t w = bitsR[((size_t)b * NW + (c >> 5)) * Nc_pad + cell];
-      if ((w >> (c & 31)) & 1u) coef -= alpha[(size_t)b * Nc_pad + c];
-    }
-    rowcoef[base + n] = coef;
-  }
-  // column list of cell = c: sort by row, then coefficients
+  // row list of cell = r.  A cell has 0.8 partners on average (descriptor_dist 4 on an 8-pixel grid): the 4-slot path
+  // is the one that runs; longer lists (descriptor_dist close to the cell size, strong minification) take the full one.
+  if (rowcol[base + 3] < 0)
+    pos_coef_rows<4>(rowcol, rowdot, base, b, cell, Nc_pad, NW, bitsR, mv_pad, alpha, g3, norm, lamda, mpos, rowcoef);
+  else
+    pos_coef_rows<DESC_MAXP>(rowcol, rowdot, base, b, cell, Nc_pad, NW, bitsR, mv_pad, alpha, g3, norm, lamda, mpos, rowcoef);
+  // column list of cell = c
   int cnt = min(colcnt[(size_t)b * Nc_pad + cell], DESC_MAXP);
-  int rr[DESC_MAXP];
-  float dd[DESC_MAXP];
-#pragma unroll
-  for (int n = 0; n < DESC_MAXP; ++n) {
-    rr[n] = n < cnt ? colrow[base + n] : 0x7fffffff;
-    dd[n] = n < cnt ? coldot[base + n] : 0.f;
-  }
-#pragma unroll
-  for (int i = 1; i < DESC_MAXP; ++i)
-#pragma unroll
-    for (int j = DESC_MAXP - 1; j >= 1; --j)
-      if (j >= i && rr[j] < rr[j - 1]) {
-        int t = rr[j]; rr[j] = rr[j - 1]; rr[j - 1] = t;
-        float u = dd[j]; dd[j] = dd[j - 1]; dd[j - 1] = u;
-      }
   float mv = mv_pad[(size_t)b * Nc_pad + cell], al = alpha[(size_t)b * Nc_pad + cell];
-#pragma unroll
-  for (int n = 0; n < DESC_MAXP; ++n) {
-    float coef = 0.f;
-    int r = -1;
-    if (n < cnt) {
-      r = rr[n];
-      coef = pos_coef(dd[n], mv, g3, norm, lamda, mpos);
-      uint32_t w = bitsR[((size_t)b * NW + (cell >> 5)) * Nc_pad + r];
-      if ((w >> (cell & 31)) & 1u) coef -= al;
-    }
-    colrow[base + n] = r;
-    colcoef[base + n] = coef;
-  }
+  if (cnt <= 4)
+    pos_coef_cols<4>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colcoef);
+  else
+    pos_coef_cols<DESC_MAXP>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colcoef);
 }
 
 extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, int* colrow,

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                          const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
                          const int* __restrict__ plist, const float* __restrict__ pcoef, const float* __restrict__ possrc,
-                         int B, int Nc, int Nc_pad, float* __restrict__ out) {
+                         int B, int Nc, int Nc_pad, int sched, float* __restrict__ out) {
   using Cfg = BgCfg<P, NS_>;
   constexpr int NS = Cfg::NS;
   static_assert(256 + 32 * NS <= 512, "TMEM A ring does not fit");
@@ -324,7 +324,12 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   const uint32_t cta_rank = tc::cluster_ctarank();
   const int ncluster = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const long long T = (long long)B * MP * 2;
-  const int it0 = (int)(T * cid / ncluster), it1 = (int)(T * (cid + 1) / ncluster);
+  // item schedule.  0: contiguous ranges per cluster.  1: round-robin (cluster cid takes items cid, cid + ncluster, ...):
+  // at any moment the 74 clusters work on ~7 consecutive pairs b, so the B planes of a pair (1.3 MB) are fetched from
+  // HBM once and hit in L2 for the other row tiles, instead of all 32 pairs' planes (42 MB + outputs) cycling through L2.
+  const int it0 = sched ? cid : (int)(T * cid / ncluster);
+  const int it1 = sched ? (int)T : (int)(T * (cid + 1) / ncluster);
+  const int itstep = sched ? ncluster : 1;
   constexpr uint32_t A_COL0 = 256;  // TMEM: accumulators at columns [0,128) and [128,256), then NS x 32 columns of A
 
   if (warp == 12 && lane == 0) {
@@ -349,7 +354,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int st_it = 0;
-      for (int it = it0; it < it1; ++it) {
+      for (int it = it0; it < it1; it += itstep) {
         const int key = it >> 1, dh = it & 1;
         const int b = key / MP;
         const int row_base = b * Nc_pad;
@@ -374,7 +379,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BG_N, 0, 1);  // A K-major (TMEM), B MN-major
       const uint32_t smem_u = tc::smem_u32(smem);
       int st_it = 0, tcount = 0;
-      for (int it = it0; it < it1; ++it, ++tcount) {
+      for (int it = it0; it < it1; it += itstep, ++tcount) {
         const int as = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
         tc::mbar_wait(d_empty + as, aph ^ 1);
@@ -404,7 +409,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // ------------------------------ expanders: indicator bits -> bf16 A operand in TMEM ------------------------------
     const int q = warp;
     int st_it = 0;
-    for (int it = it0; it < it1; ++it) {
+    for (int it = it0; it < it1; it += itstep) {
       const int key = it >> 1;
       const int b = key / MP, mp = key - b * MP;
       const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
@@ -447,7 +452,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // two warps per TMEM lane quadrant, each draining two of the four 32-column chunks of the accumulator
     const int q = warp & 3, chalf = (warp - 4) >> 2;
     int tcount = 0;
-    for (int it = it0; it < it1; ++it, ++tcount) {
+    for (int it = it0; it < it1; it += itstep, ++tcount) {
       const int key = it >> 1, dh = it & 1;
       const int b = key / MP, mp = key - b * MP;
       const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
@@ -636,11 +641,12 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   cudaStream_t st = (cudaStream_t)stream;
   // ring depth: SSP_BG_NS=deep selects the deeper stage ring (6 x 32 KB for the split engine, 8 x 16 KB single pass)
   static const bool deep = [] { const char* e = getenv("SSP_BG_NS"); return e && e[0] == 'd'; }();
+  static const int sched = [] { const char* e = getenv("SSP_BG_SCHED"); return (e && e[0] == 'r') ? 1 : 0; }();
 #define LAUNCH_BG(PP, NN)                                                                                             \
   do {                                                                                                                \
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<PP, NN>, BgCfg<PP, NN>::SMEM))) return rc;                            \
     if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<PP, NN>, grid, BG_THREADS, BgCfg<PP, NN>::SMEM, st, mh, ml, bits, \
-                              rowscale, plist, pcoef, possrc, B, Nc, Nc_pad, out))) return rc;                        \
+                              rowscale, plist, pcoef, possrc, B, Nc, Nc_pad, sched, out))) return rc;                        \
   } while (0)
   if (Blo) { if (deep) LAUNCH_BG(2, 6); else LAUNCH_BG(2, 4); }
   else     { if (deep) LAUNCH_BG(1, 8); else LAUNCH_BG(1, 6); }

@@ -29,6 +29,7 @@ def get_descriptor_engine():
 
 
 _side_streams = {}
+_SAME = object()  # marker: "second gradient == first gradient" (no stack / cat kernels)
 
 
 class _Fork(object):
@@ -217,11 +218,15 @@ class DetectorLossPairFn(torch.autograd.Function):
         out = ctx.out
         B, C, Hc, Wc = x0.shape
         dev = x0.device
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
-        g = torch.stack([(a if a is not None else zero).reshape(()).to(torch.float32) for a in (g0, g1)]).contiguous()
+        if g1 is _SAME:  # fused step: both losses share one upstream gradient scalar
+            g = f32c(g0.reshape(1), dev).expand(2)
+        else:
+            zero = torch.zeros((), dtype=torch.float32, device=dev)
+            g = torch.stack([(a if a is not None else zero).reshape(()).to(torch.float32) for a in (g0, g1)]).contiguous()
         d0, d1 = torch.empty_like(x0), torch.empty_like(x1)
         call("ssp_detector_loss_bwd_pair", ptr(x0), ptr(t0), ptr(m0), ptr(x1), ptr(t1), ptr(m1), B, Hc, Wc,
-             1 if ctx.fused2d else 0, ptr(out[0]), ptr(out[1]), ptr(g[0:1]), ptr(g[1:2]), ptr(d0), ptr(d1), stream_of(x0))
+             1 if ctx.fused2d else 0, ptr(out[0]), ptr(out[1]), ptr(g[0:1]), ptr(g[1:2]) if g1 is not _SAME else ptr(g[0:1]),
+             ptr(d0), ptr(d1), stream_of(x0))
         return d0, None, None, d1, None, None, None, None
 
 
@@ -333,9 +338,12 @@ class DescriptorLossFn(torch.autograd.Function):
         Nc = Hc * Wc
         Ncp = _nc_pad(Nc)
         st = stream_of(Dc)
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
-        g3 = torch.stack([(g if g is not None else zero).reshape(()).to(torch.float32) for g in (g_loss, g_pos, g_neg)])
-        g3 = g3.contiguous()
+        if g_pos is _SAME:  # fused step: g_loss already is the [g_loss, g_pos, g_neg] device vector
+            g3 = g_loss
+        else:
+            zero = torch.zeros((), dtype=torch.float32, device=dev)
+            g3 = torch.stack([(g if g is not None else zero).reshape(()).to(torch.float32) for g in (g_loss, g_pos, g_neg)])
+            g3 = g3.contiguous()
         # alpha[b,c] = (g_loss * mv[c] + g_neg) / norm: coefficient of the negative hinge of column c
         alpha = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
         call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), st)
@@ -372,6 +380,60 @@ class DescriptorLossFn(torch.autograd.Function):
             call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 0,
                  ptr(dD), ptr(dDw), st)
         return dD, dDw, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+class _Ctx(object):
+    """Stand-in for the autograd context so LossStepFn can run the bodies of the two Functions above."""
+
+    def __init__(self, needs):
+        self.needs_input_grad = needs
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *tensors):
+        pass
+
+
+_lam3 = {}
+
+
+class LossStepFn(torch.autograd.Function):
+    """The whole loss step (Train_model_heatmap_all.py:295-365, uniform weighting) as ONE autograd node:
+    loss = loss_det + loss_det_warp + lambda_loss * loss_desc.  Same kernels as DetectorLossPairFn + DescriptorLossFn;
+    what disappears is the dozen 2-microsecond torch kernels (scalar mul / add, ones_like, zeros, stack) that autograd
+    needs to route three scalars through two nodes -- 7 % of a 0.45 ms step.
+    Returns (loss, loss_det, loss_det_warp, loss_desc, pos, neg); only `loss` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, desc, desc_w, Hm, lamda_d, dist,
+                lambda_loss, engine):
+        c1 = _Ctx((ctx.needs_input_grad[0], False, False, ctx.needs_input_grad[3], False, False, False, False))
+        l0, l1, cellmask = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
+        B, _, Hc, Wc = semi.shape
+        c2 = _Ctx((ctx.needs_input_grad[6], ctx.needs_input_grad[7]) + (False,) * 8)
+        ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine)
+        loss = (l0 + l1).add_(ld, alpha=lambda_loss)
+        ctx.c1, ctx.c2, ctx.lambda_loss = c1, c2, float(lambda_loss)
+        ctx.mark_non_differentiable(l0, l1, ld, pos, neg)
+        return loss, l0, l1, ld, pos, neg
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, *_unused):
+        dev = g.device
+        key = (dev.index, ctx.lambda_loss)
+        if key not in _lam3:
+            _lam3[key] = torch.tensor([ctx.lambda_loss, 0.0, 0.0], dtype=torch.float32, device=dev)
+        g = f32c(g.reshape(1), dev)
+        d0 = d1 = dD = dDw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
+            d0, _, _, d1 = DetectorLossPairFn.backward(ctx.c1, g, _SAME, None)[:4]
+        if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
+            dD, dDw = DescriptorLossFn.backward(ctx.c2, g * _lam3[key], _SAME, None, None)[:2]
+        return d0, None, None, d1, None, None, dD, dDw, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

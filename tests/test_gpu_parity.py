@@ -490,6 +490,14 @@ def test_loss_step_and_adaptation_step():
     close(out["loss_det"], ref_det); close(out["loss_det_warp"], ref_detw); close(out["loss_desc"], ref_desc[0])
     close(out["loss"], float(ref_det) + float(ref_detw) + float(ref_desc[0]))
     assert all(t.grad is not None and torch.isfinite(t.grad).all() for t in (semi, semi_w, D, Dw))
+    # the one-node fused step (default) and the three-node autograd composition give the same values and gradients
+    twins = [t.detach().clone().requires_grad_(True) for t in (semi, semi_w, D, Dw)]
+    out2 = S.step.loss_step(twins[0], twins[1], twins[2], twins[3], cu(lab), cu(labw), cu(m), cu(mw), cu(Hs), fused=False)
+    out2["loss"].backward()
+    close(out2["loss"], out["loss"], rtol=1e-6)
+    for a, b in zip(twins, (semi, semi_w, D, Dw)):
+        close(a.grad, b.grad, rtol=1e-5, atol=1e-6 * float(b.grad.abs().max()))
+    assert out2["positive_dist"].requires_grad and not out["positive_dist"].requires_grad
     # homography adaptation, N = 10 views of one image
     N = 10
     Hs, Hinv = homographies(N, 32, identity_first=True)
