@@ -385,22 +385,25 @@ def bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, steps):
                                    "workload": "detector x2 + descriptor + semantic CE x2 (133 classes, fused x8 upsample), fwd+bwd"}}
 
 
-def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, images_per_step=4, steps=6):
+def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, images_per_step=16, steps=6):
     """export_detector_homoAdapt hot loop: flattenDetection -> combine_heatmap -> getPtsFromHeatmap -> top-k for
     N=100 views per source image; source images sharded over ranks (no collective)."""
     from ssp_b200 import synth
-    I, N = images_per_step, N_ADAPT
+    I, N = 4, N_ADAPT  # 4 distinct synthetic source images, replicated (rescaled logits) to images_per_step on the device
+    rep = max(1, images_per_step // I)
     rng = np.random.default_rng(500 + rank)
     Hs = np.stack([[np.linalg.inv(synth.sample_homography(rng, max_angle=3.14 / 2)) for _ in range(N)] for _ in range(I)])
     Hs[:, 0] = np.eye(3)
     Hs = Hs.astype(np.float32)
     Hinv = torch.from_numpy(np.linalg.inv(Hs).astype(np.float32)).to(dev)
     sets = []
-    for s in range(2):  # 2 x 250 MB > L2
+    for s in range(2):  # 2 sets, each far larger than L2
         semi = torch.from_numpy(synth.pseudo_normal((I, N, 65, HC, WC), 7000 + 10 * rank + s) * 3).to(dev)
         mask = S.compute_valid_mask(torch.tensor([H_IMG, W_IMG]), Hinv.reshape(-1, 3, 3), device=dev).reshape(I, N, H_IMG, W_IMG)
-        sets.append((semi, mask))
-    Hw = torch.from_numpy(Hs).to(dev)
+        semi = torch.cat([semi * (1.0 + 0.05 * k) for k in range(rep)])
+        sets.append((semi, mask.repeat(rep, 1, 1, 1)))
+    Hw = torch.from_numpy(Hs).to(dev).repeat(rep, 1, 1, 1)
+    I = I * rep
     for s in range(2):
         pts = S.step.adaptation_step(sets[s][0], Hw, sets[s][1])
     barrier()

@@ -641,7 +641,9 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   cudaStream_t st = (cudaStream_t)stream;
   // ring depth: SSP_BG_NS=deep selects the deeper stage ring (6 x 32 KB for the split engine, 8 x 16 KB single pass)
   static const bool deep = [] { const char* e = getenv("SSP_BG_NS"); return e && e[0] == 'd'; }();
-  static const int sched = [] { const char* e = getenv("SSP_BG_SCHED"); return (e && e[0] == 'r') ? 1 : 0; }();
+  // round-robin items by default (measured: 87 -> 77 us per launch at B=32, DRAM re-reads of the B planes gone);
+  // SSP_BG_SCHED=contiguous restores the contiguous ranges.  The deeper ring measured slower (96 us) and stays opt-in.
+  static const int sched = [] { const char* e = getenv("SSP_BG_SCHED"); return (e && e[0] == 'c') ? 0 : 1; }();
 #define LAUNCH_BG(PP, NN)                                                                                             \
   do {                                                                                                                \
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<PP, NN>, BgCfg<PP, NN>::SMEM))) return rc;                            \

@@ -27,6 +27,7 @@ def cu(a):
 
 def close(a, b, rtol=TOL, atol=1e-6):
     a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b
     np.testing.assert_allclose(a.astype(np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
 
 
