@@ -5,6 +5,7 @@
 // intermediate [N,1,H,W] warped stacks of the reference never exist.  HBM traffic = the algorithmic
 // (2N+1)*H*W*4 bytes.  A block owns an 8x8 output tile x 4 interleaved view groups.
 #include "common.cuh"
+#include <cstdlib>
 
 #define CH_PIX 64
 #define CH_GROUPS 4
@@ -78,10 +79,208 @@ combine_heatmap_kernel(const float* __restrict__ heat, const float* __restrict__
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Tiled variant: shared-memory staging of the source footprint.
+// The gather kernel above is bound by L1 wavefronts: a warp's 8x4 output patch lands on ~8 different 128 B lines per
+// load under rotation, 8 loads per (pixel, view).  Here a block owns a 32x32 output tile; for every view the source
+// footprint of the tile (bounding box of its four warped corners -- a homography with Z > 0 maps the tile to a convex
+// quadrilateral -- widened to 16 B columns, +1 pixel of slack) is copied row by row with 16-byte cp.async
+// (coalesced, double buffered: view n+1 streams in while view n is sampled) and the 8 bilinear taps come from
+// shared memory (8x4 patches per warp, row stride = 4 mod 8 floats: conflict-free along x, y and diagonals).
+// Views whose footprint does not fit (or with a non-positive Z at a corner) take the global gather for that view.
+// ----------------------------------------------------------------------------------------------
+#define CT_TILE 32
+#define CT_THREADS 256
+#define CT_CAP 4096  // floats per plane and buffer
+
+struct CtMeta { int bx0, by0, bw, bh; };  // bw = staged width (multiple of 4), bh = rows; bh == 0: nothing to sample; bw < 0: gather path
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+__device__ __forceinline__ int ct_stride(int bw) {  // multiple of 4, congruent 4 mod 8
+  return (bw & 4) ? bw : bw + 4;
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+combine_heatmap_tiled_kernel(const float* __restrict__ heat, const float* __restrict__ mask,
+                             const float* __restrict__ Hinv, int N, int H, int W, const float* __restrict__ xs,
+                             const float* __restrict__ ys, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sh[];
+  float* bufs = sh;                                  // 2 buffers x 2 planes x CT_CAP
+  float* hs = bufs + 4 * CT_CAP;                     // N*9
+  CtMeta* meta = reinterpret_cast<CtMeta*>(hs + ((N * 9 + 3) & ~3));  // N
+  heat += (size_t)blockIdx.y * N * H * W;
+  mask += (size_t)blockIdx.y * N * H * W;
+  Hinv += (size_t)blockIdx.y * N * 9;
+  out += (size_t)blockIdx.y * H * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (W + CT_TILE - 1) / CT_TILE;
+  const int tx0 = (blockIdx.x % tiles_x) * CT_TILE, ty0 = (blockIdx.x / tiles_x) * CT_TILE;
+  for (int i = tid; i < N * 9; i += CT_THREADS) hs[i] = Hinv[i];
+  __syncthreads();
+  // footprint of the tile under every view
+  for (int n = tid; n < N; n += CT_THREADS) {
+    const float* h = hs + n * 9;
+    const int cx[2] = {tx0, min(tx0 + CT_TILE - 1, W - 1)}, cy[2] = {ty0, min(ty0 + CT_TILE - 1, H - 1)};
+    float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float gx = __ldg(xs + cx[c & 1]), gy = __ldg(ys + cy[c >> 1]);
+      float Z = fmaf(h[7], gy, h[6] * gx) + h[8];
+      float nx, ny;
+      homography_apply(h, gx, gy, nx, ny);
+      float ix = ((nx + 1.f) / 2.f) * (float)(W - 1), iy = ((ny + 1.f) / 2.f) * (float)(H - 1);
+      ok = ok && Z > 1e-6f && fabsf(ix) < 1.0e6f && fabsf(iy) < 1.0e6f;
+      xmin = fminf(xmin, ix); xmax = fmaxf(xmax, ix); ymin = fminf(ymin, iy); ymax = fmaxf(ymax, iy);
+    }
+    CtMeta m;
+    m.bx0 = m.by0 = m.bh = 0;
+    m.bw = -1;
+    if (ok) {
+      int x0 = max((int)floorf(xmin) - 1, 0) & ~3, x1 = min(((int)floorf(xmax) + 3 + 3) & ~3, W);
+      int y0 = max((int)floorf(ymin) - 1, 0), y1 = min((int)floorf(ymax) + 3, H);
+      if (x1 <= x0 || y1 <= y0) {
+        m.bw = 4; m.bh = 0;  // the whole footprint is outside the image: every tap is zero
+      } else if (ct_stride(x1 - x0) * (y1 - y0) <= CT_CAP) {
+        m.bx0 = x0; m.by0 = y0; m.bw = x1 - x0; m.bh = y1 - y0;
+      }
+    }
+    meta[n] = m;
+  }
+  __syncthreads();
+
+  auto prefetch = [&](int n) {
+    const CtMeta m = meta[n];
+    if (m.bw > 0 && m.bh > 0) {
+      float* bh_ = bufs + (n & 1) * 2 * CT_CAP;
+      float* bm_ = bh_ + CT_CAP;
+      const int vpr = m.bw >> 2, stride = ct_stride(m.bw), nvec = vpr * m.bh;
+      const float* hp = heat + (size_t)n * H * W + (size_t)m.by0 * W + m.bx0;
+      const float* mp = mask + (size_t)n * H * W + (size_t)m.by0 * W + m.bx0;
+      for (int v = tid; v < nvec; v += CT_THREADS) {
+        int row = v / vpr, c4 = (v - row * vpr) << 2;
+        cp_async16(bh_ + row * stride + c4, hp + (size_t)row * W + c4);
+        cp_async16(bm_ + row * stride + c4, mp + (size_t)row * W + c4);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // pixel k of this thread: 8x4 patch p = warp + 8k of the 4 x 8 patch grid of the tile
+  float gxv[4], gyv[4], sum_h[4], sum_m[4];
+  bool inside[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int p = warp + 8 * k;
+    int x = tx0 + (p & 3) * 8 + (lane & 7), y = ty0 + (p >> 2) * 4 + (lane >> 3);
+    inside[k] = x < W && y < H;
+    gxv[k] = inside[k] ? __ldg(xs + x) : 0.f;
+    gyv[k] = inside[k] ? __ldg(ys + y) : 0.f;
+    sum_h[k] = 0.f;
+    sum_m[k] = 0.f;
+  }
+  const size_t plane = (size_t)H * W;
+  prefetch(0);
+  for (int n = 0; n < N; ++n) {
+    if (n + 1 < N) {
+      prefetch(n + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const CtMeta m = meta[n];
+    if (m.bh != 0 || m.bw < 0) {
+      const float* h = hs + n * 9;
+      const bool staged = m.bw > 0;
+      const float* bh_ = bufs + (n & 1) * 2 * CT_CAP;
+      const float* bm_ = bh_ + CT_CAP;
+      const int stride = ct_stride(m.bw > 0 ? m.bw : 4);
+      const float* hp = heat + n * plane;
+      const float* mp = mask + n * plane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!inside[k]) continue;
+        float nx, ny;
+        homography_apply(h, gxv[k], gyv[k], nx, ny);
+        float ix = ((nx + 1.f) / 2.f) * (float)(W - 1);
+        float iy = ((ny + 1.f) / 2.f) * (float)(H - 1);
+        float fx = floorf(ix), fy = floorf(iy);
+        if (!(fx >= -1.f && fx < (float)W && fy >= -1.f && fy < (float)H)) continue;
+        int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+        float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+        float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+        bool xin0 = x0 >= 0, xin1 = x1 < W, yin0 = y0 >= 0, yin1 = y1 < H;
+        // staged taps must also lie inside the staged box (they do, by construction; the test keeps a rounding
+        // surprise from reading the wrong pixel: such a tap goes to global memory instead)
+        bool box = staged && x0 >= m.bx0 - (xin0 ? 0 : 1) && x1 < m.bx0 + m.bw + (xin1 ? 0 : 1) &&
+                   y0 >= m.by0 - (yin0 ? 0 : 1) && y1 < m.by0 + m.bh + (yin1 ? 0 : 1);
+        float ah = 0.f, am = 0.f;
+        if (box) {
+          const int o00 = (y0 - m.by0) * stride + (x0 - m.bx0);
+          if (yin0) {
+            if (xin0) { float mm = bm_[o00], w = wx0 * wy0; am += mm * w; ah += (bh_[o00] * mm) * w; }
+            if (xin1) { float mm = bm_[o00 + 1], w = wx1 * wy0; am += mm * w; ah += (bh_[o00 + 1] * mm) * w; }
+          }
+          if (yin1) {
+            if (xin0) { float mm = bm_[o00 + stride], w = wx0 * wy1; am += mm * w; ah += (bh_[o00 + stride] * mm) * w; }
+            if (xin1) { float mm = bm_[o00 + stride + 1], w = wx1 * wy1; am += mm * w; ah += (bh_[o00 + stride + 1] * mm) * w; }
+          }
+        } else {
+          if (yin0) {
+            size_t r = (size_t)y0 * W;
+            if (xin0) { float mm = __ldg(mp + r + x0), w = wx0 * wy0; am += mm * w; ah += (__ldg(hp + r + x0) * mm) * w; }
+            if (xin1) { float mm = __ldg(mp + r + x1), w = wx1 * wy0; am += mm * w; ah += (__ldg(hp + r + x1) * mm) * w; }
+          }
+          if (yin1) {
+            size_t r = (size_t)y1 * W;
+            if (xin0) { float mm = __ldg(mp + r + x0), w = wx0 * wy1; am += mm * w; ah += (__ldg(hp + r + x0) * mm) * w; }
+            if (xin1) { float mm = __ldg(mp + r + x1), w = wx1 * wy1; am += mm * w; ah += (__ldg(hp + r + x1) * mm) * w; }
+          }
+        }
+        sum_h[k] += ah;
+        sum_m[k] += am;
+      }
+    }
+    __syncthreads();  // buffer (n & 1) is refilled by the prefetch of view n + 2
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!inside[k]) continue;
+    int p = warp + 8 * k;
+    int x = tx0 + (p & 3) * 8 + (lane & 7), y = ty0 + (p >> 2) * 4 + (lane >> 3);
+    out[(size_t)y * W + x] = sum_h[k] / sum_m[k];  // 0/0 -> NaN exactly like the reference when no view covers the pixel
+  }
+}
+
 extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const float* Hinv, int I, int N, int H, int W,
                                    const float* xs, const float* ys, float* out, void* stream) {
   SSP_REQUIRE(heat && mask && Hinv && xs && ys && out, "ssp_combine_heatmap: null pointer");
   SSP_REQUIRE(I > 0 && I <= 65535 && N > 0 && H > 0 && W > 0, "ssp_combine_heatmap: bad sizes I=%d N=%d H=%d W=%d", I, N, H, W);
+  // tiled (shared-memory staged) kernel whenever rows can be copied in 16-byte pieces; SSP_COMBINE=gather forces the
+  // direct-gather kernel
+  static const bool force_gather = [] { const char* e = getenv("SSP_COMBINE"); return e && e[0] == 'g'; }();
+  size_t smem_t = (4 * (size_t)CT_CAP + (((size_t)N * 9 + 3) & ~(size_t)3)) * sizeof(float) + (size_t)N * sizeof(CtMeta);
+  bool tiled = !force_gather && W % 4 == 0 && ((((uintptr_t)heat | (uintptr_t)mask) & 15) == 0) && smem_t <= 200 * 1024;
+  if (tiled) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      SSP_CUDA_CALL(cudaFuncSetAttribute(combine_heatmap_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    dim3 nblk(ssp_ceil_div(W, CT_TILE) * ssp_ceil_div(H, CT_TILE), I);
+    combine_heatmap_tiled_kernel<<<nblk, CT_THREADS, smem_t, (cudaStream_t)stream>>>(heat, mask, Hinv, N, H, W, xs, ys, out);
+    SSP_CUDA_CHECK_LAUNCH("combine_heatmap_tiled_kernel");
+    return SSP_OK;
+  }
   size_t smem = ((size_t)N * 9 + 2 * CH_PIX * CH_GROUPS) * sizeof(float);
   SSP_REQUIRE(smem <= 48 * 1024, "ssp_combine_heatmap: N=%d views exceed the shared-memory table (max ~1100)", N);
   dim3 nblk(ssp_ceil_div(W, 8) * ssp_ceil_div(H, 8), I);
