@@ -157,6 +157,18 @@ int ssp_sem_ce_up8(const float* logits_lr, const long long* labels, int B, int C
 int ssp_sem_ce_up8_bwd(const float* gsum, const float* out3, const float* gout, int B, int C, int Hc, int Wc,
                        float* dlogits /*[B,C,Hc,Wc]*/, void* stream);
 
+/* ---- sparse descriptors: sampling at keypoints and two-way nearest-neighbour matching ---------
+ * ssp_sample_desc replaces SuperPointFrontend_torch.sample_desc_from_points (models/model_wrap.py:295-313):
+ *   coarse [D,Hc,Wc] fp32, pts = the reference's [3,K] float64 array (x row, y row, conf row; device memory),
+ *   desc [D,K] fp32 = bilinear samples (grid_sample align_corners=True, zero padding), L2-normalised per point.
+ * ssp_nn_match replaces the K1 x K2 part of PointTracker.nn_match_two_way (models/model_wrap.py:451-494):
+ *   best1[i] = (bits(min_j dist(i,j)) << 32 | argmin_j), best2[j] likewise over i, dist = sqrt(2 - 2 clip(d1_i . d2_j, -1, 1));
+ *   ties go to the lowest index (np.argmin).  The threshold / mutual test on 2K numbers stays with the caller. */
+int ssp_sample_desc(const float* coarse, const double* pts, int K, int D, int Hc, int Wc, int cell, float* desc,
+                    void* stream);
+int ssp_nn_match(const float* desc1 /*[D,K1]*/, const float* desc2 /*[D,K2]*/, int D, int K1, int K2,
+                 unsigned long long* best1 /*[K1]*/, unsigned long long* best2 /*[K2]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

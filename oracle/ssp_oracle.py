@@ -482,3 +482,44 @@ def sem_loss(pred, label, ignore_index=133, grad=False, gout=1.0):
     if lowres:
         g = upsample_bilinear_adjoint(g, pred.shape[2:])
     return loss, g.astype(f32)
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse descriptors: sampling at keypoints + two-way nearest-neighbour matching  
+# ------------------------------------------------------------------------------------------------
+def sample_desc_from_points(coarse_desc, pts, cell=8):
+    """models/model_wrap.py:295-313.  coarse_desc [1,D,Hc,Wc], pts [3,K] (x, y, conf) -> float32 [D,K]."""
+    coarse_desc = np.asarray(coarse_desc, dtype=f32)
+    D, Hc, Wc = coarse_desc.shape[1:]
+    H, W = Hc * cell, Wc * cell
+    pts = np.asarray(pts)
+    if pts.shape[1] == 0:
+        return np.zeros((D, 0))
+    samp = pts[:2, :].astype(np.float64).copy()
+    samp[0, :] = samp[0, :] / (float(W) / 2.0) - 1.0
+    samp[1, :] = samp[1, :] / (float(H) / 2.0) - 1.0
+    grid = samp.T.astype(f32).reshape(1, 1, -1, 2)
+    desc = grid_sample(coarse_desc, grid, "bilinear").reshape(D, -1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (desc / np.linalg.norm(desc, axis=0)[np.newaxis, :]).astype(f32)
+
+
+def nn_match_two_way(desc1, desc2, nn_thresh):
+    """models/model_wrap.py:451-494.  [D,K1], [D,K2] -> float64 [3,L] (index 1, index 2, distance)."""
+    assert desc1.shape[0] == desc2.shape[0]
+    if desc1.shape[1] == 0 or desc2.shape[1] == 0:
+        return np.zeros((3, 0))
+    if nn_thresh < 0.0:
+        raise ValueError("'nn_thresh' should be non-negative")
+    dmat = np.dot(desc1.T, desc2)
+    dmat = np.sqrt(2 - 2 * np.clip(dmat, -1, 1))
+    idx = np.argmin(dmat, axis=1)
+    scores = dmat[np.arange(dmat.shape[0]), idx]
+    keep = scores < nn_thresh
+    idx2 = np.argmin(dmat, axis=0)
+    keep = np.logical_and(keep, np.arange(len(idx)) == idx2[idx])
+    matches = np.zeros((3, int(keep.sum())))
+    matches[0, :] = np.arange(desc1.shape[1])[keep]
+    matches[1, :] = idx[keep]
+    matches[2, :] = scores[keep]
+    return matches

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ssp_sem_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ssp_sem_ce_up8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "ssp_sem_ce_up8_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "ssp_sample_desc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "ssp_nn_match": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

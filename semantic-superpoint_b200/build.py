@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libssp_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "warp.cu", "detector.cu", "semantic.cu", "heatmap.cu", "nms.cu", "desc_common.cu", "desc_simt.cu", "desc_tc.cu"]
+SOURCES = ["api.cu", "warp.cu", "detector.cu", "semantic.cu", "match.cu", "heatmap.cu", "nms.cu", "desc_common.cu", "desc_simt.cu", "desc_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

@@ -30,10 +30,11 @@ def _bind(obj, name, fn, bound):
     bound.append("%s.%s" % (getattr(obj, "__name__", type(obj).__name__), name))
 
 
-def install(utils_module=None, trainer_class=None, frontend_class=None, export_module=None):
+def install(utils_module=None, trainer_class=None, frontend_class=None, export_module=None, tracker_class=None):
     """Patch `utils.utils` (imported from sys.path unless given) and, when passed, the trainer class
     (`Train_model_heatmap_all`: detector_loss, getMasks, sem_loss), the inference front-end class
-    (`SuperPointFrontend_torch`: getPtsFromHeatmap, nms_fast) and the `export` module (combine_heatmap)."""
+    (`SuperPointFrontend_torch`: getPtsFromHeatmap, nms_fast, sample_desc_from_points), the tracker class
+    (`PointTracker`: nn_match_two_way) and the `export` module (combine_heatmap)."""
     bound = []
     if utils_module is None:
         utils_module = importlib.import_module("utils.utils")
@@ -50,6 +51,15 @@ def install(utils_module=None, trainer_class=None, frontend_class=None, export_m
               lambda self, heatmap: _u.getPtsFromHeatmap(heatmap, self.conf_thresh, self.nms_dist), bound)
         _bind(frontend_class, "nms_fast",
               lambda self, in_corners, H, W, dist_thresh: _u.nms_fast(in_corners, H, W, dist_thresh), bound)
+        _bind(frontend_class, "sample_desc_from_points",
+              lambda self, coarse_desc, pts: _u.sample_desc_from_points(coarse_desc, pts, self.cell), bound)
+    if tracker_class is not None:  # models/model_wrap.py PointTracker
+
+        def _nn(self, desc1, desc2, nn_thresh):
+            self.mscores = _u.nn_match_two_way(desc1, desc2, nn_thresh)   # the reference keeps the matches here too
+            return self.mscores
+
+        _bind(tracker_class, "nn_match_two_way", _nn, bound)
     if export_module is None:
         export_module = sys.modules.get("export")
     if export_module is not None:

@@ -510,3 +510,55 @@ def descriptor_loss(descriptors, descriptors_warped, homographies, mask_valid=No
     loss, pos_sum, neg_sum, wpts = out
     mask = LazyPairMask(wpts, B, Hc, Wc, int(cell_size), float(descriptor_dist))
     return loss, mask, pos_sum, neg_sum
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f rank 3: sparse descriptors (export_descriptor / evaluation, the step after NMS)
+# ------------------------------------------------------------------------------------------------
+def sample_desc_from_points(coarse_desc, pts, cell=8):
+    """reference: models/model_wrap.py:295-313 (SuperPointFrontend_torch.sample_desc_from_points(self, coarse_desc, pts)).
+
+    coarse_desc [1,D,Hc,Wc] tensor, pts numpy [3,K] (x, y, conf) -> numpy float32 [D,K], bilinear samples of the coarse
+    map at the keypoints (grid_sample align_corners=True), L2-normalised per point; K = 0 -> zeros((D,0))."""
+    D = int(coarse_desc.shape[1])
+    pts = np.asarray(pts)
+    K = int(pts.shape[1])
+    if K == 0:
+        return np.zeros((D, 0))
+    dev = _cuda_device("cuda", coarse_desc)
+    cd = f32c(coarse_desc.detach(), dev)
+    if cd.dim() != 4 or cd.shape[0] != 1:
+        raise RuntimeError("sample_desc_from_points: coarse_desc must be [1,D,Hc,Wc], got %s" % (tuple(coarse_desc.shape),))
+    p = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64)).to(dev)
+    out = torch.empty((D, K), dtype=torch.float32, device=dev)
+    call("ssp_sample_desc", ptr(cd), ptr(p), K, D, int(cd.shape[2]), int(cd.shape[3]), int(cell), ptr(out), stream_of(out))
+    return out.cpu().numpy()
+
+
+def nn_match_two_way(desc1, desc2, nn_thresh):
+    """reference: models/model_wrap.py:451-494 (PointTracker.nn_match_two_way(self, desc1, desc2, nn_thresh)).
+
+    desc1 [D,K1], desc2 [D,K2] unit descriptors (numpy or tensors) -> numpy float64 [3,L] rows (index in 1, index in 2,
+    distance) of the mutual nearest neighbours closer than nn_thresh, in increasing index-1 order."""
+    if desc1.shape[0] != desc2.shape[0]:
+        raise AssertionError("nn_match_two_way: descriptor dimensions differ")
+    K1, K2 = int(desc1.shape[1]), int(desc2.shape[1])
+    if K1 == 0 or K2 == 0:
+        return np.zeros((3, 0))
+    if nn_thresh < 0.0:
+        raise ValueError("'nn_thresh' should be non-negative")
+    dev = _cuda_device("cuda", *[d for d in (desc1, desc2) if isinstance(d, torch.Tensor)])
+    t = lambda d: f32c(d.detach() if isinstance(d, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(d, dtype=np.float32)), dev)
+    a, b = t(desc1), t(desc2)
+    best = torch.empty((K1 + K2,), dtype=torch.int64, device=dev)
+    call("ssp_nn_match", ptr(a), ptr(b), int(a.shape[0]), K1, K2, ptr(best[:K1]), ptr(best[K1:]), stream_of(a))
+    keys = best.cpu().numpy().view(np.uint64)
+    idx = (keys[:K1] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    scores = (keys[:K1] >> np.uint64(32)).astype(np.uint32).view(np.float32).astype(np.float64)
+    idx2 = (keys[K1:] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    keep = np.logical_and(scores < nn_thresh, np.arange(K1) == idx2[idx])     # model_wrap.py:476-481
+    matches = np.zeros((3, int(keep.sum())))
+    matches[0, :] = np.arange(K1)[keep]
+    matches[1, :] = idx[keep]
+    matches[2, :] = scores[keep]
+    return matches

@@ -108,9 +108,33 @@ def gen_semantic():
          dfull2_sample=full2.grad.numpy()[:, ::9, ::3, ::5])
 
 
+def gen_matching():
+    """sample_desc_from_points / nn_match_two_way of the unmodified reference (models/model_wrap.py)."""
+    import models.model_wrap as MW
+    t = torch.from_numpy
+    me = types.SimpleNamespace(cell=8, device="cpu")
+    coarse = synth.unit_descriptors(1, 256, 15, 20, 111, smooth=0.5)            # 120 x 160 image
+    coarse2 = (coarse + 0.35 * synth.unit_descriptors(1, 256, 15, 20, 112, smooth=0.5)).astype(np.float32)
+    n = 90
+    pts = np.stack([synth.uniform((n,), 113) * 159, synth.uniform((n,), 114) * 119, synth.uniform((n,), 115)]).astype(np.float64)
+    pts[:2] = np.round(pts[:2])                                                 # keypoints are integer pixels
+    pts[:2, :4] = [[0, 159, 0, 159], [0, 0, 119, 119]]                          # image corners
+    pts2 = pts.copy()
+    pts2[:2] = np.clip(pts2[:2] + np.round((synth.uniform((2, n), 116) - 0.5) * 3), 0, [[159], [119]])
+    pts2 = pts2[:, 17:]                                                         # different counts on the two sides
+    d1 = MW.SuperPointFrontend_torch.sample_desc_from_points(me, t(coarse), pts)
+    d2 = MW.SuperPointFrontend_torch.sample_desc_from_points(me, t(coarse2), pts2)
+    out = {}
+    for thr in (0.36, 0.7):
+        out["matches_%d" % int(round(thr * 100))] = MW.PointTracker.nn_match_two_way(types.SimpleNamespace(), d1, d2, thr)
+    save("matching", pts=pts, pts2=pts2, desc1=d1, desc2=d2, **out)   # coarse maps: synth seeds 111 / 112, see the tests
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "semantic":
         return gen_semantic()
+    if len(sys.argv) > 1 and sys.argv[1] == "matching":
+        return gen_matching()
     torch.manual_seed(0)
     t = torch.from_numpy
 
@@ -242,6 +266,7 @@ def main():
     save("desc_identity", loss=rI["loss"], pos=rI["pos"], neg=rI["neg"])
 
     gen_semantic()
+    gen_matching()
 
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:
         json.dump({"torch": torch.__version__, "numpy": np.__version__, "cv2": cv2.__version__,

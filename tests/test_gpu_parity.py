@@ -459,6 +459,36 @@ def test_loss_step_semantic():
     close(res["grads"][4], d1, atol=1e-4 * np.abs(d1).max())
 
 
+# ------------------------------------------------------------------ 8f rank 3: sparse descriptors + matching
+def test_sample_desc_and_nn_match(golden):
+    g = golden("matching")
+    coarse = synth.unit_descriptors(1, 256, 15, 20, 111, smooth=0.5)
+    coarse2 = (coarse + 0.35 * synth.unit_descriptors(1, 256, 15, 20, 112, smooth=0.5)).astype(np.float32)
+    d1 = S.utils.sample_desc_from_points(cu(coarse), g["pts"])
+    d2 = S.utils.sample_desc_from_points(cu(coarse2), g["pts2"])
+    assert d1.dtype == np.float32 and d1.shape == (256, 90)
+    close(d1, g["desc1"], atol=1e-6); close(d2, g["desc2"], atol=1e-6)
+    for thr, key in ((0.36, "matches_36"), (0.7, "matches_70")):
+        m = S.utils.nn_match_two_way(g["desc1"], g["desc2"], thr)          # numpy in, like the reference
+        assert m.dtype == np.float64 and np.array_equal(m[:2], g[key][:2])
+        close(m[2], g[key][2], atol=2e-4)   # sqrt(2 - 2 dot) amplifies fp32 rounding of the dot near dist = 0
+        m2 = S.utils.nn_match_two_way(cu(d1), cu(d2), thr)                   # device tensors, own descriptors
+        assert np.array_equal(m2[:2], g[key][:2])
+    assert S.utils.nn_match_two_way(g["desc1"], g["desc2"][:, :0], 0.7).shape == (3, 0)
+    assert S.utils.sample_desc_from_points(cu(coarse), np.zeros((3, 0))).shape == (256, 0)
+    # HPatches-size case (BASELINE configs[4]): 1000 x 1000 keypoints at 480x640 against the oracle
+    big = synth.unit_descriptors(1, 256, 60, 80, 121, smooth=0.4)
+    big2 = (big + 0.5 * synth.unit_descriptors(1, 256, 60, 80, 122, smooth=0.4)).astype(np.float32)
+    p1 = np.stack([np.round(synth.uniform((1000,), 123) * 639), np.round(synth.uniform((1000,), 124) * 479), synth.uniform((1000,), 125)])
+    p2 = p1[:, ::-1][:, :937].copy()
+    e1, e2 = S.utils.sample_desc_from_points(cu(big), p1), S.utils.sample_desc_from_points(cu(big2), p2)
+    close(e1, O.sample_desc_from_points(big, p1), atol=1e-6)
+    ref = O.nn_match_two_way(e1, e2, 0.7)
+    got = S.utils.nn_match_two_way(e1, e2, 0.7)
+    same = set(map(tuple, ref[:2].T.astype(int))) ^ set(map(tuple, got[:2].T.astype(int)))
+    assert len(same) <= 2 and ref.shape[1] > 300       # near-tie distances may flip between BLAS and the kernel
+
+
 def test_abi_errors():
     from ssp_b200 import _lib
     lib = _lib.load()

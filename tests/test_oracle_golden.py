@@ -131,3 +131,24 @@ def test_semantic_head(golden):
         close(loss_f, g[loss_k], rtol=1e-5)
         sy, sx = (5, 7) if lr_k == "lr" else (3, 5)
         close(d_f[:, ::9, ::sy, ::sx], g[ds_k], atol=1e-4 * np.abs(g[ds_k]).max())
+
+
+def _matching_inputs():
+    coarse = synth.unit_descriptors(1, 256, 15, 20, 111, smooth=0.5)
+    coarse2 = (coarse + 0.35 * synth.unit_descriptors(1, 256, 15, 20, 112, smooth=0.5)).astype(np.float32)
+    return coarse, coarse2
+
+
+def test_sparse_descriptors_and_matching(golden):
+    """sample_desc_from_points + nn_match_two_way (models/model_wrap.py:295-313, 451-494)."""
+    g = golden("matching")
+    coarse, coarse2 = _matching_inputs()
+    close(O.sample_desc_from_points(coarse, g["pts"]), g["desc1"], atol=1e-6)
+    close(O.sample_desc_from_points(coarse2, g["pts2"]), g["desc2"], atol=1e-6)
+    for thr, key in ((0.36, "matches_36"), (0.7, "matches_70")):
+        m = O.nn_match_two_way(g["desc1"], g["desc2"], thr)
+        assert np.array_equal(m[:2], g[key][:2])
+        close(m[2], g[key][2], atol=1e-6)
+    assert g["matches_36"].shape[1] < g["matches_70"].shape[1]
+    assert O.nn_match_two_way(g["desc1"], g["desc2"][:, :0], 0.7).shape == (3, 0)
+    assert O.sample_desc_from_points(coarse, np.zeros((3, 0))).shape == (256, 0)
