@@ -100,6 +100,13 @@ int ssp_desc_pos_fwd(const float* D /*[B,Dch,Hc,Wc]*/, const float* Dw, const fl
                      int Hc, int Wc, int Dch, int cell, float dist, float lamda, float mpos, float mneg,
                      double* partials, int* rowcol, float* rowdot, int* colcnt, int* colrow, float* coldot,
                      void* stream);
+/* Same contract from the packed hi/lo planes [B,Nc_pad,256] bf16 of D (A*) and Dw (B*) written by ssp_desc_pack2 (bf16x3
+ * engine): a cell's descriptor is 2 x 512 contiguous bytes there instead of 256 channels 4*Nc bytes apart. */
+int ssp_desc_pos_planes_nblocks(int B, int Nc);
+int ssp_desc_pos_fwd_planes(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* wpts,
+                            const float* mv_pad, int B, int Hc, int Wc, int cell, float dist, float lamda, float mpos,
+                            float mneg, double* partials, int* rowcol, float* rowdot, int* colcnt, int* colrow,
+                            float* coldot, void* stream);
 int ssp_desc_dense_simt_nblocks(int B, int Nc);
 int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const float* mv_pad, int B, int Hc, int Wc, int Dch,
                             float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ssp_desc_pos_nblocks": (_I, [_I, _I]),
     "ssp_desc_maxp": (_I, []),
     "ssp_desc_pos_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "ssp_desc_pos_planes_nblocks": (_I, [_I, _I]),
+    "ssp_desc_pos_fwd_planes": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ssp_desc_dense_simt_nblocks": (_I, [_I, _I]),
     "ssp_desc_dense_fwd_simt": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "ssp_desc_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

@@ -224,6 +224,137 @@ extern "C" int ssp_desc_pos_fwd(const float* D, const float* Dw, const float* wp
 }
 
 // ----------------------------------------------------------------------------------------------
+// positive pairs, forward, from the PACKED planes (bf16x3 engine).  NCHW keeps the 256 channels of a cell 4.8 KB
+// apart, so the kernel above pays one 32 B sector (and one L1 wavefront) per channel per gathered partner; the
+// [cell][256] hi/lo planes that the tensor-core kernels consume hold a cell's descriptor as 2 x 512 contiguous bytes.
+// One warp per row: lanes test the candidate window in parallel (ballot compaction keeps the k-major, l-minor order
+// of the sequential scan), then every partner costs four fully coalesced 512 B loads and a warp reduction.
+// hi + lo carries 16 mantissa bits (relative error 2^-17 per element): the dot is as accurate as the bf16x3 GEMM's own
+// value for the pair, which is what the negative-hinge correction must cancel.
+// partials: 4 doubles per block, as above.  Same lists.
+// ----------------------------------------------------------------------------------------------
+#define POSP_WARPS 8
+__device__ __forceinline__ void bf16x8_sum(const uint4& h, const uint4& l, float (&v)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(POSP_WARPS * 32)
+desc_pos_fwd_planes_kernel(const uint4* __restrict__ Ahi, const uint4* __restrict__ Alo, const uint4* __restrict__ Bhi,
+                           const uint4* __restrict__ Blo, const float2* __restrict__ wpts,
+                           const float* __restrict__ mv_pad, DescGeom g, double* __restrict__ partials,
+                           int* __restrict__ rowcol, float* __restrict__ rowdot, int* __restrict__ colcnt,
+                           int* __restrict__ colrow, float* __restrict__ coldot) {
+  __shared__ double sacc[POSP_WARPS][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, r = blockIdx.x * POSP_WARPS + warp;  // grid.x covers Nc_pad rows
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  // ---- candidate scan, lanes in parallel
+  int mycol = -1, cnt = 0;  // lane n < cnt holds the n-th partner
+  if (r < g.Nc) {
+    const float2 w = wpts[(size_t)b * g.Nc_pad + r];
+    int k0, k1, l0, l1;
+    pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
+    const int nl = l1 - l0 + 1, ncand = (k1 >= k0 && nl > 0) ? (k1 - k0 + 1) * nl : 0;
+    for (int base = 0; base < ncand && cnt < DESC_MAXP; base += 32) {
+      const int i = base + lane;
+      bool hit = false;
+      int c = -1;
+      if (i < ncand) {
+        c = (k0 + i / nl) * g.Wc + (l0 + i % nl);
+        float cx, cy;
+        cell_center(c, g.Wc, g.cell, cx, cy);
+        hit = pair_positive(w.x, w.y, cx, cy, g.dist);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+      // hand the hit of this lane to lane `slot`
+#pragma unroll 1
+      for (unsigned m = bal; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const int s = __shfl_sync(0xffffffffu, slot, src), cc = __shfl_sync(0xffffffffu, c, src);
+        if (lane == s && s < DESC_MAXP) mycol = cc;
+      }
+      cnt = min(cnt + __popc(bal), DESC_MAXP);
+    }
+  }
+  if (r < g.Nc_pad && lane < DESC_MAXP) rowcol[((size_t)b * g.Nc_pad + r) * DESC_MAXP + lane] = lane < cnt ? mycol : -1;
+  if (cnt) {
+    const size_t ra = ((size_t)b * g.Nc_pad + r) * 32 + lane;  // uint4 index: 256 bf16 = 32 x 16 B per cell
+    float a[8];
+    bf16x8_sum(__ldg(Ahi + ra), __ldg(Alo + ra), a);
+    for (int n = 0; n < cnt; ++n) {
+      const int c = __shfl_sync(0xffffffffu, mycol, n);
+      const size_t rb = ((size_t)b * g.Nc_pad + c) * 32 + lane;
+      float w8[8];
+      bf16x8_sum(__ldg(Bhi + rb), __ldg(Blo + rb), w8);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part = fmaf(a[i], w8[i], part);
+      const float dot = warp_sum(part);
+      if (lane == 0) {
+        float mv = mv_pad[(size_t)b * g.Nc_pad + c];
+        float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
+        float negc = fmaxf(dot - g.mneg, 0.f);
+        acc[0] += (double)pos;
+        acc[1] += (double)(pos * mv);
+        acc[2] += (double)negc;
+        acc[3] += (double)(negc * mv);
+        rowdot[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n] = dot;
+        int slot = atomicAdd(colcnt + (size_t)b * g.Nc_pad + c, 1);
+        if (slot < DESC_MAXP) {
+          colrow[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = r;
+          coldot[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = dot;
+        } else {
+          atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, 1);  // overflow counter
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sacc[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < POSP_WARPS; ++w) v += sacc[w][threadIdx.x];
+    partials[4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + threadIdx.x] = v;
+  }
+}
+
+extern "C" int ssp_desc_pos_planes_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / POSP_WARPS); }
+
+// Same contract as ssp_desc_pos_fwd, reading the packed hi/lo planes [B, Nc_pad, 256] of D (A*) and Dw (B*).
+extern "C" int ssp_desc_pos_fwd_planes(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
+                                       const float* wpts, const float* mv_pad, int B, int Hc, int Wc, int cell, float dist,
+                                       float lamda, float mpos, float mneg, double* partials, int* rowcol, float* rowdot,
+                                       int* colcnt, int* colrow, float* coldot, void* stream) {
+  SSP_REQUIRE(Ahi && Alo && Bhi && Blo && wpts && mv_pad && partials && rowcol && rowdot && colcnt && colrow && coldot,
+              "ssp_desc_pos_fwd_planes: null pointer");
+  SSP_REQUIRE(((((uintptr_t)Ahi | (uintptr_t)Alo | (uintptr_t)Bhi | (uintptr_t)Blo) & 15) == 0),
+              "ssp_desc_pos_fwd_planes: planes must be 16-byte aligned");
+  DescGeom g;
+  SSP_REQUIRE(fill_geom(g, B, Hc, Wc, 256, cell, dist, lamda, mpos, mneg) == 0 && B <= 65535, "ssp_desc_pos_fwd_planes: bad sizes");
+  SSP_REQUIRE(dist >= 0.f && dist <= (float)cell,
+              "ssp_desc_pos_fwd_planes: descriptor_dist %.3f > cell_size %d is not supported (sparse positive lists hold %d pairs per cell)",
+              dist, cell, DESC_MAXP);
+  cudaStream_t st = (cudaStream_t)stream;
+  SSP_CUDA_CALL(cudaMemsetAsync(colcnt, 0, ((size_t)B * g.Nc_pad + 1) * sizeof(int), st));
+  dim3 grid(g.Nc_pad / POSP_WARPS, B);
+  desc_pos_fwd_planes_kernel<<<grid, POSP_WARPS * 32, 0, st>>>(
+      (const uint4*)Ahi, (const uint4*)Alo, (const uint4*)Bhi, (const uint4*)Blo, reinterpret_cast<const float2*>(wpts), mv_pad, g,
+      partials, rowcol, rowdot, colcnt, colrow, coldot);
+  SSP_CUDA_CHECK_LAUNCH("desc_pos_fwd_planes_kernel");
+  return SSP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
 // finalize: fixed-order sums of the partials, global-batch normaliser  [utils/utils.py:883-890]
 //   out8 = { loss_desc, pos_sum, neg_sum, normalization, num_loss, num_pos, num_neg, sum(mask_valid) }
 // ----------------------------------------------------------------------------------------------

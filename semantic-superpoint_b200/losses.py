@@ -266,7 +266,7 @@ class DescriptorLossFn(torch.autograd.Function):
 
         # sparse positive pairs: exact dots, partial sums, pair lists for the backward
         maxp = lib.ssp_desc_maxp()
-        npos = lib.ssp_desc_pos_nblocks(B, Nc)
+        npos = lib.ssp_desc_pos_planes_nblocks(B, Nc) if (engine == "bf16x3") else lib.ssp_desc_pos_nblocks(B, Nc)
         pos_part = torch.empty((npos, 4), dtype=torch.float64, device=dev)
         lists_i = torch.empty((3, B, Ncp, maxp), dtype=torch.int32, device=dev)   # rowcol, colrow, (colcnt in [2,:,:,0])
         lists_f = torch.empty((2, B, Ncp, maxp), dtype=torch.float32, device=dev)  # rowdot, coldot
@@ -289,19 +289,29 @@ class DescriptorLossFn(torch.autograd.Function):
             Blo = torch.empty_like(Bhi) if split else None
         neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
         out8 = torch.empty((8,), dtype=torch.float32, device=dev)
-        # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
-        with _Fork(dev) as fork:
-            call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos, mneg,
-                 ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), stream_of(Dc))
-        if engine == "fp32":
-            call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
-                 ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
-        else:
+        if split:
+            # bf16x3: the positive pairs read the packed hi/lo planes (2 x 512 contiguous bytes per cell instead of 256
+            # strided channels), so they run right after the pack, in front of the tensor-core kernel
             call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
+            call("ssp_desc_pos_fwd_planes", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc, cell,
+                 dist, lamda, mpos, mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
             call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
                  ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             planes = (Ahi, Alo)
-        fork.join()
+        else:
+            # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
+            with _Fork(dev) as fork:
+                call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos,
+                     mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), stream_of(Dc))
+            if engine == "fp32":
+                call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
+                     ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+            else:
+                call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
+                call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
+                     ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+                planes = (Ahi, Alo)
+            fork.join()
 
         if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
             raise RuntimeError("descriptor_loss: %d positive pairs overflowed the per-column lists" % int(colcnt[B * Ncp]))
