@@ -75,6 +75,11 @@ int ssp_flatten_detection(const float* semi /*[N,65,Hc,Wc]*/, int N, int Hc, int
 int ssp_combine_heatmap(const float* heat /*[I,N,H,W]*/, const float* mask /*[I,N,H,W]*/,
                         const float* Hinv /*[I,N,3,3]*/, int I, int N, int H, int W, const float* xs, const float* ys,
                         float* out /*[I,H,W]*/, void* stream);
+/* Same arguments and results through the shared-memory staged kernel (32x32 output tiles, source footprints copied with
+ * 16-byte cp.async); needs W % 4 == 0 and 16-byte aligned maps.  Opt-in: measured slower than the gather kernel at
+ * 240x320 (see heatmap.cu). */
+int ssp_combine_heatmap_tiled(const float* heat, const float* mask, const float* Hinv, int I, int N, int H, int W,
+                              const float* xs, const float* ys, float* out, void* stream);
 
 /* ---- a8 / a9: getPtsFromHeatmap + nms_fast (utils/utils.py:581-609, 653-712), box_nms (:612-650).
  *      stencil: device (2R+1)^2 bytes, 1 = suppressed offset.  pts: [I,3,capacity] float64 rows x,y,conf,

@@ -37,6 +37,7 @@ SIGNATURES = {
     "ssp_detector_loss_bwd_pair": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "ssp_flatten_detection": (_I, [_P, _I, _I, _I, _P, _P]),
     "ssp_combine_heatmap": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ssp_combine_heatmap_tiled": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ssp_nms_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "ssp_nms_fast": (_I, [_P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _Z, _P]),
     "ssp_box_nms": (_I, [_P, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),

@@ -261,17 +261,20 @@ combine_heatmap_tiled_kernel(const float* __restrict__ heat, const float* __rest
   }
 }
 
-extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const float* Hinv, int I, int N, int H, int W,
-                                   const float* xs, const float* ys, float* out, void* stream) {
+static int combine_launch(int variant /*0 gather, 1 tiled, -1 default*/, const float* heat, const float* mask,
+                          const float* Hinv, int I, int N, int H, int W, const float* xs, const float* ys, float* out,
+                          void* stream) {
   SSP_REQUIRE(heat && mask && Hinv && xs && ys && out, "ssp_combine_heatmap: null pointer");
   SSP_REQUIRE(I > 0 && I <= 65535 && N > 0 && H > 0 && W > 0, "ssp_combine_heatmap: bad sizes I=%d N=%d H=%d W=%d", I, N, H, W);
   // The direct-gather kernel is the default: measured on B200 (16 images x 100 views per call) the adaptation step ran
   // 9.5 k images/s with it and 8.6 k with the tiled kernel -- three 69 KB blocks per SM and two barriers per view hide
   // less latency than eight gather blocks, although the tiled kernel issues a third of the L1 wavefronts.
-  // SSP_COMBINE=tiled selects the staged kernel (kept for larger images / future tuning, parity-tested).
-  static const bool force_gather = [] { const char* e = getenv("SSP_COMBINE"); return !(e && e[0] == 't'); }();
+  // SSP_COMBINE=tiled makes the staged kernel the default (kept for larger images / future tuning, parity-tested).
+  static const bool env_tiled = [] { const char* e = getenv("SSP_COMBINE"); return e && e[0] == 't'; }();
   size_t smem_t = (4 * (size_t)CT_CAP + (((size_t)N * 9 + 3) & ~(size_t)3)) * sizeof(float) + (size_t)N * sizeof(CtMeta);
-  bool tiled = !force_gather && W % 4 == 0 && ((((uintptr_t)heat | (uintptr_t)mask) & 15) == 0) && smem_t <= 200 * 1024;
+  bool can_tile = W % 4 == 0 && ((((uintptr_t)heat | (uintptr_t)mask) & 15) == 0) && smem_t <= 200 * 1024;
+  SSP_REQUIRE(variant != 1 || can_tile, "ssp_combine_heatmap_tiled: needs W %% 4 == 0, 16-byte aligned maps and N <= ~3500 views");
+  bool tiled = variant == 1 || (variant < 0 && env_tiled && can_tile);
   if (tiled) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -289,4 +292,15 @@ extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const f
   combine_heatmap_kernel<<<nblk, CH_PIX * CH_GROUPS, smem, (cudaStream_t)stream>>>(heat, mask, Hinv, N, H, W, xs, ys, out);
   SSP_CUDA_CHECK_LAUNCH("combine_heatmap_kernel");
   return SSP_OK;
+}
+
+extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const float* Hinv, int I, int N, int H, int W,
+                                   const float* xs, const float* ys, float* out, void* stream) {
+  return combine_launch(-1, heat, mask, Hinv, I, N, H, W, xs, ys, out, stream);
+}
+
+// the shared-memory staged variant, explicitly (same arguments and results)
+extern "C" int ssp_combine_heatmap_tiled(const float* heat, const float* mask, const float* Hinv, int I, int N, int H,
+                                         int W, const float* xs, const float* ys, float* out, void* stream) {
+  return combine_launch(1, heat, mask, Hinv, I, N, H, W, xs, ys, out, stream);
 }

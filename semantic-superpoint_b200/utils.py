@@ -337,13 +337,14 @@ def combine_heatmap(heatmap, inv_homographies, mask_2D, device="cpu"):
     return out.to(out_dev)
 
 
-def combine_heatmap_batch(heatmap, inv_homographies, mask_2D):
-    """Batched export form: heatmap/mask [I,N,H,W], inv_homographies [I,N,3,3] -> [I,H,W] in one launch."""
+def combine_heatmap_batch(heatmap, inv_homographies, mask_2D, tiled=False):
+    """Batched export form: heatmap/mask [I,N,H,W], inv_homographies [I,N,3,3] -> [I,H,W] in one launch.
+    tiled=True runs the shared-memory staged kernel (same results; see csrc/heatmap.cu for when it pays)."""
     dev = _cuda_device("cuda", heatmap)
     h, m, Hm = f32c(heatmap, dev), f32c(mask_2D, dev), f32c(inv_homographies, dev)
     I, N, H, W = h.shape
     out = torch.empty((I, H, W), dtype=torch.float32, device=dev)
-    call("ssp_combine_heatmap", ptr(h), ptr(m), ptr(Hm), I, N, H, W, ptr(_linspace_grid(W, dev)),
+    call("ssp_combine_heatmap_tiled" if tiled else "ssp_combine_heatmap", ptr(h), ptr(m), ptr(Hm), I, N, H, W, ptr(_linspace_grid(W, dev)),
          ptr(_linspace_grid(H, dev)), ptr(out), stream_of(out))
     return out
 

@@ -170,6 +170,12 @@ def test_flatten_combine(golden):
     close(np.nan_to_num(out), np.nan_to_num(c["out"]), atol=2e-6)
 
 
+def test_combine_heatmap_tiled_golden(golden):
+    g = golden("combine")
+    out = S.combine_heatmap_batch(cu(g["heat"][None, :, 0]), cu(g["Hwarp"][None]), cu(g["mask"][None, :, 0]), tiled=True)
+    close(out[0], g["out"][0] if g["out"].ndim == 3 else g["out"], atol=2e-6)
+
+
 def test_combine_heatmap_n100():
     N = 100
     Hs, Hinv = homographies(N, 14, identity_first=True)
@@ -183,6 +189,10 @@ def test_combine_heatmap_n100():
                                    cu(np.stack([mask[:, 0], mask[::-1, 0]]))).cpu().numpy()
     close(both[0], ref[0] if ref.ndim == 3 else ref, atol=2e-6)
     close(both[1], both[0], atol=2e-6)  # same set of views in another order
+    # the shared-memory staged kernel gives the same map (also on the small golden case with a partial tile)
+    tiled = S.combine_heatmap_batch(cu(np.stack([heat[:, 0], heat[::-1, 0]])), cu(np.stack([Hs, Hs[::-1]])),
+                                    cu(np.stack([mask[:, 0], mask[::-1, 0]])), tiled=True).cpu().numpy()
+    close(tiled, both, atol=2e-6)
 
 
 # ------------------------------------------------------------------ a8 / a9
