@@ -428,11 +428,14 @@ class LossStepFn(torch.autograd.Function):
         loss = (l0 + l1).add_(ld, alpha=lambda_loss)
         ctx.c1, ctx.c2, ctx.lambda_loss = c1, c2, float(lambda_loss)
         ctx.mark_non_differentiable(l0, l1, ld, pos, neg)
+        ctx.set_materialize_grads(False)  # no zero-filled gradient tensors for the five logging outputs
         return loss, l0, l1, ld, pos, neg
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g, *_unused):
+        if g is None:
+            return (None,) * 13
         dev = g.device
         key = (dev.index, ctx.lambda_loss)
         if key not in _lam3:
