@@ -147,6 +147,11 @@ int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src /*[B,Dch,Nc]*
 int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
                           const int* plist, const float* pcoef, const float* possrc /*[B,256,Nc]*/, int B, int Nc,
                           float* out /*[B,256,Nc]*/, void* stream);
+/* Same GEMM, positive-pair partners read from packed planes [B,Nc_pad,256] bf16 (pos_lo may be NULL): 64 contiguous
+ * bytes per plane and 32-channel chunk instead of 32 words 4*Nc bytes apart. */
+int ssp_desc_bits_gemm_tc_planes(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
+                                 const int* plist, const float* pcoef, const void* pos_hi, const void* pos_lo, int B,
+                                 int Nc, float* out /*[B,256,Nc]*/, void* stream);
 
 /* ---- semantic head: cross entropy with ignore_index, optionally fused with the x8 bilinear upsample ------------
  * (not part of the five north-star pieces, same boundary.)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ssp_desc_pos_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "ssp_desc_bits_gemm_tc_planes": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "ssp_sem_ce_ws_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "ssp_sem_ce_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "ssp_sem_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                          const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
                          const int* __restrict__ plist, const float* __restrict__ pcoef, const float* __restrict__ possrc,
+                         const uint4* __restrict__ pos_hi, const uint4* __restrict__ pos_lo,
                          int B, int Nc, int Nc_pad, int sched, float* __restrict__ out) {
   using Cfg = BgCfg<P, NS_>;
   constexpr int NS = Cfg::NS;
@@ -488,9 +489,32 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
             int pc = n < npos ? pl[n] : -1;
             if (pc < 0) continue;
             float pf = pcf[n];
-            const float* ps = possrc + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + pc;
+            if (pos_hi) {
+              // partner descriptor from the packed planes: the 32 channels of this chunk are 64 contiguous bytes per
+              // plane (4 x 16 B per lane, every fetched sector fully used) instead of 32 words 4*Nc bytes apart
+              const size_t o = (((size_t)b * Nc_pad + pc) * KD + dh * BG_N + ch * 32) >> 3;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
+              for (int q = 0; q < 4; ++q) {
+                const uint4 h = __ldg(pos_hi + o + q);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                uint32_t lw[4] = {0u, 0u, 0u, 0u};
+                if (pos_lo) {
+                  const uint4 l = __ldg(pos_lo + o + q);
+                  lw[0] = l.x; lw[1] = l.y; lw[2] = l.z; lw[3] = l.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float e0 = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+                  float e1 = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+                  val[q * 8 + 2 * i] = fmaf(pf, e0, val[q * 8 + 2 * i]);
+                  val[q * 8 + 2 * i + 1] = fmaf(pf, e1, val[q * 8 + 2 * i + 1]);
+                }
+              }
+            } else {
+              const float* ps = possrc + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + pc;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
+            }
           }
           float* o = out + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + row;
 #pragma unroll
@@ -622,13 +646,15 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
 
 // out[b, d, r] = rowscale[b, r] * sum_k bit(r, k) * (Bhi + Blo)[b, k, d]      (out is [B, 256, Nc] fp32)
 //                + sum_n pcoef[b, r, n] * possrc[b, d, plist[b, r, n]]   (sparse positive pairs; plist may be NULL)
-extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
-                                     const int* plist, const float* pcoef, const float* possrc, int B, int Nc,
-                                     float* out, void* stream) {
+// The positive-pair source is either fp32 NCHW (possrc) or the packed planes pos_hi (+ pos_lo) [B, Nc_pad, 256] bf16.
+static int bits_gemm_tc_launch(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
+                               const int* plist, const float* pcoef, const float* possrc, const void* pos_hi,
+                               const void* pos_lo, int B, int Nc, float* out, void* stream) {
   SSP_REQUIRE(bits && Bhi && out, "ssp_desc_bits_gemm_tc: null pointer");
-  SSP_REQUIRE(!plist || (pcoef && possrc), "ssp_desc_bits_gemm_tc: plist needs pcoef and possrc");
+  SSP_REQUIRE(!plist || (pcoef && (possrc || pos_hi)), "ssp_desc_bits_gemm_tc: plist needs pcoef and a positive-pair source");
   SSP_REQUIRE(B > 0 && Nc > 0, "ssp_desc_bits_gemm_tc: bad sizes");
-  SSP_REQUIRE((((uintptr_t)Bhi | (uintptr_t)Blo) & 15) == 0, "ssp_desc_bits_gemm_tc: operands must be 16-byte aligned");
+  SSP_REQUIRE((((uintptr_t)Bhi | (uintptr_t)Blo | (uintptr_t)pos_hi | (uintptr_t)pos_lo) & 15) == 0,
+              "ssp_desc_bits_gemm_tc: operands must be 16-byte aligned");
   int Nc_pad = desc_nc_pad(Nc);
   uint64_t rows = (uint64_t)B * Nc_pad;
   CUtensorMap mh, ml;
@@ -648,11 +674,26 @@ extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, cons
   do {                                                                                                                \
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<PP, NN>, BgCfg<PP, NN>::SMEM))) return rc;                            \
     if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<PP, NN>, grid, BG_THREADS, BgCfg<PP, NN>::SMEM, st, mh, ml, bits, \
-                              rowscale, plist, pcoef, possrc, B, Nc, Nc_pad, sched, out))) return rc;                        \
+                              rowscale, plist, pcoef, possrc, (const uint4*)pos_hi, (const uint4*)pos_lo, B, Nc,      \
+                              Nc_pad, sched, out))) return rc;                                                        \
   } while (0)
   if (Blo) { if (deep) LAUNCH_BG(2, 6); else LAUNCH_BG(2, 4); }
   else     { if (deep) LAUNCH_BG(1, 8); else LAUNCH_BG(1, 6); }
 #undef LAUNCH_BG
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;
+}
+
+extern "C" int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
+                                     const int* plist, const float* pcoef, const float* possrc, int B, int Nc,
+                                     float* out, void* stream) {
+  return bits_gemm_tc_launch(bits, Bhi, Blo, rowscale, plist, pcoef, possrc, nullptr, nullptr, B, Nc, out, stream);
+}
+
+// Same GEMM with the positive-pair partners read from packed planes (pos_lo may be NULL: single-pass bf16 engine).
+extern "C" int ssp_desc_bits_gemm_tc_planes(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
+                                            const int* plist, const float* pcoef, const void* pos_hi, const void* pos_lo,
+                                            int B, int Nc, float* out, void* stream) {
+  SSP_REQUIRE(pos_hi, "ssp_desc_bits_gemm_tc_planes: null pointer");
+  return bits_gemm_tc_launch(bits, Bhi, Blo, rowscale, plist, pcoef, nullptr, pos_hi, pos_lo, B, Nc, out, stream);
 }

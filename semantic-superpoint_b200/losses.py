@@ -11,7 +11,13 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 from ._lib import call, f32c, ptr, stream_of
 
+import os
+
 _ENGINES = ("bf16x3", "bf16", "fp32")
+# A/B switches (read once): positive pairs of the bf16x3 forward from the packed planes or from NCHW fp32, and the
+# positive-pair partners of the backward epilogues from the packed planes or from NCHW fp32
+POS_FWD_PLANES = os.environ.get("SSP_POS_FWD", "planes") != "nchw"
+POS_EPI_PLANES = os.environ.get("SSP_POS_EPI", "planes") != "fp32"
 _engine = "bf16x3"
 CHECK_LIST_OVERFLOW = False  # tests turn this on (costs a host sync per call)
 
@@ -266,7 +272,7 @@ class DescriptorLossFn(torch.autograd.Function):
 
         # sparse positive pairs: exact dots, partial sums, pair lists for the backward
         maxp = lib.ssp_desc_maxp()
-        npos = lib.ssp_desc_pos_planes_nblocks(B, Nc) if (engine == "bf16x3") else lib.ssp_desc_pos_nblocks(B, Nc)
+        npos = lib.ssp_desc_pos_planes_nblocks(B, Nc) if (engine == "bf16x3" and POS_FWD_PLANES) else lib.ssp_desc_pos_nblocks(B, Nc)
         pos_part = torch.empty((npos, 4), dtype=torch.float64, device=dev)
         lists_i = torch.empty((3, B, Ncp, maxp), dtype=torch.int32, device=dev)   # rowcol, colrow, (colcnt in [2,:,:,0])
         lists_f = torch.empty((2, B, Ncp, maxp), dtype=torch.float32, device=dev)  # rowdot, coldot
@@ -289,7 +295,7 @@ class DescriptorLossFn(torch.autograd.Function):
             Blo = torch.empty_like(Bhi) if split else None
         neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
         out8 = torch.empty((8,), dtype=torch.float32, device=dev)
-        if split:
+        if split and POS_FWD_PLANES:
             # bf16x3: the positive pairs read the packed hi/lo planes (2 x 512 contiguous bytes per cell instead of 256
             # strided channels), so they run right after the pack, in front of the tensor-core kernel
             call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
@@ -297,7 +303,7 @@ class DescriptorLossFn(torch.autograd.Function):
                  dist, lamda, mpos, mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
             call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
                  ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
-            planes = (Ahi, Alo)
+            planes = (Ahi, Alo, Bhi, Blo)
         else:
             # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
             with _Fork(dev) as fork:
@@ -310,7 +316,7 @@ class DescriptorLossFn(torch.autograd.Function):
                 call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
                 call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
                      ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
-                planes = (Ahi, Alo)
+                planes = (Ahi, Alo, Bhi, Blo)
             fork.join()
 
         if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
@@ -329,7 +335,7 @@ class DescriptorLossFn(torch.autograd.Function):
 
         if need_grad:
             ctx.save_for_backward(Dc, Dwc, mv_pad, bitsR, bitsC, lists_i, lists_f,
-                                  *( [planes[0]] + ([planes[1]] if planes[1] is not None else []) if planes else []))
+                                  *([p for p in planes if p is not None] if planes else []))
             ctx.out8 = out8  # see DetectorLossFn
         ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
         ctx.mark_non_differentiable(wpts)
@@ -364,8 +370,10 @@ class DescriptorLossFn(torch.autograd.Function):
         dDw = torch.empty_like(Dwc)
         tc_engine = engine != "fp32"
         if tc_engine:
-            Ahi = saved[7]
-            Alo = saved[8] if split else None
+            if split:
+                Ahi, Alo, Bhi, Blo = saved[7:11]
+            else:
+                (Ahi, Bhi), Alo, Blo = saved[7:9], None, None
             Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
             Slo = torch.empty_like(Shi) if split else None
         # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
@@ -379,10 +387,17 @@ class DescriptorLossFn(torch.autograd.Function):
         if tc_engine:
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
             f1.join()
-            call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc), B, Nc,
-                 ptr(dD), st)
-            call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc), B, Nc,
-                 ptr(dDw), st)
+            if POS_EPI_PLANES:
+                # positive-pair partners from the packed planes of the forward (Dw for dD, D for dDw)
+                call("ssp_desc_bits_gemm_tc_planes", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]),
+                     ptr(Bhi), ptr(Blo), B, Nc, ptr(dD), st)
+                call("ssp_desc_bits_gemm_tc_planes", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]),
+                     ptr(Ahi), ptr(Alo), B, Nc, ptr(dDw), st)
+            else:
+                call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc), B, Nc,
+                     ptr(dD), st)
+                call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc), B,
+                     Nc, ptr(dDw), st)
         else:
             call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
             call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
