@@ -288,6 +288,7 @@ def run_ours(args):
     flops_pair = 2.0 * NC * NC * DCH
     bound_tbl = {
         "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
+        "ssp_desc_bits_gemm_tc_planes": ("tensor", flops_pair * B), "ssp_desc_pos_fwd_planes": ("hbm", 2.0 * B * NC * DCH * 4),
         "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
         "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
         "ssp_desc_pos_coef": ("hbm", 8.0 * B * NC * 16 * 4),
@@ -305,7 +306,8 @@ def run_ours(args):
         achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
     # DRAM traffic of that kernel from the committed ncu --set full capture of this same command (per launch)
     traffic = None
-    kern_of = {"ssp_desc_bits_gemm_tc": "desc_bits_gemm_tc_kernel", "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
+    kern_of = {"ssp_desc_bits_gemm_tc": "desc_bits_gemm_tc_kernel", "ssp_desc_bits_gemm_tc_planes": "desc_bits_gemm_tc_kernel",
+               "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
                "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel"}
     tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
     if top in kern_of and os.path.exists(tpath) and args.engine == "bf16x3":
@@ -320,7 +322,7 @@ def run_ours(args):
     extra = {}
     if not args.no_adapt:
         extra = bench_adaptation(torch, S, dev, rank, world, sdist, barrier)
-    if not args.no_semantic:
+    if not args.no_semantic and world == 1:  # auxiliary timing, single GPU only
         try:
             extra.update(bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, args.steps))
         except Exception as e:  # auxiliary measurement: never lose the headline line to it
