@@ -225,135 +225,167 @@ def run_ours(args):
     value = B * world * args.steps / (ms * 1e-3)
     loss_val = float(loss)
 
-    # ---- e2e: same step through the public API from pinned HOST buffers, H2D inside the timed region
-    #      (double-buffered on a copy stream), loss scalar read back every step
-    copy_stream = torch.cuda.Stream(device=dev)
-    if use_graph:
-        slots = [S.step.GraphedLossStep(dsets[0], dist_group=group) for _ in range(2)]
-        bufs = [g.static for g in slots]
-    else:
-        bufs = [{k: torch.empty_like(dsets[0][k]) for k in in_keys} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    # ---- everything below is secondary to the timed region above: if a later phase fails (or, with several ranks, a peer
+    #      is lost and rank 0 would wait forever) the line is still printed, with e2e / roofline marked as failed
+    import threading
+    import traceback
+    emitted = threading.Event()
 
-    def upload(i):
-        slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[slot])
-            for k in in_keys:
-                bufs[slot][k].copy_(pinned[i % NSETS][k], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def run_slot(slot):
-        return slots[slot].replay()["loss"] if use_graph else step(bufs[slot])[0]
-
-    def e2e_loop(n):
-        for f in freed:
-            f.record()
-        upload(0)
-        last = 0.0
-        for i in range(n):
-            slot = i % 2
-            if i + 1 < n:
-                upload(i + 1)
-            torch.cuda.current_stream().wait_event(ready[slot])
-            l = run_slot(slot)
-            freed[slot].record()
-            last = float(l)  # device -> host read of the step's result
-        return last
-
-    e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    e2e_ms = sdist.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)), dev)
-    e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
-
-    # ---- roofline of the dominant kernel: per-entry-point CUDA-event durations over K more steps
-    _lib.profile_begin()
-    for i in range(args.steps):
-        step(dsets[i % NSETS])
-    torch.cuda.synchronize()
-    prof = _lib.profile_end()  # {entry point: (calls, total ms)}
-    clocks = sampler.stop()  # sampled every 20 ms from before the timed region to the end of the profiled steps (same workload)
-    total_prof = sum(v[1] for v in prof.values())
-    shares = {k: {"calls_per_step": v[0] / args.steps, "us_per_call": 1e3 * v[1] / v[0], "share": v[1] / total_prof}
-              for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    top = next(iter(shares))
-    pk = peaks()
-    flops_pair = 2.0 * NC * NC * DCH
-    bound_tbl = {
-        "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
-        "ssp_desc_bits_gemm_tc_planes": ("tensor", flops_pair * B), "ssp_desc_pos_fwd_planes": ("hbm", 2.0 * B * NC * DCH * 4),
-        "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
-        "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
-        "ssp_desc_pos_coef": ("hbm", 8.0 * B * NC * 16 * 4),
-        "ssp_detector_loss_fwd_pair": ("hbm", 2 * B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
-        "ssp_detector_loss_bwd_pair": ("hbm", 2 * B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
-        "ssp_desc_pack2": ("hbm", 2 * B * NC * DCH * 4 * 2.0),
-    }
-    bound_tbl["ssp_desc_pos_apply"] = ("hbm", 2.0 * 3.0 * B * NC * DCH * 4)
-    # the roofline is reported for the dominant KERNEL of the dense contraction / its data movement
-    kind, work = bound_tbl.get(top, ("hbm", 0.0))
-    dur_s = shares[top]["us_per_call"] * 1e-6
-    if kind == "tensor":
-        achieved, peak, unit = work / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
-    else:
-        achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
-    # DRAM traffic of that kernel from the committed ncu --set full capture of this same command (per launch)
-    traffic = None
-    kern_of = {"ssp_desc_bits_gemm_tc": "desc_bits_gemm_tc_kernel", "ssp_desc_bits_gemm_tc_planes": "desc_bits_gemm_tc_kernel",
-               "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
-               "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel"}
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if top in kern_of and os.path.exists(tpath) and args.engine == "bf16x3":
-        traffic = json.load(open(tpath)).get(kern_of[top], {}).get("dram_bytes_per_launch")
-    roofline = {"kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
-                "us_per_launch": shares[top]["us_per_call"],
-                "note": "algorithmic 2*Nc^2*256 flop per pair x 32 pairs per launch; bf16x3 issues 3 (fwd) / 2 (bwd) MMAs per "
-                        "algorithmic MAC, so its ceiling is 1/3 (1/2) of the bf16 peak"}
-
-    # ---- second headline of BASELINE.json: homography adaptation images/s (N=100), measured in the same run
-    extra = {}
-    if not args.no_adapt:
-        extra = bench_adaptation(torch, S, dev, rank, world, sdist, barrier)
-    if not args.no_semantic and world == 1:  # auxiliary timing, single GPU only
-        try:
-            extra.update(bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, args.steps))
-        except Exception as e:  # auxiliary measurement: never lose the headline line to it
-            extra["with_semantic_head"] = {"error": repr(e)}
-
-    if rank == 0:
-        cpu = cpu_baseline(8, 2) if world == 1 and not args.no_cpu else None
-        line = {
-            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16x3": "bf16x3 (hi/lo split bf16 on tcgen05, fp32 accumulate, fp32-grade)", "bf16": "bf16", "fp32": "f32"}[args.engine],
-            "data": "synthetic",
-            "config": {"workload": "SSp loss step: detector loss x2 + dense descriptor loss, fwd+bwd, 32 pairs of 240x320 per GPU "
-                                   "(Nc=1200 cells, 256-d), inputs = head outputs resident in HBM",
-                       "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine, "cuda_graph": use_graph,
-                       "l2": "3 input sets x 138 MB rotate (> 126 MB L2)", "exchange": "all-reduce of 6 scalars (global normalisers)" if world > 1 else "none"},
-            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs (head outputs + labels + masks), double-buffered H2D on a copy stream, loss read back per step; PCIe-bound"},
-            "gpu_launches": kernels, "clocks": clocks, "roofline": roofline, "kernel_shares": shares, "loss": loss_val,
-        }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        line.update(extra)
+    def emit(line):
+        if emitted.is_set():
+            return
+        emitted.set()
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.write(1, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        torch.distributed.barrier()
-        torch.cuda.synchronize()
+
+    def bail(reason):
+        if rank == 0:
+            emit({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                  "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                  "vs_baseline": None, "dtype": args.engine, "data": "synthetic",
+                  "config": {"workload": "SSp loss step: detector loss x2 + dense descriptor loss, fwd+bwd, 32 pairs of 240x320 per GPU",
+                             "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine, "cuda_graph": use_graph},
+                  "e2e": {"value": None, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "error": reason},
+                  "gpu_launches": kernels, "clocks": None, "roofline": None, "loss": loss_val, "incomplete": reason})
         sys.stderr.flush()
-        os._exit(0)  # skip NCCL / graph teardown: destroying a process group with captured collectives can hang
+        os._exit(0)
+
+    if world > 1 and rank == 0:
+        wd = threading.Timer(200.0, bail, args=("watchdog: a phase after the timed region did not finish (peer rank lost?)",))
+        wd.daemon = True
+        wd.start()
+    try:
+        # ---- e2e: same step through the public API from pinned HOST buffers, H2D inside the timed region
+        #      (double-buffered on a copy stream), loss scalar read back every step
+        copy_stream = torch.cuda.Stream(device=dev)
+        if use_graph:
+            slots = [S.step.GraphedLossStep(dsets[0], dist_group=group) for _ in range(2)]
+            bufs = [g.static for g in slots]
+        else:
+            bufs = [{k: torch.empty_like(dsets[0][k]) for k in in_keys} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[slot])
+                for k in in_keys:
+                    bufs[slot][k].copy_(pinned[i % NSETS][k], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def run_slot(slot):
+            return slots[slot].replay()["loss"] if use_graph else step(bufs[slot])[0]
+
+        def e2e_loop(n):
+            for f in freed:
+                f.record()
+            upload(0)
+            last = 0.0
+            for i in range(n):
+                slot = i % 2
+                if i + 1 < n:
+                    upload(i + 1)
+                torch.cuda.current_stream().wait_event(ready[slot])
+                l = run_slot(slot)
+                freed[slot].record()
+                last = float(l)  # device -> host read of the step's result
+            return last
+
+        e2e_loop(3)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        e2e_ms = sdist.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)), dev)
+        e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
+
+        # ---- roofline of the dominant kernel: per-entry-point CUDA-event durations over K more steps
+        _lib.profile_begin()
+        for i in range(args.steps):
+            step(dsets[i % NSETS])
+        torch.cuda.synchronize()
+        prof = _lib.profile_end()  # {entry point: (calls, total ms)}
+        clocks = sampler.stop()  # sampled every 20 ms from before the timed region to the end of the profiled steps (same workload)
+        total_prof = sum(v[1] for v in prof.values())
+        shares = {k: {"calls_per_step": v[0] / args.steps, "us_per_call": 1e3 * v[1] / v[0], "share": v[1] / total_prof}
+                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        top = next(iter(shares))
+        pk = peaks()
+        flops_pair = 2.0 * NC * NC * DCH
+        bound_tbl = {
+            "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
+            "ssp_desc_bits_gemm_tc_planes": ("tensor", flops_pair * B), "ssp_desc_pos_fwd_planes": ("hbm", 2.0 * B * NC * DCH * 4),
+            "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
+            "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
+            "ssp_desc_pos_coef": ("hbm", 8.0 * B * NC * 16 * 4),
+            "ssp_detector_loss_fwd_pair": ("hbm", 2 * B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+            "ssp_detector_loss_bwd_pair": ("hbm", 2 * B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
+            "ssp_desc_pack2": ("hbm", 2 * B * NC * DCH * 4 * 2.0),
+        }
+        bound_tbl["ssp_desc_pos_apply"] = ("hbm", 2.0 * 3.0 * B * NC * DCH * 4)
+        # the roofline is reported for the dominant KERNEL of the dense contraction / its data movement
+        kind, work = bound_tbl.get(top, ("hbm", 0.0))
+        dur_s = shares[top]["us_per_call"] * 1e-6
+        if kind == "tensor":
+            achieved, peak, unit = work / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
+        else:
+            achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+        # DRAM traffic of that kernel from the committed ncu --set full capture of this same command (per launch)
+        traffic = None
+        kern_of = {"ssp_desc_bits_gemm_tc": "desc_bits_gemm_tc_kernel", "ssp_desc_bits_gemm_tc_planes": "desc_bits_gemm_tc_kernel",
+                   "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
+                   "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel"}
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if top in kern_of and os.path.exists(tpath) and args.engine == "bf16x3":
+            traffic = json.load(open(tpath)).get(kern_of[top], {}).get("dram_bytes_per_launch")
+        roofline = {"kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
+                    "us_per_launch": shares[top]["us_per_call"],
+                    "note": "algorithmic 2*Nc^2*256 flop per pair x 32 pairs per launch; bf16x3 issues 3 (fwd) / 2 (bwd) MMAs per "
+                            "algorithmic MAC, so its ceiling is 1/3 (1/2) of the bf16 peak"}
+
+        # ---- second headline of BASELINE.json: homography adaptation images/s (N=100), measured in the same run
+        extra = {}
+        if not args.no_adapt:
+            extra = bench_adaptation(torch, S, dev, rank, world, sdist, barrier)
+        if not args.no_semantic and world == 1:  # auxiliary timing, single GPU only
+            try:
+                extra.update(bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, args.steps))
+            except Exception as e:  # auxiliary measurement: never lose the headline line to it
+                extra["with_semantic_head"] = {"error": repr(e)}
+
+        if rank == 0:
+            cpu = cpu_baseline(8, 2) if world == 1 and not args.no_cpu else None
+            line = {
+                "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16x3": "bf16x3 (hi/lo split bf16 on tcgen05, fp32 accumulate, fp32-grade)", "bf16": "bf16", "fp32": "f32"}[args.engine],
+                "data": "synthetic",
+                "config": {"workload": "SSp loss step: detector loss x2 + dense descriptor loss, fwd+bwd, 32 pairs of 240x320 per GPU "
+                                       "(Nc=1200 cells, 256-d), inputs = head outputs resident in HBM",
+                           "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine, "cuda_graph": use_graph,
+                           "l2": "3 input sets x 138 MB rotate (> 126 MB L2)", "exchange": "all-reduce of 6 scalars (global normalisers)" if world > 1 else "none"},
+                "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs (head outputs + labels + masks), double-buffered H2D on a copy stream, loss read back per step; PCIe-bound"},
+                "gpu_launches": kernels, "clocks": clocks, "roofline": roofline, "kernel_shares": shares, "loss": loss_val,
+            }
+            if cpu is not None:
+                line["cpu_baseline"] = cpu
+            line.update(extra)
+            emit(line)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+            sys.stderr.flush()
+            os._exit(0)  # skip NCCL / graph teardown: destroying a process group with captured collectives can hang
+    except Exception as e:  # noqa: BLE001 -- a sticky CUDA error cannot be recovered, only reported
+        traceback.print_exc()
+        bail("phase after the timed region failed: %r" % (e,))
 
 
 def bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, steps):
