@@ -71,6 +71,10 @@ def test_signatures_mirror_reference():
     assert list(inspect.signature(S.getPtsFromHeatmap).parameters) == ["heatmap", "conf_thresh", "nms_dist"]
     assert list(inspect.signature(S.box_nms).parameters) == ["prob", "size", "iou", "min_prob", "keep_top_k"]
     assert list(inspect.signature(S.compute_valid_mask).parameters)[:4] == ["image_shape", "inv_homography", "device", "erosion_radius"]
+    # Train_model_heatmap_all.sem_loss(self, pred, label, device="cpu")
+    sem = inspect.signature(S.utils.sem_loss)
+    assert list(sem.parameters)[:3] == ["pred", "label", "device"] and sem.parameters["device"].default == "cpu"
+    assert sem.parameters["ignore_index"].default == 133
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -119,7 +123,24 @@ def test_signatures_match_live_reference_and_dropin_binds():
         assert RU.descriptor_loss is S.utils.descriptor_loss and len(bound) >= len(S.dropin.UTILS_NAMES)
         S.dropin.uninstall()
         assert RU.descriptor_loss is orig
+        # method twins in models/model_wrap.py (8a8 + 8f rank 3): same parameters after `self`, bound over the classes
+        import collections
+        import collections.abc
+        collections.Mapping = collections.abc.Mapping
+        MW = importlib.import_module("models.model_wrap")
+        for cls, meth, ours in ((MW.SuperPointFrontend_torch, "sample_desc_from_points", S.utils.sample_desc_from_points),
+                                (MW.PointTracker, "nn_match_two_way", S.utils.nn_match_two_way),
+                                (MW.SuperPointFrontend_torch, "nms_fast", S.utils.nms_fast)):
+            ref_p = [p.name for p in inspect.signature(getattr(cls, meth)).parameters.values()][1:]
+            our_p = [p.name for p in inspect.signature(ours).parameters.values()]
+            assert our_p[:len(ref_p)] == ref_p, meth
+        saved = (MW.SuperPointFrontend_torch.sample_desc_from_points, MW.PointTracker.nn_match_two_way)
+        bound = S.dropin.install(utils_module=RU, frontend_class=MW.SuperPointFrontend_torch, tracker_class=MW.PointTracker)
+        assert any(b.endswith("nn_match_two_way") for b in bound) and any(b.endswith("sample_desc_from_points") for b in bound)
+        assert MW.PointTracker.nn_match_two_way is not saved[1]
+        S.dropin.uninstall()
+        assert (MW.SuperPointFrontend_torch.sample_desc_from_points, MW.PointTracker.nn_match_two_way) == saved
     finally:
         sys.path.remove(REF)
-        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+        for m in [k for k in sys.modules if k in ("utils", "models") or k.startswith(("utils.", "models."))]:
             del sys.modules[m]
