@@ -89,12 +89,62 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
   sw += sw1;
 }
 
+// Variant of epi_chunk with the 32 mask_valid values already in registers (EPI2 epilogue, see the kernel).
+template <bool BITS>
+__device__ __forceinline__ void epi_chunk_pre(const uint32_t (&v)[32], const float4 (&mq)[8], float mneg, float& su,
+                                              float& sw, uint32_t& rowword, uint32_t& colword,
+                                              uint32_t* __restrict__ scratch, int lane) {
+  rowword = 0;
+  colword = 0;
+  float su1 = 0.f, sw1 = 0.f;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float mvv[4] = {mq[j4].x, mq[j4].y, mq[j4].z, mq[j4].w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j4 * 4 + jj;
+      float neg = fmaxf(__uint_as_float(v[j]) - mneg, 0.f);
+      if (jj & 1) { su1 += neg; sw1 = fmaf(neg, mvv[jj], sw1); }
+      else        { su += neg;  sw = fmaf(neg, mvv[jj], sw); }
+      if (BITS) {
+        bool p = neg > 0.f;
+        rowword |= p ? (1u << j) : 0u;
+        uint32_t bal = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) scratch[j] = bal;
+      }
+    }
+  }
+  if (BITS) {
+    __syncwarp();
+    colword = scratch[lane];
+    __syncwarp();
+  }
+  su += su1;
+  sw += sw1;
+}
+
+// float -> double by bit manipulation (exact for normal numbers and zero; denormals flush to zero, inf / nan kept):
+// keeps the epilogue off the FP64 pipe, whose conversions and adds took 28 % of the kernel's stall samples.
+__device__ __forceinline__ double f32_to_f64_bits(float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t e = (u >> 23) & 0xffu;
+  const unsigned long long sign = (unsigned long long)(u & 0x80000000u) << 32;
+  unsigned long long d;
+  if (e == 0u) d = sign;
+  else if (e == 0xffu) d = sign | (0x7ffull << 52) | ((unsigned long long)(u & 0x7fffffu) << 29);
+  else d = sign | ((unsigned long long)(e + 896u) << 52) | ((unsigned long long)(u & 0x7fffffu) << 29);
+  return __longlong_as_double((long long)d);
+}
+
 // Persistent forward kernel.  Work item = (pair b, row-tile pair mp, column tile nt); the flattened item range is
 // split evenly over the clusters (one 2-CTA cluster per SM pair), so all SMs finish together instead of running
 // 2.16 waves of whole row tiles.  Within a cluster CTA rank r owns row tile 2*mp + r; A is reloaded only when
 // (b, mp) changes (items are contiguous in nt).  Per-item, per-warp partial sums go to
 // partials[((item*2 + rank)*8 + warp)*2 + {0,1}].
-template <int P, bool BITS>
+// EPI2 (opt-in, SSP_FWD_EPI=2; written from the round-1 stall analysis, to be validated on hardware before it becomes the
+// default): tile sums stay in fp32 and are converted once per item without the FP64 pipe, and the mask_valid values of a
+// chunk are fetched one chunk ahead (the first chunk's before the accumulator wait) instead of inside the chunk.
+template <int P, bool BITS, bool EPI2>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -227,21 +277,45 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       const int row = m0 + q * 32 + lane;  // row inside the padded pair
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
+      float4 mq[8];
+      if (EPI2) {
+        const float4* mvq = reinterpret_cast<const float4*>(mv_pad + (size_t)row_base + nt * BN + half * 128);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) mq[j4] = __ldg(mvq + j4);
+      }
       tc::mbar_wait(t_full + as, aph);
       tc::fence_after_sync();
       double su_d = 0.0, sw_d = 0.0;
+      float su_t = 0.f, sw_t = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int cbase = nt * BN + half * 128 + ch * 32;
         uint32_t v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * 128 + ch * 32, v);
-        tc::tmem_ld_wait();
-        const float* mvp = mv_pad + (size_t)row_base + cbase;
         uint32_t rowword, colword;
         float su = 0.f, sw = 0.f;
-        epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane);
-        su_d += (double)su;
-        sw_d += (double)sw;
+        if (EPI2) {
+          float4 mnext[8];
+          if (ch < 3) {
+            const float4* mvq = reinterpret_cast<const float4*>(mv_pad + (size_t)row_base + cbase + 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) mnext[j4] = __ldg(mvq + j4);
+          }
+          tc::tmem_ld_wait();
+          epi_chunk_pre<BITS>(v, mq, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane);
+          su_t += su;
+          sw_t += sw;
+          if (ch < 3) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) mq[j4] = mnext[j4];
+          }
+        } else {
+          tc::tmem_ld_wait();
+          const float* mvp = mv_pad + (size_t)row_base + cbase;
+          epi_chunk<BITS>(v, mvp, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane);
+          su_d += (double)su;
+          sw_d += (double)sw;
+        }
         if (BITS) {
           bitsR[((size_t)b * NW + cbase / 32) * g.Nc_pad + row] = rowword;
           bitsC[((size_t)b * NW + (m0 + q * 32) / 32) * g.Nc_pad + cbase + lane] = colword;
@@ -256,12 +330,22 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(t_empty + as);
-      su_d = warp_sum_d(su_d);
-      sw_d = warp_sum_d(sw_d);
-      if (lane == 0) {
-        size_t slot = (((size_t)it * 2 + cta_rank) * 8 + warp) * 2;
-        partials[slot] = su_d;
-        partials[slot + 1] = sw_d;
+      if (EPI2) {
+        su_t = warp_sum(su_t);
+        sw_t = warp_sum(sw_t);
+        if (lane == 0) {
+          size_t slot = (((size_t)it * 2 + cta_rank) * 8 + warp) * 2;
+          partials[slot] = f32_to_f64_bits(su_t);
+          partials[slot + 1] = f32_to_f64_bits(sw_t);
+        }
+      } else {
+        su_d = warp_sum_d(su_d);
+        sw_d = warp_sum_d(sw_d);
+        if (lane == 0) {
+          size_t slot = (((size_t)it * 2 + cta_rank) * 8 + warp) * 2;
+          partials[slot] = su_d;
+          partials[slot + 1] = sw_d;
+        }
       }
     }
   }
@@ -294,7 +378,13 @@ template <int P, int NS_> struct BgCfg {
 // evenly over 2-CTA clusters.  The fp32 accumulator is double buffered in TMEM (2 x 128 columns), so the epilogue of
 // item i (warps 4-7: TMEM -> registers -> coalesced NCHW stores) overlaps the main loop of item i+1 (warps 0-3 expand
 // indicator bits into the TMEM A ring, warp 8 streams B through TMA multicast, warp 9 issues the MMAs).
-template <int P, int NS_>
+// DEEPBITS (opt-in, SSP_BG_BITS=deep; from the round-1 stall analysis, to be validated on hardware): the expanders fetch
+// the indicator words two 4-stage groups ahead over the FLAT stage sequence of all items of the cluster, so neither the
+// L2 latency inside an item nor the cold start of every item (no prefetch across the item boundary today) is exposed.
+// LATEPOS (opt-in, SSP_BG_POS=late; same status): the epilogue stores the scaled accumulator first, hands the TMEM stage
+// back, and only then adds the sparse positive-pair terms as a read-modify-write of its own stores (bit-identical
+// arithmetic), so the partner gathers (DRAM latency) no longer extend the time the accumulator stage is held.
+template <int P, int NS_, bool DEEPBITS, bool LATEPOS>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                          const uint32_t* __restrict__ bits, const float* __restrict__ rowscale,
@@ -410,42 +500,71 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // ------------------------------ expanders: indicator bits -> bf16 A operand in TMEM ------------------------------
     const int q = warp;
     int st_it = 0;
-    for (int it = it0; it < it1; it += itstep) {
-      const int key = it >> 1;
-      const int b = key / MP, mp = key - b * MP;
-      const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
-      const uint32_t* brow = bits + (size_t)b * NW * Nc_pad + row;
-      // indicator words are fetched four stages (8 words) ahead: the loads of group g+1 are in flight while group g
-      // is expanded, so the HBM/L2 latency of the bit matrix never sits on the per-stage critical path
-      uint32_t cur[8], nxt[8];
+    // one ring stage: expand the 64 indicator bits (w0, w1) of this row into 32 TMEM columns of bf16 {0,1}
+    auto expand_stage = [&](uint32_t w0, uint32_t w1) {
+      int s = st_it % NS;
+      uint32_t ph = (st_it / NS) & 1;
+      tc::mbar_wait(s_free + s, ph ^ 1);
+      tc::fence_after_sync();
+      uint32_t r[32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) cur[u] = __ldg(brow + (size_t)u * Nc_pad);
-      for (int kc0 = 0; kc0 < NK; kc0 += 4) {  // NK = Nc_pad / 64 is a multiple of 4
-        if (kc0 + 4 < NK) {
+      for (int i = 0; i < 8; ++i) {
+        uint2 e0 = lut[(w0 >> (4 * i)) & 15u], e1 = lut[(w1 >> (4 * i)) & 15u];
+        r[2 * i] = e0.x; r[2 * i + 1] = e0.y;
+        r[16 + 2 * i] = e1.x; r[16 + 2 * i + 1] = e1.y;
+      }
+      tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(a_full + s);
+      ++st_it;
+    };
+    if (DEEPBITS) {
+      const int GPI = NK / 4;  // 4-stage groups per item (NK = Nc_pad / 64 is a multiple of 4)
+      const int nitems = it1 > it0 ? (it1 - it0 + itstep - 1) / itstep : 0;
+      const int ngroups = nitems * GPI;
+      auto load_group = [&](int gi, uint32_t (&dst)[8]) {
+        if (gi < ngroups) {
+          const int itn = it0 + (gi / GPI) * itstep, kc0 = (gi % GPI) * 4;
+          const int key = itn >> 1;
+          const int b = key / MP, mp = key - b * MP;
+          const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
+          const uint32_t* brow = bits + (size_t)b * NW * Nc_pad + row;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) nxt[u] = __ldg(brow + (size_t)((kc0 + 4) * 2 + u) * Nc_pad);
+          for (int u = 0; u < 8; ++u) dst[u] = __ldg(brow + (size_t)(kc0 * 2 + u) * Nc_pad);
         }
+      };
+      uint32_t c0[8], c1[8], c2[8];
+      load_group(0, c0);
+      load_group(1, c1);
+      for (int gi = 0; gi < ngroups; ++gi) {
+        load_group(gi + 2, c2);
 #pragma unroll
-        for (int u = 0; u < 4; ++u, ++st_it) {
-          int s = st_it % NS;
-          uint32_t ph = (st_it / NS) & 1;
-          const uint32_t w0 = cur[2 * u], w1 = cur[2 * u + 1];
-          tc::mbar_wait(s_free + s, ph ^ 1);
-          tc::fence_after_sync();
-          uint32_t r[32];
+        for (int u = 0; u < 4; ++u) expand_stage(c0[2 * u], c0[2 * u + 1]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint2 e0 = lut[(w0 >> (4 * i)) & 15u], e1 = lut[(w1 >> (4 * i)) & 15u];
-            r[2 * i] = e0.x; r[2 * i + 1] = e0.y;
-            r[16 + 2 * i] = e1.x; r[16 + 2 * i + 1] = e1.y;
+        for (int u = 0; u < 8; ++u) { c0[u] = c1[u]; c1[u] = c2[u]; }
+      }
+    } else {
+      for (int it = it0; it < it1; it += itstep) {
+        const int key = it >> 1;
+        const int b = key / MP, mp = key - b * MP;
+        const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
+        const uint32_t* brow = bits + (size_t)b * NW * Nc_pad + row;
+        // indicator words are fetched four stages (8 words) ahead: the loads of group g+1 are in flight while group g
+        // is expanded, so the HBM/L2 latency of the bit matrix never sits on the per-stage critical path
+        uint32_t cur[8], nxt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = __ldg(brow + (size_t)u * Nc_pad);
+        for (int kc0 = 0; kc0 < NK; kc0 += 4) {  // NK = Nc_pad / 64 is a multiple of 4
+          if (kc0 + 4 < NK) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nxt[u] = __ldg(brow + (size_t)((kc0 + 4) * 2 + u) * Nc_pad);
           }
-          tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
-          tc::tmem_st_wait();
-          tc::fence_before_sync();
-          tc::mbar_arrive(a_full + s);
-        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+          for (int u = 0; u < 4; ++u) expand_stage(cur[2 * u], cur[2 * u + 1]);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+        }
       }
     }
   } else {
@@ -475,6 +594,38 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       const uint32_t aph = (tcount >> 1) & 1;
       tc::mbar_wait(d_full + as, aph);
       tc::fence_after_sync();
+      // adds the positive-pair terms of partner list entry n to the 32 channels of chunk ch held in val[]
+      auto add_partner = [&](int n, int ch, float (&val)[32]) {
+        int pc = n < npos ? pl[n] : -1;
+        if (pc < 0) return;
+        float pf = pcf[n];
+        if (pos_hi) {
+          // partner descriptor from the packed planes: the 32 channels of this chunk are 64 contiguous bytes per
+          // plane (4 x 16 B per lane, every fetched sector fully used) instead of 32 words 4*Nc bytes apart
+          const size_t o = (((size_t)b * Nc_pad + pc) * KD + dh * BG_N + ch * 32) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 h = __ldg(pos_hi + o + q);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+            uint32_t lw[4] = {0u, 0u, 0u, 0u};
+            if (pos_lo) {
+              const uint4 l = __ldg(pos_lo + o + q);
+              lw[0] = l.x; lw[1] = l.y; lw[2] = l.z; lw[3] = l.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float e0 = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+              float e1 = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+              val[q * 8 + 2 * i] = fmaf(pf, e0, val[q * 8 + 2 * i]);
+              val[q * 8 + 2 * i + 1] = fmaf(pf, e1, val[q * 8 + 2 * i + 1]);
+            }
+          }
+        } else {
+          const float* ps = possrc + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + pc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
+        }
+      };
 #pragma unroll 1
       for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
         uint32_t v[32];
@@ -484,37 +635,9 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
           float val[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]) * rs;
+          if (!LATEPOS) {
 #pragma unroll 1
-          for (int n = 0; n < nmax; ++n) {
-            int pc = n < npos ? pl[n] : -1;
-            if (pc < 0) continue;
-            float pf = pcf[n];
-            if (pos_hi) {
-              // partner descriptor from the packed planes: the 32 channels of this chunk are 64 contiguous bytes per
-              // plane (4 x 16 B per lane, every fetched sector fully used) instead of 32 words 4*Nc bytes apart
-              const size_t o = (((size_t)b * Nc_pad + pc) * KD + dh * BG_N + ch * 32) >> 3;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 h = __ldg(pos_hi + o + q);
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-                uint32_t lw[4] = {0u, 0u, 0u, 0u};
-                if (pos_lo) {
-                  const uint4 l = __ldg(pos_lo + o + q);
-                  lw[0] = l.x; lw[1] = l.y; lw[2] = l.z; lw[3] = l.w;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float e0 = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-                  float e1 = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
-                  val[q * 8 + 2 * i] = fmaf(pf, e0, val[q * 8 + 2 * i]);
-                  val[q * 8 + 2 * i + 1] = fmaf(pf, e1, val[q * 8 + 2 * i + 1]);
-                }
-              }
-            } else {
-              const float* ps = possrc + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + pc;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) val[j] = fmaf(pf, __ldg(ps + (size_t)j * Nc), val[j]);
-            }
+            for (int n = 0; n < nmax; ++n) add_partner(n, ch, val);
           }
           float* o = out + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + row;
 #pragma unroll
@@ -524,6 +647,20 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(d_empty + as);
+      if (LATEPOS && nmax > 0 && row_ok) {
+        // the accumulator stage is free again; this thread re-reads its own stores and adds the partner terms
+#pragma unroll 1
+        for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
+          float* o = out + ((size_t)b * KD + dh * BG_N + ch * 32) * Nc + row;
+          float val[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = o[(size_t)j * Nc];
+#pragma unroll 1
+          for (int n = 0; n < nmax; ++n) add_partner(n, ch, val);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[(size_t)j * Nc] = val[j];
+        }
+      }
     }
   }
 
@@ -631,14 +768,17 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
   int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_FWD(PP, BB)                                                                                   \
-  do {                                                                                                       \
-    if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB>, FwdCfg<PP>::SMEM))) return rc;                      \
-    if ((rc = launch_cluster2(desc_dense_fwd_tc_kernel<PP, BB>, grid, FWD_THREADS, FwdCfg<PP>::SMEM, st, mAh, mAl, mBh, \
-                              mBl, mv_pad, g, partials, bitsR, bitsC, dbgS))) return rc;                       \
+  static const bool epi2 = [] { const char* e = getenv("SSP_FWD_EPI"); return e && e[0] == '2'; }();
+#define LAUNCH_FWD(PP, BB, EE)                                                                                   \
+  do {                                                                                                           \
+    if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB, EE>, FwdCfg<PP>::SMEM))) return rc;                      \
+    if ((rc = launch_cluster2(desc_dense_fwd_tc_kernel<PP, BB, EE>, grid, FWD_THREADS, FwdCfg<PP>::SMEM, st, mAh, mAl, \
+                              mBh, mBl, mv_pad, g, partials, bitsR, bitsC, dbgS))) return rc;                      \
   } while (0)
-  if (Alo) { if (bitsR) LAUNCH_FWD(2, true); else LAUNCH_FWD(2, false); }
-  else     { if (bitsR) LAUNCH_FWD(1, true); else LAUNCH_FWD(1, false); }
+#define LAUNCH_FWD2(PP, BB) do { if (epi2) LAUNCH_FWD(PP, BB, true); else LAUNCH_FWD(PP, BB, false); } while (0)
+  if (Alo) { if (bitsR) LAUNCH_FWD2(2, true); else LAUNCH_FWD2(2, false); }
+  else     { if (bitsR) LAUNCH_FWD2(1, true); else LAUNCH_FWD2(1, false); }
+#undef LAUNCH_FWD2
 #undef LAUNCH_FWD
   SSP_CUDA_CHECK_LAUNCH("desc_dense_fwd_tc_kernel");
   return SSP_OK;
@@ -670,16 +810,24 @@ static int bits_gemm_tc_launch(const uint32_t* bits, const void* Bhi, const void
   // round-robin items by default (measured: 87 -> 77 us per launch at B=32, DRAM re-reads of the B planes gone);
   // SSP_BG_SCHED=contiguous restores the contiguous ranges.  The deeper ring measured slower (96 us) and stays opt-in.
   static const int sched = [] { const char* e = getenv("SSP_BG_SCHED"); return (e && e[0] == 'c') ? 0 : 1; }();
-#define LAUNCH_BG(PP, NN)                                                                                             \
+  static const bool deepbits = [] { const char* e = getenv("SSP_BG_BITS"); return e && e[0] == 'd'; }();
+  static const bool latepos = [] { const char* e = getenv("SSP_BG_POS"); return e && e[0] == 'l'; }();
+#define LAUNCH_BG(PP, NN)                                                                    \
+  do {                                                                                       \
+    if (deepbits) { if (latepos) LAUNCH_BG3(PP, NN, true, true); else LAUNCH_BG3(PP, NN, true, false); }   \
+    else          { if (latepos) LAUNCH_BG3(PP, NN, false, true); else LAUNCH_BG3(PP, NN, false, false); } \
+  } while (0)
+#define LAUNCH_BG3(PP, NN, DD, LL)                                                                                    \
   do {                                                                                                                \
-    if ((rc = set_smem(desc_bits_gemm_tc_kernel<PP, NN>, BgCfg<PP, NN>::SMEM))) return rc;                            \
-    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<PP, NN>, grid, BG_THREADS, BgCfg<PP, NN>::SMEM, st, mh, ml, bits, \
+    if ((rc = set_smem(desc_bits_gemm_tc_kernel<PP, NN, DD, LL>, BgCfg<PP, NN>::SMEM))) return rc;                    \
+    if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<PP, NN, DD, LL>, grid, BG_THREADS, BgCfg<PP, NN>::SMEM, st, mh, ml, bits, \
                               rowscale, plist, pcoef, possrc, (const uint4*)pos_hi, (const uint4*)pos_lo, B, Nc,      \
                               Nc_pad, sched, out))) return rc;                                                        \
   } while (0)
   if (Blo) { if (deep) LAUNCH_BG(2, 6); else LAUNCH_BG(2, 4); }
   else     { if (deep) LAUNCH_BG(1, 8); else LAUNCH_BG(1, 6); }
 #undef LAUNCH_BG
+#undef LAUNCH_BG3
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;
 }
