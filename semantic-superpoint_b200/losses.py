@@ -5,13 +5,13 @@ Multi-GPU: both losses use GLOBAL-batch normalisers, so with `dist_g
 numerators / mask sums are all-reduced (one tiny NCCL call each) before the division, and the backward
 kernels scale by the global normaliser.
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import call, f32c, ptr, stream_of
-
-import os
 
 _ENGINES = ("bf16x3", "bf16", "fp32")
 # A/B switches (read once): positive pairs of the bf16x3 forward from the packed planes or from NCHW fp32, and the
