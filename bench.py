@@ -318,7 +318,8 @@ def run_ours(args):
         pk = peaks()
         flops_pair = 2.0 * NC * NC * DCH
         bound_tbl = {
-            "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
+            "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_dense_fwd_tc_ex": ("tensor", flops_pair * B),
+        "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
             "ssp_desc_bits_gemm_tc_planes": ("tensor", flops_pair * B), "ssp_desc_pos_fwd_planes": ("hbm", 2.0 * B * NC * DCH * 4),
             "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
             "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),

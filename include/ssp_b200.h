@@ -124,6 +124,12 @@ int ssp_desc_dense_tc_nblocks(int B, int Nc);
 int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
                           int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
                           float* dbgS, void* stream);
+/* Same, with flags.  Bit 0: bitsR (row orientation) drops the columns whose mask_valid is 0, so the dD indicator GEMM can
+ * take the unscaled forward planes of Dw and one scalar (valid when mask_valid is binary and g_neg = 0).  Needs the
+ * EPI2 epilogue (SSP_FWD_EPI=2); experimental, see DESIGN 7. */
+int ssp_desc_dense_fwd_tc_ex(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
+                             int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
+                             float* dbgS, int flags, void* stream);
 int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const double* mv_part,
                       int nmv, int B, int Hc, int Wc, float* out8, void* stream);
 int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,

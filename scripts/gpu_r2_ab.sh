@@ -15,3 +15,5 @@ run fwdepi2 SSP_FWD_EPI=2
 run deepbits SSP_BG_BITS=deep
 run latepos SSP_BG_POS=late
 run all3 SSP_FWD_EPI=2 SSP_BG_BITS=deep SSP_BG_POS=late
+run fold SSP_FWD_EPI=2 SSP_BG_ALPHA=fold
+run all4 SSP_FWD_EPI=2 SSP_BG_BITS=deep SSP_BG_POS=late SSP_BG_ALPHA=fold

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ssp_desc_pack2": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
     "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "ssp_desc_dense_fwd_tc_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _I, _P]),
     "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P]),
     "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
     "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P]),

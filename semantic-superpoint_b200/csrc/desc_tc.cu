@@ -93,7 +93,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
 template <bool BITS>
 __device__ __forceinline__ void epi_chunk_pre(const uint32_t (&v)[32], const float4 (&mq)[8], float mneg, float& su,
                                               float& sw, uint32_t& rowword, uint32_t& colword,
-                                              uint32_t* __restrict__ scratch, int lane) {
+                                              uint32_t* __restrict__ scratch, int lane, bool maskbits) {
   rowword = 0;
   colword = 0;
   float su1 = 0.f, sw1 = 0.f;
@@ -108,7 +108,10 @@ __device__ __forceinline__ void epi_chunk_pre(const uint32_t (&v)[32], const flo
       else        { su += neg;  sw = fmaf(neg, mvv[jj], sw); }
       if (BITS) {
         bool p = neg > 0.f;
-        rowword |= p ? (1u << j) : 0u;
+        // maskbits: the ROW-orientation indicator (consumed by the dD GEMM) drops columns whose mask_valid is 0, so that
+        // GEMM can run on the unscaled forward planes of Dw with one scalar in its epilogue (alpha_c = s * mv_c for a
+        // binary mask and g_neg = 0); the column orientation (dDw GEMM, row-scaled by alpha_c) stays complete
+        rowword |= (p && (!maskbits || mvv[jj] != 0.f)) ? (1u << j) : 0u;
         uint32_t bal = __ballot_sync(0xffffffffu, p);
         if (lane == 0) scratch[j] = bal;
       }
@@ -302,7 +305,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             for (int j4 = 0; j4 < 8; ++j4) mnext[j4] = __ldg(mvq + j4);
           }
           tc::tmem_ld_wait();
-          epi_chunk_pre<BITS>(v, mq, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane);
+          epi_chunk_pre<BITS>(v, mq, g.mneg, su, sw, rowword, colword, ballot_scratch + warp * 32, lane, g.cell != 0);
           su_t += su;
           sw_t += sw;
           if (ch < 3) {
@@ -743,9 +746,20 @@ extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) {
 
 // Ahi/Alo: packed planes of `descriptors`, Bhi/Blo: packed planes of `descriptors_warped`
 // ([B, Nc_pad, 256] bf16).  Alo == Blo == NULL selects single-pass bf16; otherwise bf16x3.
+// flags bit 0: bitsR drops the columns whose mask_valid is 0 (see epi_chunk_pre); only the EPI2 epilogue implements it
+extern "C" int ssp_desc_dense_fwd_tc_ex(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
+                                        const float* mv_pad, int B, int Hc, int Wc, float mneg, double* partials,
+                                        uint32_t* bitsR, uint32_t* bitsC, float* dbgS, int flags, void* stream);
+
 extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
                                      const float* mv_pad, int B, int Hc, int Wc, float mneg, double* partials,
                                      uint32_t* bitsR, uint32_t* bitsC, float* dbgS, void* stream) {
+  return ssp_desc_dense_fwd_tc_ex(Ahi, Alo, Bhi, Blo, mv_pad, B, Hc, Wc, mneg, partials, bitsR, bitsC, dbgS, 0, stream);
+}
+
+extern "C" int ssp_desc_dense_fwd_tc_ex(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
+                                        const float* mv_pad, int B, int Hc, int Wc, float mneg, double* partials,
+                                        uint32_t* bitsR, uint32_t* bitsC, float* dbgS, int flags, void* stream) {
   SSP_REQUIRE(Ahi && Bhi && mv_pad && partials, "ssp_desc_dense_fwd_tc: null pointer");
   SSP_REQUIRE((Alo == nullptr) == (Blo == nullptr), "ssp_desc_dense_fwd_tc: lo planes must both be given or both null");
   SSP_REQUIRE((bitsR == nullptr) == (bitsC == nullptr), "ssp_desc_dense_fwd_tc: bitsR/bitsC must both be given or both null");
@@ -754,7 +768,10 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   SSP_REQUIRE((((uintptr_t)Ahi | (uintptr_t)Bhi | (uintptr_t)Alo | (uintptr_t)Blo | (uintptr_t)mv_pad) & 15) == 0,
               "ssp_desc_dense_fwd_tc: operands must be 16-byte aligned");
   DescGeom g;
-  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = KD; g.cell = 0;
+  static const bool epi2 = [] { const char* e = getenv("SSP_FWD_EPI"); return e && e[0] == '2'; }();
+  SSP_REQUIRE(flags == 0 || (flags == 1 && epi2), "ssp_desc_dense_fwd_tc_ex: flags=%d needs the EPI2 epilogue (SSP_FWD_EPI=2)", flags);
+  g.B = B; g.Hc = Hc; g.Wc = Wc; g.Nc = Hc * Wc; g.Nc_pad = desc_nc_pad(g.Nc); g.Dch = KD;
+  g.cell = flags;  // this kernel has no use for the cell size: the field carries the flags
   g.dist = 0.f; g.lamda = 0.f; g.mpos = 0.f; g.mneg = mneg;
   uint64_t rows = (uint64_t)B * g.Nc_pad;
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -768,7 +785,6 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
   int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool epi2 = [] { const char* e = getenv("SSP_FWD_EPI"); return e && e[0] == '2'; }();
 #define LAUNCH_FWD(PP, BB, EE)                                                                                   \
   do {                                                                                                           \
     if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB, EE>, FwdCfg<PP>::SMEM))) return rc;                      \

@@ -18,6 +18,11 @@ _ENGINES = ("bf16x3", "bf16", "fp32")
 # positive-pair partners of the backward epilogues from the packed planes or from NCHW fp32
 POS_FWD_PLANES = os.environ.get("SSP_POS_FWD", "planes") != "nchw"
 POS_EPI_PLANES = os.environ.get("SSP_POS_EPI", "planes") != "fp32"
+# experimental (not yet run on hardware): in the fused step the mask is folded into the row-orientation indicator
+# bits, the dD GEMM takes the unscaled forward planes of Dw and the backward pack disappears.  Valid only for a BINARY
+# mask and g_neg = 0 (structural in LossStepFn); needs SSP_FWD_EPI=2.
+FOLD_ALPHA = os.environ.get("SSP_BG_ALPHA") == "fold" and os.environ.get("SSP_FWD_EPI") == "2"
+_ones = {}
 _engine = "bf16x3"
 CHECK_LIST_OVERFLOW = False  # tests turn this on (costs a host sync per call)
 
@@ -246,7 +251,7 @@ class DescriptorLossFn(torch.autograd.Function):
     differentiable w.r.t. descriptors and descriptors_warped, wpts (warped cell centres) is not."""
 
     @staticmethod
-    def forward(ctx, D, Dw, Hm, mv, cell, lamda, dist, engine, dist_group=None, debug_S=None):
+    def forward(ctx, D, Dw, Hm, mv, cell, lamda, dist, engine, dist_group=None, debug_S=None, fold_alpha=False):
         lib = _lib.load()
         dev = D.device
         Dc = f32c(D.detach(), dev)
@@ -301,10 +306,16 @@ class DescriptorLossFn(torch.autograd.Function):
             call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
             call("ssp_desc_pos_fwd_planes", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc, cell,
                  dist, lamda, mpos, mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
-            call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
-                 ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+            fold_alpha = bool(fold_alpha and need_grad and POS_EPI_PLANES)
+            if fold_alpha:
+                call("ssp_desc_dense_fwd_tc_ex", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
+                     ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), 1, st)
+            else:
+                call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
+                     ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             planes = (Ahi, Alo, Bhi, Blo)
         else:
+            fold_alpha = False
             # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
             with _Fork(dev) as fork:
                 call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos,
@@ -338,6 +349,7 @@ class DescriptorLossFn(torch.autograd.Function):
                                   *([p for p in planes if p is not None] if planes else []))
             ctx.out8 = out8  # see DetectorLossFn
         ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
+        ctx.fold_alpha = fold_alpha
         ctx.mark_non_differentiable(wpts)
         if res is not None:
             return res[0], res[1], res[2], wpts
@@ -384,7 +396,19 @@ class DescriptorLossFn(torch.autograd.Function):
         with _Fork(dev) as f1:
             call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
                  ptr(mv_pad), ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(coefs[1]), stream_of(Dc))
-        if tc_engine:
+        if tc_engine and getattr(ctx, "fold_alpha", False):
+            # bitsR already excludes the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
+            key = (dev.index, B, Ncp)
+            if key not in _ones:
+                _ones[key] = torch.ones((B, Ncp), dtype=torch.float32, device=dev)
+            srow = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
+            call("ssp_desc_alpha", ptr(_ones[key]), ptr(g3), ptr(out8), B, Ncp, ptr(srow), st)
+            f1.join()
+            call("ssp_desc_bits_gemm_tc_planes", ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]),
+                 ptr(Bhi), ptr(Blo), B, Nc, ptr(dD), st)
+            call("ssp_desc_bits_gemm_tc_planes", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]),
+                 ptr(Ahi), ptr(Alo), B, Nc, ptr(dDw), st)
+        elif tc_engine:
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
             f1.join()
             if POS_EPI_PLANES:
@@ -439,7 +463,8 @@ class LossStepFn(torch.autograd.Function):
         l0, l1, cellmask = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
         B, _, Hc, Wc = semi.shape
         c2 = _Ctx((ctx.needs_input_grad[6], ctx.needs_input_grad[7]) + (False,) * 8)
-        ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine)
+        ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine,
+                                                       None, None, FOLD_ALPHA)
         loss = (l0 + l1).add_(ld, alpha=lambda_loss)
         ctx.c1, ctx.c2, ctx.lambda_loss = c1, c2, float(lambda_loss)
         ctx.mark_non_differentiable(l0, l1, ld, pos, neg)
