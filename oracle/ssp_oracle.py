@@ -524,3 +524,42 @@ def nn_match_two_way(desc1, desc2, nn_thresh):
     matches[1, :] = idx[keep]
     matches[2, :] = scores[keep]
     return matches
+
+
+# ------------------------------------------------------------------------------------------------
+# label warping of the dataset side  (oracle only so far -- no CUDA counterpart yet)
+# ------------------------------------------------------------------------------------------------
+def homography_scaling(homography, H, W):
+    """utils/utils.py:291-300: normalised -> pixel coordinates, T^-1 . H . T with T = [[2/W,0,-1],[0,2/H,-1],[0,0,1]] (fp32)."""
+    trans = np.array([[2.0 / W, 0.0, -1], [0.0, 2.0 / H, -1], [0.0, 0.0, 1.0]], dtype=f32)
+    return (np.linalg.inv(trans).astype(f32) @ np.asarray(homography, f32) @ trans).astype(f32)
+
+
+def _scatter_last_wins(H, W, pts, values, channels=None):
+    """datasets/data_tools.py:19-23: out[round(y), round(x)] = value; sequential index_put, the last duplicate wins."""
+    out = np.zeros((H, W) if channels is None else (H, W, channels), dtype=f32)
+    q = np.round(np.asarray(pts, dtype=f32)).astype(np.int64)  # torch.round = half to even, like np.round
+    for i in range(q.shape[0]):
+        out[q[i, 1], q[i, 0]] = values if np.isscalar(values) else values[i]
+    return out
+
+
+def warp_labels(pnts, H, W, homography, bilinear=False):
+    """datasets/data_tools.py:37-63 warpLabels (+ :6-34 for labels_bi).  pnts [P,2] (x, y), truncated to integers;
+    homography [3,3] in normalised coordinates.  Returns dict(labels [1,H,W], res [H,W,2], warped_pnts [M,2]
+    [, labels_bi [1,H,W]])."""
+    pnts = np.trunc(np.asarray(pnts, dtype=np.float64)).astype(np.int64)
+    warped = warp_points(pnts[:, :2].astype(f32), homography_scaling(homography, H, W))
+    outs = {}
+    if bilinear:
+        base = np.trunc(warped).astype(f32)                                   # .long() truncates toward zero
+        ext = np.concatenate([base, base + np.array([0, 1], f32), base + np.array([1, 0], f32), base + 1], axis=0)
+        rx, ry = warped[:, 0] - base[:, 0], warped[:, 1] - base[:, 1]
+        wts = np.concatenate([(1 - rx) * (1 - ry), (1 - rx) * ry, rx * (1 - ry), rx * ry]).astype(f32)
+        ext_f, keep = filter_points(ext, [W, H], return_mask=True)
+        outs["labels_bi"] = _scatter_last_wins(H, W, ext_f, wts[keep])[None]
+    warped = filter_points(warped, [W, H])
+    outs["labels"] = _scatter_last_wins(H, W, warped, 1.0)[None]
+    outs["res"] = _scatter_last_wins(H, W, warped, (warped - np.round(warped)).astype(f32), channels=2)
+    outs["warped_pnts"] = warped
+    return outs

@@ -130,7 +130,24 @@ def gen_matching():
     save("matching", pts=pts, pts2=pts2, desc1=d1, desc2=d2, **out)   # coarse maps: synth seeds 111 / 112, see the tests
 
 
+def gen_warp_labels():
+    """datasets/data_tools.warpLabels of the unmodified reference (oracle pinned ahead of the kernels)."""
+    from datasets.data_tools import warpLabels
+    t = torch.from_numpy
+    Hs, _ = ref_homographies(2, 9)
+    H, W = 48, 64
+    pts = np.stack([np.floor(synth.uniform((120,), 131) * W), np.floor(synth.uniform((120,), 132) * H)], axis=1)
+    out = {}
+    for i in range(2):
+        o = warpLabels(t(pts.copy()), H, W, t(Hs[i]), bilinear=True)
+        for k, v in o.items():
+            out["%s_%d" % (k, i)] = v.numpy()
+    save("warp_labels", pts=pts, H=Hs, **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "warp_labels":
+        return gen_warp_labels()
     if len(sys.argv) > 1 and sys.argv[1] == "semantic":
         return gen_semantic()
     if len(sys.argv) > 1 and sys.argv[1] == "matching":
@@ -267,6 +284,7 @@ def main():
 
     gen_semantic()
     gen_matching()
+    gen_warp_labels()
 
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:
         json.dump({"torch": torch.__version__, "numpy": np.__version__, "cv2": cv2.__version__,

@@ -168,3 +168,15 @@ def test_matching_oracle_against_the_reference_shipped_fixture():
     pred = np.concatenate([g["keypoints1"][m[0].astype(int)], g["keypoints2"][m[1].astype(int)]], axis=1)
     assert pred.shape == g["matches"].shape == (584, 4)
     assert np.array_equal(pred, g["matches"])
+
+
+def test_warp_labels_oracle(golden):
+    """SURVEY 8f rank 4 (oracle pinned ahead of the kernels): datasets/data_tools.warpLabels incl. the bilinear label map."""
+    g = golden("warp_labels")
+    for i in range(2):
+        o = O.warp_labels(g["pts"], 48, 64, g["H"][i], bilinear=True)
+        assert np.array_equal(o["labels"], g["labels_%d" % i])
+        close(o["warped_pnts"], g["warped_pnts_%d" % i], atol=2e-5)
+        close(o["res"], g["res_%d" % i], atol=2e-5)
+        close(o["labels_bi"], g["labels_bi_%d" % i], atol=2e-5)
+        assert o["labels"].sum() <= o["warped_pnts"].shape[0]  # collisions keep one label per pixel
