@@ -1,7 +1,7 @@
 /* ssp_b200 -- C ABI of the B200-native homography-warp correspondence path of Semantic-SuperPoint.
  *
  * The reference (Gabriel-SGama/Semantic-SuperPoint) has no FFI: its boundary for this path is a set of
- * Python callables in utils/utils.py, Train_model_heatmap_all.py and export.py.  Every entry point below
+ * Python callables in utils/utils.py, Train_model_heatmap_all.py, export.py and models/model_wrap.py.  Every entry point below
  * names the reference callable (file:line) it serves; the Python host side (semantic-superpoint_b200/*.py)
  * re-exports those callables with unchanged signatures and binds them to this library through ctypes.
  *
