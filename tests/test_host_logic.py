@@ -99,6 +99,63 @@ def test_shard_range_covers_everything():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
+def test_orchestration_call_sequences(monkeypatch):
+    """The host side of the loss step with the C library faked out (every entry point recorded, nothing computed): the
+    Python orchestration -- buffer shapes, autograd plumbing, engine dispatch, fused / unfused / semantic variants -- runs
+    on a CPU-only box and issues the documented kernel sequence."""
+    from ssp_b200 import _lib, losses, step, utils
+    calls = []
+    for m in (_lib, losses, utils):
+        monkeypatch.setattr(m, "call", lambda name, *a: calls.append(name))
+        monkeypatch.setattr(m, "stream_of", lambda t: None)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(utils, "_cuda_device", lambda device, *t: torch.device("cpu"))
+
+    class NoFork(object):
+        def __init__(self, dev):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def join(self):
+            pass
+
+    monkeypatch.setattr(losses, "_Fork", NoFork)
+    B, Hc, Wc = 2, 6, 8
+    leaf = lambda *shape: torch.randn(*shape).requires_grad_()
+    semi, semi_w, D, Dw = leaf(B, 65, Hc, Wc), leaf(B, 65, Hc, Wc), leaf(B, 256, Hc, Wc), leaf(B, 256, Hc, Wc)
+    lab, m, H = torch.zeros(B, 1, Hc * 8, Wc * 8), torch.ones(B, 1, Hc * 8, Wc * 8), torch.eye(3).repeat(B, 1, 1)
+
+    def run(**kw):
+        del calls[:]
+        out = step.loss_step(semi, semi_w, D, Dw, lab, lab, m, m, H, **kw)
+        out["loss"].backward()
+        return list(calls)
+
+    fwd = ["ssp_detector_loss_fwd_pair", "ssp_desc_geometry", "ssp_desc_pack2", "ssp_desc_pos_fwd_planes",
+           "ssp_desc_dense_fwd_tc", "ssp_desc_finalize"]
+    bwd_desc = ["ssp_desc_alpha", "ssp_desc_pos_coef", "ssp_desc_pack", "ssp_desc_bits_gemm_tc_planes", "ssp_desc_bits_gemm_tc_planes"]
+    assert run() == fwd + ["ssp_detector_loss_bwd_pair"] + bwd_desc                       # one-node fused step
+    unfused = run(fused=False)
+    assert unfused[:6] == fwd and sorted(unfused[6:]) == sorted(bwd_desc + ["ssp_detector_loss_bwd_pair"])
+    assert [c for c in run(engine="fp32") if "desc" in c] == [
+        "ssp_desc_geometry", "ssp_desc_pos_fwd", "ssp_desc_dense_fwd_simt", "ssp_desc_finalize", "ssp_desc_alpha",
+        "ssp_desc_pos_coef", "ssp_desc_bits_gemm_simt", "ssp_desc_bits_gemm_simt", "ssp_desc_pos_apply"]
+    assert "ssp_desc_pos_fwd" in run(engine="bf16") and "ssp_desc_pos_fwd_planes" not in run(engine="bf16")
+    sp, sl = leaf(B, 133, Hc, Wc), torch.randint(0, 134, (B, Hc * 8, Wc * 8))
+    sem = run(sem_pred=sp, sem=sl, sem_warp_pred=sp, warped_sem=sl)
+    assert sem.count("ssp_sem_ce_up8") == 2 and sem.count("ssp_sem_ce_up8_bwd") == 2      # 1/8-resolution logits: fused upsample
+    full = leaf(B, 133, Hc * 8, Wc * 8)
+    sem = run(sem_pred=full, sem=sl, sem_warp_pred=full, warped_sem=sl)
+    assert sem.count("ssp_sem_ce_fwd") == 2 and sem.count("ssp_sem_ce_bwd") == 2          # full-resolution logits
+    with pytest.raises(RuntimeError, match="1/8"):
+        utils.sem_loss(leaf(B, 133, Hc * 4, Wc * 4), sl)
+
+
 REF = "/root/reference"
 
 
