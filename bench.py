@@ -57,6 +57,19 @@ def host_inputs(B, seed):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Give the CPU path every host core (torchrun exports OMP_NUM_THREADS=1, which would throttle the BLAS behind the
+    oracle port) and return the thread count actually in effect."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        got = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+        return max(got) if got else n
+    except Exception:  # noqa: BLE001
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
 def cpu_loss_step(inp):
     from oracle import ssp_oracle as O
     B = inp["semi"].shape[0]
@@ -71,12 +84,13 @@ def cpu_loss_step(inp):
 
 def cpu_baseline(sample_pairs, reps):
     inp = host_inputs(sample_pairs, 99)
+    threads = host_threads()
     cpu_loss_step(inp)  # warm-up (BLAS threads, page faults)
     t0 = time.perf_counter()
     for _ in range(reps):
         cpu_loss_step(inp)
     dt = (time.perf_counter() - t0) / reps
-    return {"value": sample_pairs / dt, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": sample_pairs / dt, "unit": "pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
             "sample": "%d pairs of 240x320 per step (fwd+bwd, numpy/BLAS oracle port of the reference path; the reference "
                       "itself materialises a 1.47 GB/pair product and ran ~1 pair/s on 8 cores), %d reps" % (sample_pairs, reps)}
 
@@ -86,6 +100,7 @@ def run_reference(args):
     if rank != 0:
         return
     pairs = 2  # BASELINE configs[0]: the reference's own CPU-runnable case
+    threads = host_threads()
     inp = host_inputs(pairs, 99)
     for _ in range(max(1, min(args.warmup, 2))):
         cpu_loss_step(inp)
@@ -99,8 +114,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "loss step (detector x2 + dense descriptor, fwd+bwd), bounded sample of %d pairs 240x320 per step" % pairs},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": "%d pairs per step, %d steps" % (pairs, args.steps)},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d pairs per step, %d steps, %d BLAS threads" % (pairs, args.steps, threads)},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -160,6 +175,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    placement = sdist.bind_to_gpu_numa_node(local)  # before the pinned staging buffers are allocated (first touch)
     group = True if world > 1 else None
     S.set_descriptor_engine(args.engine)
     B = B_PER_GPU
@@ -197,7 +213,7 @@ def run_ours(args):
     k0 = _lib.kernel_count
     step(dsets[0])
     kernels_per_step = _lib.kernel_count - k0
-    use_graph = not args.no_graph  # with world > 1 the three tiny NCCL all-reduces are captured inside the graph
+    use_graph = not args.no_graph  # with world > 1 the exchange kernel is captured inside the graph like any other kernel
     if use_graph:
         # fwd+bwd of the whole step captured once per input set and replayed: the step is ~25 short kernels
         graphs = [S.step.GraphedLossStep(d, dist_group=group) for d in dsets]
@@ -249,7 +265,7 @@ def run_ours(args):
                   "e2e": {"value": None, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "error": reason},
                   "gpu_launches": kernels, "clocks": None, "roofline": None, "loss": loss_val, "incomplete": reason})
         sys.stderr.flush()
-        os._exit(0)
+        os._exit(3)  # a phase failed (CUDA error, lost peer): the partial line above is diagnostic, the run is NOT ok
 
     if world > 1 and rank == 0:
         wd = threading.Timer(200.0, bail, args=("watchdog: a phase after the timed region did not finish (peer rank lost?)",))
@@ -370,7 +386,8 @@ def run_ours(args):
                 "config": {"workload": "SSp loss step: detector loss x2 + dense descriptor loss, fwd+bwd, 32 pairs of 240x320 per GPU "
                                        "(Nc=1200 cells, 256-d), inputs = head outputs resident in HBM",
                            "per_gpu_pairs": B, "global_pairs": B * world, "engine": args.engine, "cuda_graph": use_graph,
-                           "l2": "3 input sets x 138 MB rotate (> 126 MB L2)", "exchange": "all-reduce of 6 scalars (global normalisers)" if world > 1 else "none"},
+                           "l2": "3 input sets x 138 MB rotate (> 126 MB L2)", "exchange": ("one peer-memory kernel per step (P2P stores over NVLink + flags, %s backend)" % sdist.get_exchange(True).backend) if world > 1 else "none",
+                           "host_placement": placement},
                 "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs (head outputs + labels + masks), double-buffered H2D on a copy stream, loss read back per step; PCIe-bound"},
                 "gpu_launches": kernels, "clocks": clocks, "roofline": roofline, "kernel_shares": shares, "loss": loss_val,
@@ -380,10 +397,11 @@ def run_ours(args):
             line.update(extra)
             emit(line)
         if world > 1:
-            torch.distributed.barrier()
+            sdist.get_exchange(True).check()  # raises if any exchange of the run timed out waiting for a peer
             torch.cuda.synchronize()
-            sys.stderr.flush()
-            os._exit(0)  # skip NCCL / graph teardown: destroying a process group with captured collectives can hang
+            sdist.close_exchanges()
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
     except Exception as e:  # noqa: BLE001 -- a sticky CUDA error cannot be recovered, only reported
         traceback.print_exc()
         bail("phase after the timed region failed: %r" % (e,))

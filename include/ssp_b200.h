@@ -192,6 +192,34 @@ int ssp_sample_desc(const float* coarse, const double* pts, int K, int D, int Hc
 int ssp_nn_match(const float* desc1 /*[D,K1]*/, const float* desc2 /*[D,K2]*/, int D, int K1, int K2,
                  unsigned long long* best1 /*[K1]*/, unsigned long long* best2 /*[K2]*/, void* stream);
 
+/* ---- multi-GPU: exchange of the global-batch normalisers of the loss step as ONE kernel over peer memory.
+ * The reference is single-GPU; what has to agree with it on a batch sharded by pair is the whole-batch divisors of
+ * detector_loss (Train_model_heatmap_all.py:178), descriptor_loss (utils/utils.py:886-887) and sem_loss (:181-193).
+ * Every rank owns one exchange buffer (ssp_xchg_alloc: the only allocation this library makes, because cudaIpc can
+ * only export a cudaMalloc'ed base pointer), exports it as a 64-byte cudaIpcMemHandle_t (HOST memory) and maps the
+ * buffers of the other ranks of the node (ssp_xchg_open).  ssp_loss_exchange pushes the local sums into every rank's
+ * buffer (peer stores over NVLink + release flag), waits for everybody's flags in local memory, adds in rank order
+ * and rewrites det0/det1 {loss, numerator, sum(mask)+1e-5}, desc8 (out8 of ssp_desc_finalize) and sem0/sem1
+ * {loss, sum, count} in place with the global-batch values (any of them may be NULL).  Stream-ordered, graph
+ * capturable, no NCCL.  A peer that does not arrive within timeout_s poisons the outputs with NaN and sets the
+ * sticky error that ssp_xchg_status reports (it synchronises the stream). ---- */
+size_t ssp_xchg_bytes(void);
+int ssp_xchg_max_ranks(void);
+int ssp_xchg_alloc(void** buf, void* ipc_handle64_host);
+int ssp_xchg_open(const void* ipc_handle64_host, void** peer_buf);
+int ssp_xchg_close(void* peer_buf);
+int ssp_xchg_free(void* buf);
+int ssp_xchg_status(const void* local_buf, void* stream);
+int ssp_loss_exchange(const void* const* bufs_host /*[world] device pointers, own buffer at [rank]*/, int rank, int world,
+                      float* det0, float* det1, float* desc8, float* sem0, float* sem1, int B_local, int Hc, int Wc,
+                      double timeout_s, void* stream);
+
+/* ---- profiling aid (not on the product path): timeline trace of the two tcgen05 kernels.  Only a library built with
+ * -DSSP_TRACE (SSP_TRACE=1 python -m ...build) records anything; the default build returns an error.  buf holds
+ * grid * 4 roles * ssp_debug_trace_cap() int64 records (clock64 << 8 | tag), NULL switches tracing off. ---- */
+int ssp_debug_trace(void* buf);
+int ssp_debug_trace_cap(void);
+
 #ifdef __cplusplus
 }
 #endif

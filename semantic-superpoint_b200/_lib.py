@@ -70,6 +70,16 @@ SIGNATURES = {
     "ssp_sem_ce_up8_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ssp_sample_desc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ssp_nn_match": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "ssp_debug_trace": (_I, [_P]),
+    "ssp_debug_trace_cap": (_I, []),
+    "ssp_xchg_bytes": (_Z, []),
+    "ssp_xchg_max_ranks": (_I, []),
+    "ssp_xchg_alloc": (_I, [_c.POINTER(_P), _P]),
+    "ssp_xchg_open": (_I, [_P, _c.POINTER(_P)]),
+    "ssp_xchg_close": (_I, [_P]),
+    "ssp_xchg_free": (_I, [_P]),
+    "ssp_xchg_status": (_I, [_P, _P]),
+    "ssp_loss_exchange": (_I, [_c.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _D, _P]),
 }
 
 _lib = None

@@ -12,10 +12,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libssp_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# SSP_TRACE=1 selects the instrumented variant (timeline trace of the tcgen05 kernels, scripts/trace_desc.py): its own
+# object directory and library name, so the product library is never the traced one
+TRACE = os.environ.get("SSP_TRACE") == "1"
+LIB_PATH = os.path.join(LIB_DIR, "libssp_b200_trace.so" if TRACE else "libssp_b200.so")
+OBJ_DIR = os.path.join(HERE, "build_trace" if TRACE else "build")
 
-SOURCES = ["api.cu", "warp.cu", "detector.cu", "semantic.cu", "match.cu", "heatmap.cu", "nms.cu", "desc_common.cu", "desc_simt.cu", "desc_tc.cu"]
+SOURCES = ["api.cu", "warp.cu", "detector.cu", "semantic.cu", "match.cu", "heatmap.cu", "nms.cu", "desc_common.cu", "desc_simt.cu", "desc_tc.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",
@@ -42,7 +45,7 @@ def build_library(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DSSP_TRACE"] if TRACE else [])
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))

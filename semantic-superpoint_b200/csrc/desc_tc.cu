@@ -28,6 +28,18 @@
 #include <algorithm>
 #include <cstdlib>
 
+// ---- optional timeline trace (build with -DSSP_TRACE, see scripts/trace_desc.py): lane 0 of one warp per role appends
+// (clock64 << 8 | tag) records to a per-CTA, per-role slice of the buffer registered with ssp_debug_trace().
+#define TRACE_CAP 4096
+#ifdef SSP_TRACE
+__device__ long long* g_trace_buf = nullptr;
+#define TR_DECL(role) long long* tr_ = g_trace_buf ? g_trace_buf + ((size_t)blockIdx.x * 4 + (role)) * TRACE_CAP : nullptr; int trn_ = 0
+#define TR(tag) do { if (tr_ && trn_ < TRACE_CAP) tr_[trn_++] = (clock64() << 8) | (long long)(tag); } while (0)
+#else
+#define TR_DECL(role) do { } while (0)
+#define TR(tag) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;        // rows per CTA
@@ -201,6 +213,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      TR_DECL(1);
       int prev_key = -1, stage_it = 0;
       uint32_t a_empty_ph = 0;
       for (int it = it0; it < it1; ++it) {
@@ -208,7 +221,9 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const int b = key / MP, mp = key - b * MP;
         const int row_base = b * g.Nc_pad;
         if (key != prev_key) {
+          TR(10);
           if (prev_key >= 0) { tc::mbar_wait(a_empty, a_empty_ph); a_empty_ph ^= 1; }  // MMAs on the old A rows are done
+          TR(11);
           tc::mbar_expect_tx(a_full, Cfg::A_BYTES);
           for (int p = 0; p < P; ++p)
             for (int kc = 0; kc < NKC; ++kc)
@@ -220,7 +235,9 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           for (int p = 0; p < P; ++p, ++stage_it) {
             int s = stage_it % NSTAGE;
             uint32_t ph = (stage_it / NSTAGE) & 1;
+            TR(12);
             tc::mbar_wait(b_empty + s, ph ^ 1);  // slot s is free in BOTH CTAs
+            TR(13);
             tc::mbar_expect_tx(b_full + s, BCHUNK_BYTES);
             // my half (128 of the 256 cells) of the chunk, written into both CTAs' slot s
             tc::tma_load_2d_mc(p == 0 ? &tmB_hi : &tmB_lo, b_full + s, sB + s * BCHUNK_BYTES + cta_rank * (BCHUNK_BYTES / 2),
@@ -234,14 +251,18 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BN, 0, 0);
       const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+      TR_DECL(0);
       int prev_key = -1, stage_it = 0, tcount = 0;
       uint32_t a_full_ph = 0;
       for (int it = it0; it < it1; ++it, ++tcount) {
         const int key = it / NT;
+        TR(1);
         if (key != prev_key) { tc::mbar_wait(a_full, a_full_ph); a_full_ph ^= 1; prev_key = key; }
+        TR(2);
         const int as = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
         tc::mbar_wait(t_empty + as, aph ^ 1);
+        TR(3);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BN;
         uint32_t first = 1;
@@ -249,7 +270,9 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           for (int p = 0; p < P; ++p, ++stage_it) {
             int s = stage_it % NSTAGE;
             uint32_t ph = (stage_it / NSTAGE) & 1;
+            TR(4);
             tc::mbar_wait(b_full + s, ph);
+            TR(5);
             tc::fence_after_sync();
             // B plane p (0 = hi, 1 = lo) meets A hi; B hi additionally meets A lo (lo*lo is dropped)
             const int n_a = (P == 2 && p == 0) ? 2 : 1;
@@ -260,6 +283,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
               first = 0;
             }
             tc::mma_commit_mc(b_empty + s, (uint16_t)0x3);  // tell both producers: this CTA is done with slot s
+            TR(6);
           }
         tc::mma_commit(t_full + as);  // accumulator tile complete
         const int next_key = (it + 1 < it1) ? (it + 1) / NT : -2;
@@ -272,6 +296,10 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     const int q = warp & 3, half = warp >> 2;
     const int NW = g.Nc_pad / 32;
     int tcount = 0;
+    TR_DECL(2 + (warp == 7 ? 1 : 0));
+#ifdef SSP_TRACE
+    if (!((warp == 0 || warp == 7) && lane == 0)) tr_ = nullptr;
+#endif
     for (int it = it0; it < it1; ++it, ++tcount) {
       const int key = it / NT, nt = it - key * NT;
       const int b = key / MP, mp = key - b * MP;
@@ -286,7 +314,9 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) mq[j4] = __ldg(mvq + j4);
       }
+      TR(30);
       tc::mbar_wait(t_full + as, aph);
+      TR(31);
       tc::fence_after_sync();
       double su_d = 0.0, sw_d = 0.0;
       float su_t = 0.f, sw_t = 0.f;
@@ -333,6 +363,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(t_empty + as);
+      TR(32);
       if (EPI2) {
         su_t = warp_sum(su_t);
         sw_t = warp_sum(sw_t);
@@ -447,6 +478,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
   if (warp == 12) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      TR_DECL(1);
       int st_it = 0;
       for (int it = it0; it < it1; it += itstep) {
         const int key = it >> 1, dh = it & 1;
@@ -455,7 +487,9 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
         for (int kc = 0; kc < NK; ++kc, ++st_it) {
           int s = st_it % NS;
           uint32_t ph = (st_it / NS) & 1;
+          TR(12);
           tc::mbar_wait(s_free + s, ph ^ 1);
+          TR(13);
           tc::mbar_expect_tx(b_full + s, Cfg::STAGE_BYTES);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           for (int p = 0; p < P; ++p)
@@ -472,19 +506,25 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BG_N, 0, 1);  // A K-major (TMEM), B MN-major
       const uint32_t smem_u = tc::smem_u32(smem);
+      TR_DECL(0);
       int st_it = 0, tcount = 0;
       for (int it = it0; it < it1; it += itstep, ++tcount) {
         const int as = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
+        TR(2);
         tc::mbar_wait(d_empty + as, aph ^ 1);
+        TR(3);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BG_N;
         uint32_t first = 1;
         for (int kc = 0; kc < NK; ++kc, ++st_it) {
           int s = st_it % NS;
           uint32_t ph = (st_it / NS) & 1;
+          TR(4);
           tc::mbar_wait(b_full + s, ph);
+          TR(5);
           tc::mbar_wait(a_full + s, ph);
+          TR(7);
           tc::fence_after_sync();
           for (int p = 0; p < P; ++p) {
             // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B per step); 128 channels = two
@@ -494,6 +534,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
             first = 0;
           }
           tc::mma_commit_mc(s_free + s, (uint16_t)0x3);
+          TR(6);
         }
         tc::mma_commit(d_full + as);
       }
@@ -503,11 +544,17 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // ------------------------------ expanders: indicator bits -> bf16 A operand in TMEM ------------------------------
     const int q = warp;
     int st_it = 0;
+    TR_DECL(2);
+#ifdef SSP_TRACE
+    if (!(warp == 0 && lane == 0)) tr_ = nullptr;
+#endif
     // one ring stage: expand the 64 indicator bits (w0, w1) of this row into 32 TMEM columns of bf16 {0,1}
     auto expand_stage = [&](uint32_t w0, uint32_t w1) {
       int s = st_it % NS;
       uint32_t ph = (st_it / NS) & 1;
+      TR(20);
       tc::mbar_wait(s_free + s, ph ^ 1);
+      TR(21);
       tc::fence_after_sync();
       uint32_t r[32];
 #pragma unroll
@@ -516,10 +563,12 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
         r[2 * i] = e0.x; r[2 * i + 1] = e0.y;
         r[16 + 2 * i] = e1.x; r[16 + 2 * i + 1] = e1.y;
       }
+      TR(22);
       tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
       tc::tmem_st_wait();
       tc::fence_before_sync();
       tc::mbar_arrive(a_full + s);
+      TR(23);
       ++st_it;
     };
     if (DEEPBITS) {
@@ -575,6 +624,10 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
     // two warps per TMEM lane quadrant, each draining two of the four 32-column chunks of the accumulator
     const int q = warp & 3, chalf = (warp - 4) >> 2;
     int tcount = 0;
+    TR_DECL(3);
+#ifdef SSP_TRACE
+    if (!(warp == 4 && lane == 0)) tr_ = nullptr;
+#endif
     for (int it = it0; it < it1; it += itstep, ++tcount) {
       const int key = it >> 1, dh = it & 1;
       const int b = key / MP, mp = key - b * MP;
@@ -595,7 +648,9 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       const int nmax = __reduce_max_sync(0xffffffffu, npos);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
+      TR(30);
       tc::mbar_wait(d_full + as, aph);
+      TR(31);
       tc::fence_after_sync();
       // adds the positive-pair terms of partner list entry n to the 32 channels of chunk ch held in val[]
       auto add_partner = [&](int n, int ch, float (&val)[32]) {
@@ -650,6 +705,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __gri
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(d_empty + as);
+      TR(32);
       if (LATEPOS && nmax > 0 && row_ok) {
         // the accumulator stage is free again; this thread re-reads its own stores and adds the partner terms
 #pragma unroll 1
@@ -737,6 +793,21 @@ int set_smem(K kernel, int bytes) {
 }
 
 }  // namespace
+
+// Profiling aid: registers a device buffer of n_cta * 4 * TRACE_CAP int64 records for the timeline trace of the two tensor-core
+// kernels (library built with -DSSP_TRACE only; otherwise SSP_EUNSUPPORTED).  NULL switches tracing off.
+extern "C" int ssp_debug_trace(void* buf) {
+#ifdef SSP_TRACE
+  long long* p = reinterpret_cast<long long*>(buf);
+  SSP_CUDA_CALL(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
+  return SSP_OK;
+#else
+  (void)buf;
+  ssp_set_error("ssp_debug_trace: library built without -DSSP_TRACE");
+  return SSP_EUNSUPPORTED;
+#endif
+}
+extern "C" int ssp_debug_trace_cap(void) { return TRACE_CAP; }
 
 // partial-sum slots of the forward kernel: one per (item, cluster rank, epilogue warp)
 extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) {

@@ -2,8 +2,9 @@
 
 reference: Train_model_heatmap_all.py:155-179 (detector_loss), utils/utils.py:779-893 (descriptor_loss).
 Multi-GPU: both losses use GLOBAL-batch normalisers, so with `dist_group` set the local
-numerators / mask sums are all-reduced (one tiny NCCL call each) before the division, and the backward
-kernels scale by the global normaliser.
+numerators / mask sums are exchanged by ONE peer-memory kernel (dist.LossExchange, csrc/exchange.cu) that rewrites
+the loss scalars and normalisers in place, stream ordered, before the forward returns; the backward kernels
+scale by the global normaliser.
 """
 import os
 
@@ -100,15 +101,12 @@ class DetectorLossFn(torch.autograd.Function):
         call("ssp_detector_loss_fwd", ptr(x), ptr(t), ptr(m), B, Hc, Wc, 1 if fused2d else 0, ptr(out3), ptr(ws),
              nbytes, stream_of(x))
         ctx.save_for_backward(x, t, m)
-        ctx.out3 = out3  # attribute, not a saved tensor: a deferred exchange patches it in place after forward
+        ctx.out3 = out3  # attribute, not a saved tensor (the exchange rewrites it in place)
         ctx.fused2d = fused2d
-        if dist_group is None:
-            return out3[0]
-        # multi-GPU: the returned scalar is its own tensor (not a view of out3), refreshed when the exchange completes
-        from .dist import globalize_detector
-        res = out3[0].clone()
-        globalize_detector(out3, dist_group, after=lambda: res.copy_(out3[0]))
-        return res
+        if dist_group is not None:
+            from .dist import globalize_detector
+            globalize_detector(out3, dist_group)
+        return out3[0]
 
     @staticmethod
     @once_differentiable
@@ -161,12 +159,10 @@ class SemanticLossFn(torch.autograd.Function):
             ctx.saved = (x, lab, lse2)
         ctx.up, ctx.shape, ctx.ignore = up, (B, C, h, w), int(ignore_index)
         ctx.out3 = out3  # attribute, see DetectorLossFn
-        if dist_group is None:
-            return out3[0]
-        from .dist import globalize_semantic
-        res = out3[0].clone()
-        globalize_semantic(out3, dist_group, after=lambda: res.copy_(out3[0]))
-        return res
+        if dist_group is not None:
+            from .dist import globalize_semantic
+            globalize_semantic(out3, dist_group)
+        return out3[0]
 
     @staticmethod
     @once_differentiable
@@ -214,13 +210,10 @@ class DetectorLossPairFn(torch.autograd.Function):
         ctx.out = out  # see DetectorLossFn
         ctx.fused2d = fused2d
         ctx.mark_non_differentiable(cellmask)
-        if dist_group is None:
-            return out[0, 0], out[1, 0], cellmask
-        from .dist import globalize_detector
-        r0, r1 = out[0, 0].clone(), out[1, 0].clone()
-        globalize_detector(out[0], dist_group, after=lambda: r0.copy_(out[0, 0]))
-        globalize_detector(out[1], dist_group, after=lambda: r1.copy_(out[1, 0]))
-        return r0, r1, cellmask
+        if dist_group is not None:
+            from .dist import get_exchange
+            get_exchange(dist_group).run(det0=out[0], det1=out[1])
+        return out[0, 0], out[1, 0], cellmask
 
     @staticmethod
     @once_differentiable
@@ -333,16 +326,9 @@ class DescriptorLossFn(torch.autograd.Function):
         if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
             raise RuntimeError("descriptor_loss: %d positive pairs overflowed the per-column lists" % int(colcnt[B * Ncp]))
         call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(out8), st)
-        res = None
         if dist_group is not None:
             from .dist import globalize_descriptor
-            res = [out8[i].clone() for i in range(3)]  # own tensors (not views), refreshed when the exchange completes
-
-            def refresh():
-                for i in range(3):
-                    res[i].copy_(out8[i])
-
-            globalize_descriptor(out8, B, Hc, Wc, dist_group, after=refresh)
+            globalize_descriptor(out8, B, Hc, Wc, dist_group)
 
         if need_grad:
             ctx.save_for_backward(Dc, Dwc, mv_pad, bitsR, bitsC, lists_i, lists_f,
@@ -351,8 +337,6 @@ class DescriptorLossFn(torch.autograd.Function):
         ctx.meta = (B, Dch, Hc, Wc, cell, lamda, dist, mpos, engine, planes is not None and planes[1] is not None)
         ctx.fold_alpha = fold_alpha
         ctx.mark_non_differentiable(wpts)
-        if res is not None:
-            return res[0], res[1], res[2], wpts
         return out8[0], out8[1], out8[2], wpts
 
     @staticmethod
@@ -458,13 +442,18 @@ class LossStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, desc, desc_w, Hm, lamda_d, dist,
-                lambda_loss, engine):
+                lambda_loss, engine, dist_group=None):
         c1 = _Ctx((ctx.needs_input_grad[0], False, False, ctx.needs_input_grad[3], False, False, False, False))
         l0, l1, cellmask = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
         B, _, Hc, Wc = semi.shape
         c2 = _Ctx((ctx.needs_input_grad[6], ctx.needs_input_grad[7]) + (False,) * 8)
         ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine,
                                                        None, None, FOLD_ALPHA)
+        if dist_group is not None:
+            # multi-GPU: ONE exchange kernel turns the three local results into global-batch values in place (the scalars
+            # above are views of c1.out / c2.out8); the backward kernels read the global normalisers from the same buffers
+            from .dist import get_exchange
+            get_exchange(dist_group).run(det0=c1.out[0], det1=c1.out[1], desc8=c2.out8, B_local=B, Hc=Hc, Wc=Wc)
         loss = (l0 + l1).add_(ld, alpha=lambda_loss)
         ctx.c1, ctx.c2, ctx.lambda_loss = c1, c2, float(lambda_loss)
         ctx.mark_non_differentiable(l0, l1, ld, pos, neg)
@@ -475,7 +464,7 @@ class LossStepFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g, *_unused):
         if g is None:
-            return (None,) * 13
+            return (None,) * 14
         dev = g.device
         key = (dev.index, ctx.lambda_loss)
         if key not in _lam3:
@@ -486,7 +475,7 @@ class LossStepFn(torch.autograd.Function):
             d0, _, _, d1 = DetectorLossPairFn.backward(ctx.c1, g, _SAME, None)[:4]
         if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
             dD, dDw = DescriptorLossFn.backward(ctx.c2, g * _lam3[key], _SAME, None, None)[:2]
-        return d0, None, None, d1, None, None, dD, dDw, None, None, None, None, None
+        return d0, None, None, d1, None, None, dD, dDw, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

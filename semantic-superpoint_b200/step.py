@@ -20,30 +20,29 @@ def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2
     are added when sem_pred / sem (and the warped twins) are given; sem_pred may be the full-resolution logits or the
     1/8-resolution head output (fused upsample, see utils.sem_loss).
     side_stream: unused (kept for compatibility).
-    fused=True (single GPU): the step is one autograd node and only `loss` carries gradient; the component scalars are
+    fused=True: the step is one autograd node and only `loss` carries gradient; the component scalars are
     values for logging.  Pass fused=False to differentiate through loss_det / positive_dist / negative_dist separately
     (the reference's multi_task_loss weighting, Train_model_heatmap_all.py:355-359).
     """
-    if dist_group is None and fused:
-        # single-GPU fast path: the whole step is one autograd node (no scalar-glue kernels), see losses.LossStepFn
+    if fused:
+        # fast path: the whole step is one autograd node (no scalar-glue kernels), see losses.LossStepFn; with dist_group
+        # set, one peer-memory exchange kernel makes the normalisers global (dist.LossExchange)
         from .losses import LossStepFn, get_descriptor_engine
         Hm = mat_H if mat_H.dim() == 3 else mat_H.unsqueeze(0)
         loss, loss_det, loss_det_warp, loss_desc, pos, neg = LossStepFn.apply(
             semi, labels_2D, mask_2D, semi_warp, warped_labels, mask_warp_2D, desc, desc_warp,
             Hm.to(device=semi.device, dtype=torch.float32).contiguous(), float(lamda_d), float(descriptor_dist),
-            float(lambda_loss), engine or get_descriptor_engine())
+            float(lambda_loss), engine or get_descriptor_engine(), dist_group)
         out = {}
         if sem_pred is not None:
-            out["loss_sem"] = U.sem_loss(sem_pred, sem)
-            out["loss_sem_warp"] = U.sem_loss(sem_warp_pred, warped_sem)
+            out["loss_sem"] = U.sem_loss(sem_pred, sem, dist_group=dist_group)
+            out["loss_sem_warp"] = U.sem_loss(sem_warp_pred, warped_sem, dist_group=dist_group)
             loss = loss + out["loss_sem"] + out["loss_sem_warp"]
         out.update({"loss": loss, "loss_det": loss_det, "loss_det_warp": loss_det_warp, "loss_desc": loss_desc,
                     "positive_dist": pos, "negative_dist": neg})
         return out
-    # multi-GPU: the global-normaliser all-reduces are launched asynchronously and overlap the following kernels
-    if dist_group is not None:
-        from .dist import DeferredExchange
-        dist_group = DeferredExchange(dist_group)
+    # separately differentiable components (the reference's multi_task_loss weighting); with dist_group each loss runs
+    # its own exchange kernel
     # both detector losses in one launch each way; getMasks(mask_warp_2D) comes out of the same kernel
     loss_det, loss_det_warp, mask_cells = U.detector_loss_pair_2d(semi, labels_2D, mask_2D, semi_warp, warped_labels,
                                                                   mask_warp_2D, dist_group=dist_group)
@@ -57,8 +56,6 @@ def loss_step(semi, semi_warp, desc, desc_warp, labels_2D, warped_labels, mask_2
     if sem_pred is not None:
         out["loss_sem"] = U.sem_loss(sem_pred, sem, dist_group=dist_group)
         out["loss_sem_warp"] = U.sem_loss(sem_warp_pred, warped_sem, dist_group=dist_group)
-    if dist_group is not None:
-        dist_group.finish()
     loss = loss_det + loss_det_warp + lambda_loss * loss_desc
     if sem_pred is not None:
         loss = loss + out["loss_sem"] + out["loss_sem_warp"]

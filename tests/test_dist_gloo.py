@@ -1,6 +1,7 @@
 """world_size-2 gloo test of the only exchange step on the path: the global-batch normalisers of both losses
-(SURVEY 8e).  Each rank holds half of the batch; after the all-reduce every rank must report the loss the
-oracle computes on the whole batch."""
+(SURVEY 8e).  The two ranks hold 3 and 2 of the 5 pairs (uneven shards: the batch size is part of the exchanged
+payload); after the exchange every rank must report the loss the oracle computes on the whole batch.  On CPU the
+exchange runs its torch.distributed form (one all-reduce); the peer-memory kernel is covered by the -m gpu tests."""
 import os
 import socket
 
@@ -11,7 +12,7 @@ import torch.multiprocessing as mp
 from oracle import ssp_oracle as O
 from ssp_b200 import synth
 
-B, HC, WC, DCH = 4, 6, 8, 32
+B, HC, WC, DCH = 5, 6, 8, 32
 
 
 def _inputs():
@@ -36,11 +37,12 @@ def _sem_inputs():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as tdist
-    from ssp_b200.dist import (DeferredExchange, globalize_descriptor, globalize_detector, globalize_semantic, init_from_env,
-                               shard_range)
+    from ssp_b200.dist import (LossExchange, get_exchange, globalize_descriptor, globalize_detector, globalize_semantic,
+                               init_from_env, shard_range)
     init_from_env(backend="gloo")
+    assert get_exchange(True).backend == "allreduce"  # CPU tensors / gloo: the torch.distributed form of the exchange
     Hs, D, Dw, mv, semi, lab, m3 = _inputs()
-    lo, hi = shard_range(B, rank, world)
+    lo, hi = shard_range(B, rank, world)   # B = 5 over 2 ranks: shards of 3 and 2 pairs (uneven on purpose)
     # local shard through the oracle -> the raw sums the kernels would emit (out8 / out3 layouts)
     l, _, p, n = O.descriptor_loss(D[lo:hi], Dw[lo:hi], Hs[lo:hi], mv[lo:hi])
     norm = np.float32(hi - lo) * (mv[lo:hi].sum() + 1) * HC * WC
@@ -50,15 +52,12 @@ def _worker(rank, world, port, q):
     den = np.float32(m3[lo:hi].sum() + 1e-5)
     out3 = torch.tensor([ld, ld * den, den], dtype=torch.float32)
     globalize_detector(out3, True)
-    # the deferred (asynchronous) exchange used by step.loss_step must give the same numbers
-    ex = DeferredExchange(True)
+    # the fused step exchanges everything in ONE call: same numbers
     out8d = torch.tensor([l, p, n, norm, l * norm, p * norm, n * norm, mv[lo:hi].sum()], dtype=torch.float32)
     out3d = torch.tensor([ld, ld * den, den], dtype=torch.float32)
-    globalize_detector(out3d, ex)
-    globalize_descriptor(out8d, hi - lo, HC, WC, ex)
-    assert len(ex.pending) == 2
-    ex.finish()
-    assert torch.equal(out8d, out8) and torch.equal(out3d, out3)
+    out3e = out3d.clone()
+    LossExchange(True).run(det0=out3d, det1=out3e, desc8=out8d, B_local=hi - lo, Hc=HC, Wc=WC)
+    assert torch.equal(out8d, out8) and torch.equal(out3d, out3) and torch.equal(out3e, out3)
     # semantic cross entropy: mean over the counted pixels of the global batch
     sl, slab = _sem_inputs()
     ls = O.sem_loss(sl[lo:hi], slab[lo:hi])
