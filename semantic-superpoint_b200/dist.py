@@ -143,7 +143,7 @@ class LossExchange(object):
                 pay[2], pay[3] = det1[1], det1[2] - 1e-5
             if desc8 is not None:
                 pay[4:8] = desc8[4:8]
-            pay[8] = float(B_local)
+            pay[8:9].fill_(float(B_local))  # a fill kernel, not a host-to-device copy: legal inside CUDA graph capture
             if sem0 is not None:
                 pay[9:11] = sem0[1:3]
             if sem1 is not None:
