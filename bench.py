@@ -334,8 +334,8 @@ def run_ours(args):
         pk = peaks()
         flops_pair = 2.0 * NC * NC * DCH
         bound_tbl = {
-            "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B), "ssp_desc_dense_fwd_tc_ex": ("tensor", flops_pair * B),
-        "ssp_desc_bits_gemm_tc": ("tensor", flops_pair * B),
+            "ssp_desc_dense_fwd_tc": ("tensor", flops_pair * B),
+            "ssp_desc_bits_gemm_tc_pair": ("tensor", 2 * flops_pair * B),  # both indicator GEMMs (dD, dDw) in one launch
             "ssp_desc_bits_gemm_tc_planes": ("tensor", flops_pair * B), "ssp_desc_pos_fwd_planes": ("hbm", 2.0 * B * NC * DCH * 4),
             "ssp_desc_dense_fwd_simt": ("tensor", flops_pair * B), "ssp_desc_bits_gemm_simt": ("tensor", flops_pair * B),
             "ssp_desc_pack": ("hbm", B * NC * DCH * 4 * 2.0), "ssp_desc_pos_fwd": ("hbm", 2.0 * B * NC * DCH * 4),
@@ -354,7 +354,7 @@ def run_ours(args):
             achieved, peak, unit = work / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
         # DRAM traffic of that kernel from the committed ncu --set full capture of this same command (per launch)
         traffic = None
-        kern_of = {"ssp_desc_bits_gemm_tc": "desc_bits_gemm_tc_kernel", "ssp_desc_bits_gemm_tc_planes": "desc_bits_gemm_tc_kernel",
+        kern_of = {"ssp_desc_bits_gemm_tc_pair": "desc_bits_gemm_tc_kernel", "ssp_desc_bits_gemm_tc_planes": "desc_bits_gemm_tc_kernel",
                    "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
                    "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel"}
         tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")

@@ -92,11 +92,15 @@ int ssp_box_nms(const float* prob /*[I,H,W]*/, int I, int H, int W, float min_pr
 
 /* ---- a5: descriptor_loss (utils/utils.py:779-893), forward and backward, split into stages.
  *      Nc = Hc*Wc, Nc_pad = ceil(Nc/256)*256.  wpts [B,Nc_pad,2], mv_pad [B,Nc_pad],
- *      bitsR/bitsC [B,Nc_pad/32,Nc_pad] u32 indicator bit-matrices, partials = per-CTA (unweighted, weighted)
- *      double pairs.  out8 = { loss, pos_sum, neg_sum, norm, num_loss, num_pos, num_neg, sum(mask_valid) } ---- */
+ *      bitsR/bitsC [B,Nc_pad/32,Nc_pad] u32 indicator bit-matrices (element j of a word at bit (j>>1)|((j&1)<<4)),
+ *      partials = per-CTA (unweighted, weighted) double pairs.
+ *      out8 = { loss, pos_sum, neg_sum, norm, num_loss, num_pos, num_neg, sum(mask_valid) }
+ *      mvbits (optional, [B,Nc_pad/32] u32): mask_valid != 0 per cell in the same bit order, for the "fold" mode of the
+ *      tensor-core engine (mask folded into the indicator words; a non-binary mask then poisons the normaliser: NaN) ---- */
 int ssp_desc_geometry_nblocks(int B, int Nc);
 int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/, int B, int Hc, int Wc,
-                      int cell, float* wpts, float* mv_pad, double* mv_part /*[geometry_nblocks]*/, void* stream);
+                      int cell, float* wpts, float* mv_pad, double* mv_part /*[geometry_nblocks]*/,
+                      uint32_t* mvbits /*or NULL*/, void* stream);
 int ssp_desc_pos_nblocks(int B, int Nc);
 int ssp_desc_maxp(void); /* DESC_MAXP: list slots per row / column */
 /* sparse positive pairs: exact fp32 dots, partial sums (4 doubles per block: pos_u, pos_w, negcorr_u, negcorr_w)
@@ -121,26 +125,28 @@ int ssp_desc_pack(const float* src /*[B,Dch,Nc]*/, const float* scale /*[B,Nc_pa
 int ssp_desc_pack2(const float* src0, const float* src1 /*or NULL*/, const float* scale, int B, int Dch, int Nc, void* hi0,
                    void* lo0, void* hi1, void* lo1, void* stream);
 int ssp_desc_dense_tc_nblocks(int B, int Nc);
+/* tcgen05 forward (CTA-pair MMAs, M=256): negative hinge over all pairs + indicator words; bitsC = transpose of bitsR
+ * (second kernel of the same call).  The lo planes must lie above their hi planes in memory (one allocation).
+ * mvbits != NULL ("fold"): the indicator words drop the columns whose mask_valid is 0, so the dD indicator GEMM can take
+ * the unscaled forward planes of Dw and one scalar (valid when mask_valid is binary and g_neg = 0). */
 int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
-                          int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
-                          float* dbgS, void* stream);
-/* Same, with flags.  Bit 0: bitsR (row orientation) drops the columns whose mask_valid is 0, so the dD indicator GEMM can
- * take the unscaled forward planes of Dw and one scalar (valid when mask_valid is binary and g_neg = 0).  Needs the
- * EPI2 epilogue (SSP_FWD_EPI=2); experimental, see DESIGN 7. */
-int ssp_desc_dense_fwd_tc_ex(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, const float* mv_pad,
-                             int B, int Hc, int Wc, float mneg, double* partials, uint32_t* bitsR, uint32_t* bitsC,
-                             float* dbgS, int flags, void* stream);
+                          const uint32_t* mvbits /*or NULL*/, int B, int Hc, int Wc, float mneg, double* partials,
+                          uint32_t* bitsR, uint32_t* bitsC, float* dbgS, void* stream);
+/* overflow (optional) = &colcnt[B*Nc_pad], the counter of positive pairs that did not fit the sparse lists: non-zero
+ * makes loss / pos_sum NaN (loud without a host sync) */
 int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const double* mv_part,
-                      int nmv, int B, int Hc, int Wc, float* out8, void* stream);
+                      int nmv, int B, int Hc, int Wc, const int* overflow, float* out8, void* stream);
 int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,
                        void* stream);
 int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)*/, const float* out8, int B,
                    int Nc_pad, float* alpha /*[B,Nc_pad]*/, void* stream);
-/* backward coefficients of the positive pairs (and removal of their negative term); sorts colrow in place */
-int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, int* colrow, const float* coldot,
+/* backward coefficients of the positive pairs (and removal of their negative term).  colrow_sorted receives the column
+ * lists ordered by row index (deterministic summation order) with their coefficients in colcoef; the forward's lists
+ * are left untouched, so a second backward over the same graph sees the same inputs */
+int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow, const float* coldot,
                       const uint32_t* bitsR, const float* mv_pad, const float* alpha, const float* g3,
-                      const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, float* colcoef,
-                      void* stream);
+                      const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, int* colrow_sorted,
+                      float* colcoef, void* stream);
 /* dD[b,:,r] += sum_n rowcoef[b,r,n] Dw[b,:,rowcol[b,r,n]];  dDw[b,:,c] += sum_n colcoef[b,c,n] D[b,:,colrow[b,c,n]] */
 int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef, const float* D,
                        const float* Dw, int B, int Dch, int Nc, int which /*0 both, 1 dD, 2 dDw*/, float* dD, float* dDw,
@@ -150,14 +156,17 @@ int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colro
 int ssp_desc_bits_gemm_simt(const uint32_t* bits, const float* src /*[B,Dch,Nc]*/, const float* colscale,
                             const float* rowscale, const int* plist, const float* pcoef, const float* possrc, int B,
                             int Dch, int Nc, float* out /*[B,Dch,Nc]*/, void* stream);
-int ssp_desc_bits_gemm_tc(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
-                          const int* plist, const float* pcoef, const float* possrc /*[B,256,Nc]*/, int B, int Nc,
-                          float* out /*[B,256,Nc]*/, void* stream);
-/* Same GEMM, positive-pair partners read from packed planes [B,Nc_pad,256] bf16 (pos_lo may be NULL): 64 contiguous
- * bytes per plane and 32-channel chunk instead of 32 words 4*Nc bytes apart. */
+/* tcgen05 indicator GEMM (CTA-pair MMAs, A = indicator bits expanded into TMEM, B = packed planes [B,Nc_pad,256] bf16,
+ * Blo above Bhi in memory or NULL); positive-pair partners read from packed planes pos_hi (+ pos_lo). */
 int ssp_desc_bits_gemm_tc_planes(const uint32_t* bits, const void* Bhi, const void* Blo, const float* rowscale,
                                  const int* plist, const float* pcoef, const void* pos_hi, const void* pos_lo, int B,
                                  int Nc, float* out /*[B,256,Nc]*/, void* stream);
+/* both indicator GEMMs of the backward (job 0: dD, job 1: dDw) in ONE persistent launch */
+int ssp_desc_bits_gemm_tc_pair(const uint32_t* bits0, const void* Bhi0, const void* Blo0, const float* rowscale0,
+                               const int* plist0, const float* pcoef0, const void* pos_hi0, const void* pos_lo0,
+                               float* out0, const uint32_t* bits1, const void* Bhi1, const void* Blo1,
+                               const float* rowscale1, const int* plist1, const float* pcoef1, const void* pos_hi1,
+                               const void* pos_lo1, float* out1, int B, int Nc, void* stream);
 
 /* ---- semantic head: cross entropy with ignore_index, optionally fused with the x8 bilinear upsample ------------
  * (not part of the five north-star pieces, same boundary.)

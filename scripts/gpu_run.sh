@@ -1,0 +1,20 @@
+#!/bin/bash
+# Parameterised GPU-lease runner (replaces the one-off gpu_r1*.sh scripts).  Every step runs under its own `timeout`
+# so that a hung kernel cannot hold the box.  usage: bash scripts/gpu_run.sh step [step ...]   steps:
+#   tests[:EXPR]   pytest -m gpu (optionally -k EXPR)          micro     isolation timings of the tcgen05 kernels
+#   bench[:ARGS]   bench.py (1 GPU) with extra ARGS             trace     timeline trace (SSP_TRACE build)
+#   smoke          __graft_entry__.smoke()                      ref       bench.py --impl reference
+mkdir -p gpurun_out
+for step in "$@"; do
+  name=${step%%:*}; arg=""; [[ "$step" == *:* ]] && arg=${step#*:}
+  case $name in
+    tests) if [ -n "$arg" ]; then timeout 900 python -m pytest tests -q -m gpu -x -p no:cacheprovider -k "$arg" > gpurun_out/t_gpu.log 2>&1; else timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_gpu.log 2>&1; fi
+           echo "tests[$arg] rc=$? $(tail -1 gpurun_out/t_gpu.log)"; grep -E "^(FAILED|ERROR)" gpurun_out/t_gpu.log | head -20 ;;
+    micro) timeout 300 python scripts/micro_desc.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?"; cat gpurun_out/micro.log | tail -20 ;;
+    trace) SSP_TRACE=1 timeout 300 python scripts/trace_desc.py gpurun_out/trace.npz > gpurun_out/trace.log 2>&1; echo "trace rc=$?"; tail -3 gpurun_out/trace.log ;;
+    bench) timeout 600 python bench.py $arg > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; python scripts/show_bench.py gpurun_out/bench.json 2>/dev/null | head -24 ;;
+    ref)   timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json | cut -c1-300 ;;
+    smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log ;;
+    *) echo "unknown step $step" ;;
+  esac
+done

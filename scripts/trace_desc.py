@@ -1,4 +1,4 @@
-"""Timeline trace of the two tcgen05 kernels (forward dense GEMM, backward indicator GEMM) at bench sizes.
+"""Timeline trace of the two tcgen05 kernels (forward dense GEMM, backward indicator GEMM pair) at bench sizes.
 
     SSP_TRACE=1 python scripts/trace_desc.py gpurun_out/trace.npz
 
@@ -8,8 +8,9 @@ waits of its pipeline; `scripts/trace_report.py` turns the dump into per-role wa
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 assert os.environ.get("SSP_TRACE") == "1", "run with SSP_TRACE=1"
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from ssp_b200 import _lib, synth
@@ -19,36 +20,44 @@ B, Hc, Wc, Dch = 32, 30, 40, 256
 Nc, Ncp = Hc * Wc, 1280
 dev = "cuda"
 lib = _lib.load()
-CAP = lib.ssp_debug_trace_cap()
 D = torch.from_numpy(synth.unit_descriptors(B, Dch, Hc, Wc, 1, smooth=0.3)).to(dev)
 Dw = torch.from_numpy(synth.unit_descriptors(B, Dch, Hc, Wc, 2, smooth=0.3)).to(dev)
 mv = torch.ones((B, Ncp), device=dev)
-planes = [torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev) for _ in range(4)]
+PA = torch.empty((2, B, Ncp, Dch), dtype=torch.bfloat16, device=dev)  # hi, lo planes of D (lo above hi)
+PB = torch.empty_like(PA)                                             # hi, lo planes of Dw
 st = stream_of(D)
-call("ssp_desc_pack2", ptr(D), ptr(Dw), None, B, Dch, Nc, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), ptr(planes[3]), st)
+call("ssp_desc_pack2", ptr(D), ptr(Dw), None, B, Dch, Nc, ptr(PA[0]), ptr(PA[1]), ptr(PB[0]), ptr(PB[1]), st)
 nneg = lib.ssp_desc_dense_tc_nblocks(B, Nc)
 part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
 bitsR = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
 bitsC = torch.empty_like(bitsR)
 out = torch.empty((B, Dch, Nc), device=dev)
+out2 = torch.empty((B, Dch, Nc), device=dev)
 plist = torch.full((B, Ncp, 16), -1, dtype=torch.int32, device=dev)
 plist[:, :Nc, 0] = torch.arange(Nc, device=dev, dtype=torch.int32)[None]
 pcoef = torch.ones((B, Ncp, 16), device=dev)
+
+
+def fwd(bits=True, split=True, transpose=True):
+    call("ssp_desc_dense_fwd_tc", ptr(PA[0]), ptr(PA[1]) if split else None, ptr(PB[0]), ptr(PB[1]) if split else None, ptr(mv), None,
+         B, Hc, Wc, 0.2, ptr(part), ptr(bitsR) if bits else None, ptr(bitsC) if (bits and transpose) else None, None, st)
+
+
+def bwd1(pos=True, split=True):
+    call("ssp_desc_bits_gemm_tc_planes", ptr(bitsR), ptr(PB[0]), ptr(PB[1]) if split else None, None, ptr(plist) if pos else None,
+         ptr(pcoef) if pos else None, ptr(PB[0]), ptr(PB[1]) if split else None, B, Nc, ptr(out), st)
+
+
+def bwd2(pos=True, split=True):
+    lo = (lambda t: ptr(t[1])) if split else (lambda t: None)
+    pl, pc = (ptr(plist), ptr(pcoef)) if pos else (None, None)
+    call("ssp_desc_bits_gemm_tc_pair", ptr(bitsR), ptr(PB[0]), lo(PB), None, pl, pc, ptr(PB[0]), lo(PB), ptr(out),
+         ptr(bitsC), ptr(PA[0]), lo(PA), ptr(mv), pl, pc, ptr(PA[0]), lo(PA), ptr(out2), B, Nc, st)
+
+CAP = lib.ssp_debug_trace_cap()
 flush = torch.empty((64 << 20,), dtype=torch.float32, device=dev)  # 256 MB > L2
-
-
-def fwd():
-    call("ssp_desc_dense_fwd_tc", ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), ptr(planes[3]), ptr(mv), B, Hc, Wc, 0.2,
-         ptr(part), ptr(bitsR), ptr(bitsC), None, st)
-
-
-def bwd():
-    call("ssp_desc_bits_gemm_tc_planes", ptr(bitsR), ptr(planes[2]), ptr(planes[3]), None, ptr(plist), ptr(pcoef),
-         ptr(planes[2]), ptr(planes[3]), B, Nc, ptr(out), st)
-
-
 res = {}
-for name, fn in (("fwd", fwd), ("bwd", bwd)):
+for name, fn in (("fwd", fwd), ("bwd", bwd2)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

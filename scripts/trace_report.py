@@ -43,7 +43,7 @@ for name in ("fwd", "bwd"):
             r["mma_issue"] = spans(t0, tag0, 7, 6)[0]
             r["n_stages"] = spans(t0, tag0, 4, 5)[1]
         else:
-            r["mma_wait_afull"] = spans(t0, tag0, 1, 2)[0]
+            r["mma_wait_afull"] = spans(t0, tag0, 1, 8)[0]
             r["mma_wait_tempty"] = spans(t0, tag0, 2, 3)[0]
             r["mma_wait_b"] = spans(t0, tag0, 4, 5)[0]
             r["mma_issue"] = spans(t0, tag0, 5, 6)[0]

@@ -42,7 +42,7 @@ SIGNATURES = {
     "ssp_nms_fast": (_I, [_P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _Z, _P]),
     "ssp_box_nms": (_I, [_P, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "ssp_desc_geometry_nblocks": (_I, [_I, _I]),
-    "ssp_desc_geometry": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ssp_desc_geometry": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ssp_desc_pos_nblocks": (_I, [_I, _I]),
     "ssp_desc_maxp": (_I, []),
     "ssp_desc_pos_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
@@ -53,16 +53,15 @@ SIGNATURES = {
     "ssp_desc_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_pack2": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
-    "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
-    "ssp_desc_dense_fwd_tc_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _I, _P]),
-    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P]),
+    "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
     "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P]),
-    "ssp_desc_pos_coef": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "ssp_desc_pos_coef": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P]),
     "ssp_desc_pos_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
-    "ssp_desc_bits_gemm_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "ssp_desc_bits_gemm_tc_planes": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "ssp_desc_bits_gemm_tc_pair": (_I, [_P] * 18 + [_I, _I, _P]),
     "ssp_sem_ce_ws_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "ssp_sem_ce_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "ssp_sem_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -119,7 +118,7 @@ def check(rc, what):
 
 # kernels launched per entry point (memsets / copies not counted); the NMS drivers launch init + >= 2 rounds +
 # compact + rank, counted at their minimum
-KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2,
+KERNELS_PER_CALL = {"ssp_desc_dense_fwd_tc": 2, "ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2,
                     "ssp_sem_ce_fwd": 2, "ssp_sem_ce_up8": 2}
 kernel_count = 0
 _prof = None

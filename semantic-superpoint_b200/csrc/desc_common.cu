@@ -9,7 +9,8 @@
 // ----------------------------------------------------------------------------------------------
 __global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* __restrict__ mask_valid, int B,
                                      int Hc, int Wc, int cell, int Nc_pad, float2* __restrict__ wpts,
-                                     float* __restrict__ mv_pad, double* __restrict__ mv_part) {
+                                     float* __restrict__ mv_pad, double* __restrict__ mv_part,
+                                     uint32_t* __restrict__ mvbits) {
   __shared__ double shd[32];
   int b = blockIdx.y;
   int c = blockIdx.x * blockDim.x + threadIdx.x;  // Nc_pad is a multiple of the block size
@@ -32,21 +33,31 @@ __global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* 
   }
   wpts[(size_t)b * Nc_pad + c] = w;
   mv_pad[(size_t)b * Nc_pad + c] = mv;
+  double mvs = (double)mv;
+  if (mvbits) {
+    // "fold" mode of the tensor-core engine: the mask is folded into the indicator words, which is only exact for a
+    // BINARY mask.  Anything else poisons the normaliser (NaN loss and gradients): loud, and without a host sync.
+    if (mv != 0.f && mv != 1.f) mvs = __longlong_as_double(0x7ff8000000000000ll);
+    const uint32_t word = __reduce_or_sync(0xffffffffu, (mv != 0.f ? 1u : 0u) << DESC_BITPOS(threadIdx.x & 31));
+    if ((threadIdx.x & 31) == 0) mvbits[((size_t)b * Nc_pad + c) >> 5] = word;
+  }
   // per-block partial of sum(mask_valid) for the global normaliser (summed in fixed order by finalize)
-  double part = block_sum_d((double)mv, shd);
+  double part = block_sum_d(mvs, shd);
   if (threadIdx.x == 0) mv_part[(size_t)b * gridDim.x + blockIdx.x] = part;
 }
 
 extern "C" int ssp_desc_geometry_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / 128); }
 
+// mvbits (optional): [B, Nc_pad/32] words of mask_valid != 0 in DESC_BITPOS order for the "fold" mode of the tensor-core
+// engine; requesting them also makes a non-binary mask poison the normaliser with NaN.
 extern "C" int ssp_desc_geometry(const float* Hm, const float* mask_valid, int B, int Hc, int Wc, int cell,
-                                 float* wpts, float* mv_pad, double* mv_part, void* stream) {
+                                 float* wpts, float* mv_pad, double* mv_part, uint32_t* mvbits, void* stream) {
   SSP_REQUIRE(Hm && wpts && mv_pad && mv_part, "ssp_desc_geometry: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Hc > 0 && Wc > 0 && cell > 0, "ssp_desc_geometry: bad sizes");
   int Nc_pad = desc_nc_pad(Hc * Wc);
   dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
   desc_geometry_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Hm, mask_valid, B, Hc, Wc, cell, Nc_pad,
-                                                                reinterpret_cast<float2*>(wpts), mv_pad, mv_part);
+                                                                reinterpret_cast<float2*>(wpts), mv_pad, mv_part, mvbits);
   SSP_CUDA_CHECK_LAUNCH("desc_geometry_kernel");
   return SSP_OK;
 }
@@ -103,13 +114,18 @@ desc_pos_fwd_kernel(const float* __restrict__ D, const float* __restrict__ Dw, c
       float2 w = wpts[(size_t)b * g.Nc_pad + r];
       int k0, k1, l0, l1;
       pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
+      int dropped = 0;
       for (int k = k0; k <= k1; ++k)
         for (int l = l0; l <= l1; ++l) {
           int c = k * g.Wc + l;
           float cx, cy;
           cell_center(c, g.Wc, g.cell, cx, cy);
-          if (pair_positive(w.x, w.y, cx, cy, g.dist) && cnt < DESC_MAXP) scol[lane][cnt++] = c;
+          if (pair_positive(w.x, w.y, cx, cy, g.dist)) {
+            if (cnt < DESC_MAXP) scol[lane][cnt++] = c;
+            else ++dropped;
+          }
         }
+      if (dropped) atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, dropped);  // overflow counter: finalize turns it into NaN
     }
     scnt[lane] = cnt;
     if (r < g.Nc_pad) {
@@ -260,7 +276,8 @@ desc_pos_fwd_planes_kernel(const uint4* __restrict__ Ahi, const uint4* __restric
     int k0, k1, l0, l1;
     pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
     const int nl = l1 - l0 + 1, ncand = (k1 >= k0 && nl > 0) ? (k1 - k0 + 1) * nl : 0;
-    for (int base = 0; base < ncand && cnt < DESC_MAXP; base += 32) {
+    int nhit = 0;
+    for (int base = 0; base < ncand; base += 32) {
       const int i = base + lane;
       bool hit = false;
       int c = -1;
@@ -279,8 +296,10 @@ desc_pos_fwd_planes_kernel(const uint4* __restrict__ Ahi, const uint4* __restric
         const int s = __shfl_sync(0xffffffffu, slot, src), cc = __shfl_sync(0xffffffffu, c, src);
         if (lane == s && s < DESC_MAXP) mycol = cc;
       }
-      cnt = min(cnt + __popc(bal), DESC_MAXP);
+      nhit += __popc(bal);
+      cnt = min(nhit, DESC_MAXP);
     }
+    if (nhit > DESC_MAXP && lane == 0) atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, nhit - DESC_MAXP);  // overflow counter
   }
   if (r < g.Nc_pad && lane < DESC_MAXP) rowcol[((size_t)b * g.Nc_pad + r) * DESC_MAXP + lane] = lane < cnt ? mycol : -1;
   if (cnt) {
@@ -360,7 +379,8 @@ extern "C" int ssp_desc_pos_fwd_planes(const void* Ahi, const void* Alo, const v
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double* __restrict__ neg_part, int nneg,
-                     const double* __restrict__ mv_part, int nmv, int B, int Hc, int Wc, float* __restrict__ out4) {
+                     const double* __restrict__ mv_part, int nmv, int B, int Hc, int Wc, const int* __restrict__ overflow,
+                     float* __restrict__ out4) {
   __shared__ double sh[32];
   double pu = 0, pw = 0, nu = 0, nw = 0, sm = 0;
   double cu = 0, cw = 0;  // negative-hinge contribution of the positive pairs, contained in the dense sums
@@ -402,6 +422,9 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
   if (threadIdx.x == 0) {
     nu -= cu;
     nw -= cw;
+    // positive pairs that did not fit the sparse lists (strong minification, descriptor_dist close to the cell size): the
+    // loss and its gradient would silently miss them -- poison the result instead (NaN, no host sync needed to notice)
+    if (overflow && *overflow != 0) pu = pw = __longlong_as_double(0x7ff8000000000000ll);
     float norm = (float)B * ((float)sm + 1.f) * (float)Hc * (float)Wc;
     out4[0] = (float)((pw + nw) / (double)norm);
     out4[1] = (float)(pu / (double)norm);
@@ -415,12 +438,14 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
   }
 }
 
+// overflow (optional): the list-overflow counter colcnt[B * Nc_pad] of the pos kernels; non-zero poisons loss and pos with NaN
 extern "C" int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg,
-                                 const double* mv_part, int nmv, int B, int Hc, int Wc, float* out4, void* stream) {
+                                 const double* mv_part, int nmv, int B, int Hc, int Wc, const int* overflow, float* out4,
+                                 void* stream) {
   SSP_REQUIRE(pos_part && neg_part && mv_part && out4, "ssp_desc_finalize: null pointer");
   SSP_REQUIRE(npos >= 0 && nneg >= 0 && nmv >= 0 && B > 0 && Hc > 0 && Wc > 0, "ssp_desc_finalize: bad sizes");
   SSP_REQUIRE((((uintptr_t)pos_part | (uintptr_t)neg_part) & 15) == 0, "ssp_desc_finalize: partial-sum arrays must be 16-byte aligned");
-  desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_part, nmv, B, Hc, Wc, out4);
+  desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_part, nmv, B, Hc, Wc, overflow, out4);
   SSP_CUDA_CHECK_LAUNCH("desc_finalize_kernel");
   return SSP_OK;
 }
@@ -508,7 +533,7 @@ __device__ __forceinline__ void pos_coef_rows(const int* __restrict__ rowcol, co
     if (c >= 0) {
       coef = pos_coef(dd[n], mv_pad[(size_t)b * Nc_pad + c], g3, norm, lamda, mpos);
       uint32_t w = bitsR[((size_t)b * NW + (c >> 5)) * Nc_pad + cell];
-      if ((w >> (c & 31)) & 1u) coef -= alpha[(size_t)b * Nc_pad + c];
+      if ((w >> DESC_BITPOS(c & 31)) & 1u) coef -= alpha[(size_t)b * Nc_pad + c];
     }
     cf[n] = coef;
   }
@@ -518,10 +543,10 @@ __device__ __forceinline__ void pos_coef_rows(const int* __restrict__ rowcol, co
 }
 
 template <int N>
-__device__ __forceinline__ void pos_coef_cols(int cnt, int* __restrict__ colrow, const float* __restrict__ coldot, size_t base,
+__device__ __forceinline__ void pos_coef_cols(int cnt, const int* __restrict__ colrow, const float* __restrict__ coldot, size_t base,
                                               int b, int cell, int Nc_pad, int NW, const uint32_t* __restrict__ bitsR,
                                               float mv, float al, const float* __restrict__ g3, float norm, float lamda,
-                                              float mpos, float* __restrict__ colcoef) {
+                                              float mpos, int* __restrict__ colrow_sorted, float* __restrict__ colcoef) {
   int rr[N];
   float dd[N];
 #pragma unroll
@@ -553,7 +578,7 @@ __device__ __forceinline__ void pos_coef_cols(int cnt, int* __restrict__ colrow,
       int r = rr[n];
       float coef = pos_coef(dd[n], mv, g3, norm, lamda, mpos);
       uint32_t w = bitsR[((size_t)b * NW + (cell >> 5)) * Nc_pad + r];
-      if ((w >> (cell & 31)) & 1u) coef -= al;
+      if ((w >> DESC_BITPOS(cell & 31)) & 1u) coef -= al;
       cf[n] = coef;
     } else {
       rr[n] = -1;
@@ -561,21 +586,22 @@ __device__ __forceinline__ void pos_coef_cols(int cnt, int* __restrict__ colrow,
   }
 #pragma unroll
   for (int n = 0; n < N; n += 4) {
-    *reinterpret_cast<int4*>(colrow + base + n) = make_int4(rr[n], rr[n + 1], rr[n + 2], rr[n + 3]);
+    *reinterpret_cast<int4*>(colrow_sorted + base + n) = make_int4(rr[n], rr[n + 1], rr[n + 2], rr[n + 3]);
     *reinterpret_cast<float4*>(colcoef + base + n) = make_float4(cf[n], cf[n + 1], cf[n + 2], cf[n + 3]);
   }
   // the consumers scan all DESC_MAXP slots of a list for entries >= 0
 #pragma unroll
-  for (int n = N; n < DESC_MAXP; n += 4) *reinterpret_cast<int4*>(colrow + base + n) = make_int4(-1, -1, -1, -1);
+  for (int n = N; n < DESC_MAXP; n += 4) *reinterpret_cast<int4*>(colrow_sorted + base + n) = make_int4(-1, -1, -1, -1);
 }
 
 __global__ void __launch_bounds__(128)
 desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowdot,
-                     const int* __restrict__ colcnt, int* __restrict__ colrow,
+                     const int* __restrict__ colcnt, const int* __restrict__ colrow,
                      const float* __restrict__ coldot, const uint32_t* __restrict__ bitsR,
                      const float* __restrict__ mv_pad, const float* __restrict__ alpha,
                      const float* __restrict__ g3, const float* __restrict__ out8, int Nc_pad,
-                     float lamda, float mpos, float* __restrict__ rowcoef, float* __restrict__ colcoef) {
+                     float lamda, float mpos, float* __restrict__ rowcoef, int* __restrict__ colrow_sorted,
+                     float* __restrict__ colcoef) {
   int b = blockIdx.y;
   int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= Nc_pad) return;
@@ -592,21 +618,21 @@ desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ r
   int cnt = min(colcnt[(size_t)b * Nc_pad + cell], DESC_MAXP);
   float mv = mv_pad[(size_t)b * Nc_pad + cell], al = alpha[(size_t)b * Nc_pad + cell];
   if (cnt <= 4)
-    pos_coef_cols<4>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colcoef);
+    pos_coef_cols<4>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colrow_sorted, colcoef);
   else
-    pos_coef_cols<DESC_MAXP>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colcoef);
+    pos_coef_cols<DESC_MAXP>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colrow_sorted, colcoef);
 }
 
-extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, int* colrow,
+extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow,
                                  const float* coldot, const uint32_t* bitsR, const float* mv_pad, const float* alpha,
                                  const float* g3, const float* out8, int B, int Nc_pad, float lamda, float mpos,
-                                 float* rowcoef, float* colcoef, void* stream) {
-  SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && alpha && g3 && out8 && rowcoef && colcoef,
-              "ssp_desc_pos_coef: null pointer");
+                                 float* rowcoef, int* colrow_sorted, float* colcoef, void* stream) {
+  SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && alpha && g3 && out8 && rowcoef &&
+                  colrow_sorted && colcoef, "ssp_desc_pos_coef: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Nc_pad > 0 && Nc_pad % DESC_PAD == 0, "ssp_desc_pos_coef: bad sizes");
   dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
   desc_pos_coef_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rowcol, rowdot, colcnt, colrow, coldot, bitsR, mv_pad, alpha,
-                                                               g3, out8, Nc_pad, lamda, mpos, rowcoef, colcoef);
+                                                               g3, out8, Nc_pad, lamda, mpos, rowcoef, colrow_sorted, colcoef);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_coef_kernel");
   return SSP_OK;
 }

@@ -12,12 +12,17 @@
 //   mv_pad [B, Nc_pad] float   mask_valid per warped-image cell, zero padded
 //   bitsR  [B, Nc_pad/32, Nc_pad] u32   word (cw, r): columns 32cw..32cw+31 of row r
 //   bitsC  [B, Nc_pad/32, Nc_pad] u32   word (rw, c): rows 32rw..32rw+31 of column c
+//          element j of a word lives at bit DESC_BITPOS(j): even elements in the low half, odd ones in the high half, so
+//          that the backward's A-operand expansion (bit pair (2i, 2i+1) -> one 32-bit register of two bf16) is one
+//          shift and one and per register
+//   mvbits [B, Nc_pad/32] u32           mask_valid != 0 per cell, same bit order (optional, "fold" mode)
 //   Nc_pad = ceil(Nc / 256) * 256
 #pragma once
 #include "common.cuh"
 
 #define SSP_FAR 1.0e30f
 #define DESC_PAD 256
+#define DESC_BITPOS(j) ((((j) >> 1) & 15) | (((j) & 1) << 4))
 #define DESC_MAXP 16  // positive pairs per row / column kept in the sparse lists (descriptor_dist <= cell);
                       // colcnt[B*Nc_pad] counts entries that did not fit (0 unless the warp shrinks by > 3x)
 

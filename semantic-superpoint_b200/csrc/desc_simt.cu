@@ -73,11 +73,11 @@ desc_dense_fwd_simt_kernel(const float* __restrict__ D, const float* __restrict_
     uint32_t word = 0;
     if (tid < 128) {
 #pragma unroll 8
-      for (int j = 0; j < 32; ++j) word |= (uint32_t)pred[q][wsel * 32 + j] << j;
+      for (int j = 0; j < 32; ++j) word |= (uint32_t)pred[q][wsel * 32 + j] << DESC_BITPOS(j);
       bitsR[((size_t)b * NW + c0 / 32 + wsel) * g.Nc_pad + r0 + q] = word;
     } else {
 #pragma unroll 8
-      for (int j = 0; j < 32; ++j) word |= (uint32_t)pred[wsel * 32 + j][q] << j;
+      for (int j = 0; j < 32; ++j) word |= (uint32_t)pred[wsel * 32 + j][q] << DESC_BITPOS(j);
       bitsC[((size_t)b * NW + r0 / 32 + wsel) * g.Nc_pad + c0 + q] = word;
     }
   }
@@ -108,7 +108,7 @@ extern "C" int ssp_desc_dense_fwd_simt(const float* D, const float* Dw, const fl
 
 // ----------------------------------------------------------------------------------------------
 // indicator GEMM (backward):  out[b, d, r] = rowscale[b,r] * sum_k bit(r, k) * colscale[b,k] * src[b, d, k]
-//   bits[b, kw, r] holds bits k = 32kw..32kw+31 of row r.  CTA = 32 rows r x 256 channels d.
+//   bits[b, kw, r] holds bits k = 32kw..32kw+31 of row r (element j at bit DESC_BITPOS(j)).  CTA = 32 rows r x 256 channels d.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 desc_bits_gemm_simt_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ src,
@@ -144,7 +144,7 @@ desc_bits_gemm_simt_kernel(const uint32_t* __restrict__ bits, const float* __res
       if (word == 0u) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (word & (1u << j)) acc[i] += v[j];
+        if (word & (1u << DESC_BITPOS(j))) acc[i] += v[j];
     }
   }
   __syncthreads();

@@ -189,25 +189,12 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) 
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {  // one whole warp of EACH CTA
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// arrive on the barrier at this offset in the LEADER CTA (callable from either CTA of the pair)
+// arrive on the barrier at this offset in the LEADER CTA (callable from either CTA of the pair).  Default semantics, as
+// cutlass::arch::umma_arrive_2x1SM_sm0: an explicit .release.cluster would put MEMBAR.ALL.GPU + ERRBAR in front of every
+// arrive (measured: it serialised the expander warps behind their own indicator-word prefetches, 2.4 k cycles per stage).
+// What the arrive publishes is tensor memory, which tcgen05.wait::st / tcgen05.fence::before_thread_sync order.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-// wait with cluster-scope acquire (the arrivals may come from the peer CTA)
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait_cluster(bar, parity)) {
-  }
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the bytes are counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, int x, int y) {

@@ -15,14 +15,10 @@ from . import _lib
 from ._lib import call, f32c, ptr, stream_of
 
 _ENGINES = ("bf16x3", "bf16", "fp32")
-# A/B switches (read once): positive pairs of the bf16x3 forward from the packed planes or from NCHW fp32, and the
-# positive-pair partners of the backward epilogues from the packed planes or from NCHW fp32
-POS_FWD_PLANES = os.environ.get("SSP_POS_FWD", "planes") != "nchw"
-POS_EPI_PLANES = os.environ.get("SSP_POS_EPI", "planes") != "fp32"
-# experimental (not yet run on hardware): in the fused step the mask is folded into the row-orientation indicator
-# bits, the dD GEMM takes the unscaled forward planes of Dw and the backward pack disappears.  Valid only for a BINARY
-# mask and g_neg = 0 (structural in LossStepFn); needs SSP_FWD_EPI=2.
-FOLD_ALPHA = os.environ.get("SSP_BG_ALPHA") == "fold" and os.environ.get("SSP_FWD_EPI") == "2"
+# The fused step folds the (binary) cell mask into the indicator words of the tensor-core engines, so the backward needs no
+# pack pass (measured: 0.339 -> 0.330 ms per step).  SSP_BG_ALPHA=pack restores the general path (alpha * Dw packed into
+# its own planes), which is also what the reference-signature `descriptor_loss` always uses (its mask may be anything).
+FOLD_ALPHA = os.environ.get("SSP_BG_ALPHA", "fold") != "pack"
 _ones = {}
 _engine = "bf16x3"
 CHECK_LIST_OVERFLOW = False  # tests turn this on (costs a host sync per call)
@@ -261,54 +257,55 @@ class DescriptorLossFn(torch.autograd.Function):
         if Dch != 256:
             engine = "fp32"  # the tcgen05 kernels are specialised for 256 channels
         need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        split = engine == "bf16x3"
+        # "fold": the (binary) mask is folded into the indicator words, the dD GEMM runs on the forward planes of Dw and
+        # the backward needs no pack pass.  Exact only for a 0/1 mask and g_neg = 0 (LossStepFn guarantees the latter);
+        # a non-binary mask poisons the normaliser with NaN in the geometry kernel (loud, no sync).
+        fold_alpha = bool(fold_alpha and need_grad and engine != "fp32")
 
         wpts = torch.empty((B, Ncp, 2), dtype=torch.float32, device=dev)
         mv_pad = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
+        mvbits = torch.empty((B, Ncp // 32), dtype=torch.int32, device=dev) if fold_alpha else None
         nmv = lib.ssp_desc_geometry_nblocks(B, Nc)
         mv_part = torch.empty((nmv,), dtype=torch.float64, device=dev)
-        call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), st)
+        call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), ptr(mvbits), st)
 
         # sparse positive pairs: exact dots, partial sums, pair lists for the backward
         maxp = lib.ssp_desc_maxp()
-        npos = lib.ssp_desc_pos_planes_nblocks(B, Nc) if (engine == "bf16x3" and POS_FWD_PLANES) else lib.ssp_desc_pos_nblocks(B, Nc)
+        npos = lib.ssp_desc_pos_planes_nblocks(B, Nc) if split else lib.ssp_desc_pos_nblocks(B, Nc)
         pos_part = torch.empty((npos, 4), dtype=torch.float64, device=dev)
         lists_i = torch.empty((3, B, Ncp, maxp), dtype=torch.int32, device=dev)   # rowcol, colrow, (colcnt in [2,:,:,0])
         lists_f = torch.empty((2, B, Ncp, maxp), dtype=torch.float32, device=dev)  # rowdot, coldot
         rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2].view(-1)[: B * Ncp + 1]
         rowdot, coldot = lists_f[0], lists_f[1]
+        overflow = colcnt[B * Ncp:]  # pairs that did not fit a list: desc_finalize turns a non-zero count into NaN
         bitsR = bitsC = None
         if need_grad:
             bitsR = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
             bitsC = torch.empty((B, Ncp // 32, Ncp), dtype=torch.int32, device=dev)
         planes = None
         # every buffer of the forward is allocated before the fork (see _Fork)
-        split = engine == "bf16x3"
         if engine == "fp32":
             nneg = lib.ssp_desc_dense_simt_nblocks(B, Nc)
         else:
             nneg = lib.ssp_desc_dense_tc_nblocks(B, Nc)
-            Ahi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
-            Bhi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
-            Alo = torch.empty_like(Ahi) if split else None
-            Blo = torch.empty_like(Bhi) if split else None
+            # hi (and lo) planes of one tensor in ONE allocation, lo above hi: the backward's TMA box spans both planes
+            PA = torch.empty((2 if split else 1, B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
+            PB = torch.empty_like(PA)
+            Ahi, Alo = PA[0], (PA[1] if split else None)
+            Bhi, Blo = PB[0], (PB[1] if split else None)
         neg_part = torch.empty((nneg, 2), dtype=torch.float64, device=dev)
         out8 = torch.empty((8,), dtype=torch.float32, device=dev)
-        if split and POS_FWD_PLANES:
+        if split:
             # bf16x3: the positive pairs read the packed hi/lo planes (2 x 512 contiguous bytes per cell instead of 256
             # strided channels), so they run right after the pack, in front of the tensor-core kernel
             call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
             call("ssp_desc_pos_fwd_planes", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc, cell,
                  dist, lamda, mpos, mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
-            fold_alpha = bool(fold_alpha and need_grad and POS_EPI_PLANES)
-            if fold_alpha:
-                call("ssp_desc_dense_fwd_tc_ex", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
-                     ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), 1, st)
-            else:
-                call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
-                     ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+            call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), ptr(mvbits), B, Hc, Wc, mneg,
+                 ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             planes = (Ahi, Alo, Bhi, Blo)
         else:
-            fold_alpha = False
             # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
             with _Fork(dev) as fork:
                 call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos,
@@ -317,15 +314,16 @@ class DescriptorLossFn(torch.autograd.Function):
                 call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
                      ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             else:
-                call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
-                call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), B, Hc, Wc, mneg,
+                call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), None, ptr(Bhi), None, st)
+                call("ssp_desc_dense_fwd_tc", ptr(Ahi), None, ptr(Bhi), None, ptr(mv_pad), ptr(mvbits), B, Hc, Wc, mneg,
                      ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
-                planes = (Ahi, Alo, Bhi, Blo)
+                planes = (Ahi, None, Bhi, None)
             fork.join()
 
-        if CHECK_LIST_OVERFLOW and int(colcnt[B * Ncp]) != 0:  # host sync: debugging / tests only
-            raise RuntimeError("descriptor_loss: %d positive pairs overflowed the per-column lists" % int(colcnt[B * Ncp]))
-        call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(out8), st)
+        call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(overflow),
+             ptr(out8), st)
+        if CHECK_LIST_OVERFLOW and int(overflow[0]) != 0:  # host sync: debugging / tests only (the NaN above is the product signal)
+            raise RuntimeError("descriptor_loss: %d positive pairs overflowed the sparse lists" % int(overflow[0]))
         if dist_group is not None:
             from .dist import globalize_descriptor
             globalize_descriptor(out8, B, Hc, Wc, dist_group)
@@ -362,57 +360,56 @@ class DescriptorLossFn(torch.autograd.Function):
         rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2]
         rowdot, coldot = lists_f[0], lists_f[1]
         coefs = torch.empty((2,) + tuple(rowdot.shape), dtype=torch.float32, device=dev)
+        colrow_sorted = torch.empty_like(colrow)  # the saved lists stay as the forward wrote them (retain_graph safe)
         dD = torch.empty_like(Dc)
         dDw = torch.empty_like(Dwc)
         tc_engine = engine != "fp32"
+        fold = tc_engine and getattr(ctx, "fold_alpha", False)
         if tc_engine:
             if split:
                 Ahi, Alo, Bhi, Blo = saved[7:11]
             else:
                 (Ahi, Bhi), Alo, Blo = saved[7:9], None, None
-            Shi = torch.empty((B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
-            Slo = torch.empty_like(Shi) if split else None
+            if not fold:
+                PS = torch.empty((2 if split else 1, B, Ncp, Dch), dtype=torch.bfloat16, device=dev)
+                Shi, Slo = PS[0], (PS[1] if split else None)
         # dD [b,:,r] = sum_c I[r,c] alpha[c] Dw[b,:,c] + sum_n rowcoef[r,n] Dw[b,:,rowcol[r,n]]
         # dDw[b,:,c] = alpha[c] sum_r I[r,c] D[b,:,r]  + sum_n colcoef[c,n] D [b,:,colrow[c,n]]
-        # tensor-core engines: the positive pairs are applied inside the GEMM epilogues (dedicated epilogue warps hide
-        # the gathers behind the next item's main loop); fp32 engine: one streaming apply kernel after the GEMMs.
-        # stream plan:  [pos_coef]  ||  [pack(alpha * Dw)]  ->  GEMM dD  ->  GEMM dDw
+        # tensor-core engines: both GEMMs run in ONE persistent launch, the positive pairs are applied inside the GEMM
+        # epilogues (dedicated epilogue warps hide the gathers behind the next item's main loop);
+        # fp32 engine: one streaming apply kernel after the GEMMs.
+        # stream plan:  [pos_coef]  ||  [pack(alpha * Dw), unless folded]  ->  GEMM pair
         with _Fork(dev) as f1:
             call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
-                 ptr(mv_pad), ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(coefs[1]), stream_of(Dc))
-        if tc_engine and getattr(ctx, "fold_alpha", False):
-            # bitsR already excludes the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
+                 ptr(mv_pad), ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
+                 ptr(coefs[1]), stream_of(Dc))
+        if fold:
+            # bitsR / bitsC already exclude the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
             key = (dev.index, B, Ncp)
             if key not in _ones:
                 _ones[key] = torch.ones((B, Ncp), dtype=torch.float32, device=dev)
             srow = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
             call("ssp_desc_alpha", ptr(_ones[key]), ptr(g3), ptr(out8), B, Ncp, ptr(srow), st)
             f1.join()
-            call("ssp_desc_bits_gemm_tc_planes", ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]),
-                 ptr(Bhi), ptr(Blo), B, Nc, ptr(dD), st)
-            call("ssp_desc_bits_gemm_tc_planes", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]),
-                 ptr(Ahi), ptr(Alo), B, Nc, ptr(dDw), st)
+            call("ssp_desc_bits_gemm_tc_pair",
+                 ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]), ptr(Bhi), ptr(Blo), ptr(dD),
+                 ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow_sorted), ptr(coefs[1]), ptr(Ahi), ptr(Alo), ptr(dDw),
+                 B, Nc, st)
         elif tc_engine:
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
             f1.join()
-            if POS_EPI_PLANES:
-                # positive-pair partners from the packed planes of the forward (Dw for dD, D for dDw)
-                call("ssp_desc_bits_gemm_tc_planes", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]),
-                     ptr(Bhi), ptr(Blo), B, Nc, ptr(dD), st)
-                call("ssp_desc_bits_gemm_tc_planes", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]),
-                     ptr(Ahi), ptr(Alo), B, Nc, ptr(dDw), st)
-            else:
-                call("ssp_desc_bits_gemm_tc", ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Dwc), B, Nc,
-                     ptr(dD), st)
-                call("ssp_desc_bits_gemm_tc", ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow), ptr(coefs[1]), ptr(Dc), B,
-                     Nc, ptr(dDw), st)
+            # positive-pair partners from the packed planes of the forward (Dw for dD, D for dDw)
+            call("ssp_desc_bits_gemm_tc_pair",
+                 ptr(bitsR), ptr(Shi), ptr(Slo), None, ptr(rowcol), ptr(coefs[0]), ptr(Bhi), ptr(Blo), ptr(dD),
+                 ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow_sorted), ptr(coefs[1]), ptr(Ahi), ptr(Alo), ptr(dDw),
+                 B, Nc, st)
         else:
             call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
             call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
             f1.join()
-            call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 0,
+            call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow_sorted), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 0,
                  ptr(dD), ptr(dDw), st)
-        return dD, dDw, None, None, None, None, None, None, None, None
+        return dD, dDw, None, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
