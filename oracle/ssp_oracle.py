@@ -60,6 +60,54 @@ def keep_in_bounds_f64(points, shape):
     return (points[:, 0] >= 0) & (points[:, 0] < shape[1]) & (points[:, 1] >= 0) & (points[:, 1] < shape[0])
 
 
+def compute_repeatability(prob, warped_prob, H, shape, keep_k_points=300, distance_thresh=3, warp_and_keep=None):
+    """evaluations/detector_evaluation.py:152-283 restated.  prob / warped_prob [K,3] (x, y, confidence) in the two
+    images, H the pixel homography, shape = (H, W).  warp_and_keep(points[K,2], Hmat, shape) -> (warped [K,2], keep [K])
+    defaults to the float64 oracle (warp_keypoints_f64 + keep_in_bounds_f64); tests plug the CUDA path in here.
+    Returns (repeatability, localization_err)."""
+    if warp_and_keep is None:
+        def warp_and_keep(p, Hm, shp):
+            w = warp_keypoints_f64(p, Hm)
+            return w, keep_in_bounds_f64(w, shp)
+    prob = np.array(prob, dtype=np.float64)
+    warped_prob = np.array(warped_prob, dtype=np.float64)
+    # keep_true_keypoints: detections of the warped image whose back-warp lies inside the image (:172-189)
+    _, keep = warp_and_keep(warped_prob[:, :2], np.linalg.inv(H), shape)
+    wk = warped_prob[keep]
+    # true warps of the detections of the first image, filtered to the image (:232-238)
+    tw, keep = warp_and_keep(prob[:, :2], H, shape)
+    twk = np.concatenate([tw, prob[:, 2:]], axis=1)[keep]
+
+    def select_k_best(points, k):  # :191-201
+        s = points[points[:, 2].argsort(), :2]
+        return s[-min(k, points.shape[0]):, :]
+
+    wk, twk = select_k_best(wk, keep_k_points), select_k_best(twk, keep_k_points)
+    N1, N2 = twk.shape[0], wk.shape[0]
+    norm = np.linalg.norm(twk[:, None, :] - wk[None, :, :], axis=2)
+    count1 = count2 = 0
+    e1 = e2 = None
+    if N2 != 0:
+        m1 = norm.min(axis=1)
+        count1 = int((m1 <= distance_thresh).sum())
+        e1 = m1[m1 <= distance_thresh]
+    if N1 != 0:
+        m2 = norm.min(axis=0)
+        count2 = int((m2 <= distance_thresh).sum())
+        e2 = m2[m2 <= distance_thresh]
+    rep = (count1 + count2) / (N1 + N2) if N1 + N2 > 0 else 0
+    loc = -1
+    if count1 + count2 > 0:
+        loc = 0
+        if e1 is not None:
+            loc += e1.sum() / (count1 + count2)
+        if e2 is not None:
+            loc += e2.sum() / (count1 + count2)
+    else:
+        rep = 0
+    return rep, loc
+
+
 def _unnormalize(coord, size):
     # ATen grid_sampler_unnormalize, align_corners=True: ((coord + 1) / 2) * (size - 1)
     return ((coord + f32(1)) / f32(2)) * f32(size - 1)
@@ -106,6 +154,20 @@ def inv_warp_image_batch(img, mat_homo_inv, mode="bilinear"):
     pts = np.stack([gx.reshape(-1), gy.reshape(-1)], axis=1)
     src = warp_points(pts, Hm).reshape(B, H, W, 2)
     return grid_sample(img, src, mode)
+
+
+def sample_coords_f64(image_shape, mat_homo_inv):
+    """Source pixel coordinates (ix, iy) [B,H,W] of inv_warp_image_batch in float64: used by tests to show that a
+    nearest-mode pixel that differs between two fp32 implementations sits on a half-pixel rounding tie."""
+    H, W = int(image_shape[0]), int(image_shape[1])
+    Hm = np.asarray(mat_homo_inv, dtype=np.float64).reshape(-1, 3, 3)
+    gx, gy = np.meshgrid(linspace_grid(W).astype(np.float64), linspace_grid(H).astype(np.float64))
+    p = np.stack([gx.reshape(-1), gy.reshape(-1), np.ones(H * W)], axis=0)  # [3, HW]
+    w = Hm @ p  # [B,3,HW]
+    nx, ny = w[:, 0] / w[:, 2], w[:, 1] / w[:, 2]
+    ix = (nx + 1.0) / 2.0 * (W - 1)
+    iy = (ny + 1.0) / 2.0 * (H - 1)
+    return ix.reshape(-1, H, W), iy.reshape(-1, H, W)
 
 
 def ellipse_kernel(radius):
@@ -407,6 +469,36 @@ def descriptor_boundary_slack(descriptors, descriptors_warped, homographies, mas
             dot = float(D[b].reshape(Dch, Nc)[:, r].astype(np.float64) @ Dw[b].reshape(Dch, Nc)[:, c].astype(np.float64))
             slack += lamda_d * max(1.0 - dot, 0.0) + max(dot - 0.2, 0.0)
     return slack / norm
+
+
+def descriptor_unstable_cells(descriptors, descriptors_warped, homographies, cell_size=8, descriptor_dist=4, eps_dot=1e-5,
+                              eps_px=1e-3, chunk=1024):
+    """Rows / columns whose GRADIENT is not a continuous function of the inputs at this point, so that two correct
+    implementations may differ there by a whole descriptor: cells touching a pair whose dot product lies within eps_dot of a
+    hinge margin (0.2 / 1.0) or whose centre distance lies within eps_px of descriptor_dist.  Returns two bool [B,Nc]
+    arrays (rows = cells of `descriptors`, cols = cells of `descriptors_warped`).  Chunked float64, any size."""
+    D = np.asarray(descriptors, dtype=np.float64)
+    Dw = np.asarray(descriptors_warped, dtype=np.float64)
+    B, Dch, Hc, Wc = D.shape
+    Nc = Hc * Wc
+    _, w = descriptor_pair_mask(homographies, Hc, Wc, cell_size, descriptor_dist)
+    kk, ll = np.meshgrid(np.arange(Hc), np.arange(Wc), indexing="ij")
+    cy = (kk.reshape(-1) * cell_size + cell_size // 2).astype(np.float64)
+    cx = (ll.reshape(-1) * cell_size + cell_size // 2).astype(np.float64)
+    rows = np.zeros((B, Nc), bool)
+    cols = np.zeros((B, Nc), bool)
+    for b in range(B):
+        A = D[b].reshape(Dch, Nc).T
+        Bm = Dw[b].reshape(Dch, Nc)
+        for r0 in range(0, Nc, chunk):
+            r1 = min(Nc, r0 + chunk)
+            dot = A[r0:r1] @ Bm
+            d = np.sqrt((cy[None, :] - w[b, r0:r1, 1:2].astype(np.float64)) ** 2 + (cx[None, :] - w[b, r0:r1, 0:1].astype(np.float64)) ** 2)
+            pos = d <= descriptor_dist + eps_px
+            near = (np.abs(d - descriptor_dist) < eps_px) | (~pos & (np.abs(dot - 0.2) < eps_dot)) | (pos & ((np.abs(dot - 1.0) < eps_dot) | (np.abs(dot - 0.2) < eps_dot)))
+            rows[b, r0:r1] |= near.any(axis=1)
+            cols[b] |= near.any(axis=0)
+    return rows, cols
 
 
 def descriptor_dots(descriptors, descriptors_warped):

@@ -23,12 +23,14 @@
 //
 // Backward kernel = indicator GEMM  out[b, d, r] = rowscale[r] * sum_k bit(r,k) * Bp[b, k, d] for up to two independent
 // jobs (dD and dDw) in one launch, work item = (pair, job, 256-row tile, channel half):
-//   warps 0-3   expand 64 indicator bits per row into bf16 {0, 2} (one shift + one and per register; the bit order of
-//               the words is chosen for that, DESC_BITPOS) and tcgen05.st them as the A operand into TMEM
-//   warps 4-11  epilogue of the previous item (double-buffered 128-column accumulators), incl. the sparse
+//   warps 0-7   expand 64 indicator bits per row into bf16 {0, 2} (one shift + one and per register; the bit order of
+//               the words is chosen for that, DESC_BITPOS) and tcgen05.st them as the A operand into TMEM; warps 0-3 take
+//               the even stages, warps 4-7 the odd ones (a single set of four warps was the per-stage critical path:
+//               ~130 dependent-issue instructions + the TMEM store round trip per 512 cycles of MMA work)
+//   warps 8-15  epilogue of the previous item (double-buffered 128-column accumulators), incl. the sparse
 //               positive-pair terms
-//   warp 12     TMA producer (both CTAs): ONE 3-D box per stage = [planes x 64 cells x 64 channels] of this CTA's half
-//   warp 13     MMA issuer (leader), M=256 N=128 K=16, A from TMEM
+//   warp 16     TMA producer (both CTAs): ONE 3-D box per stage = [planes x 64 cells x 64 channels] of this CTA's half
+//   warp 17     MMA issuer (leader), M=256 N=128 K=16, A from TMEM
 #include "desc_common.cuh"
 #include "tc_ptx.cuh"
 #include <algorithm>
@@ -173,8 +175,12 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   if (warp == 8) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow keeps the TMA / MMA operands in uniform registers; a branch on
+    // lane 0 around the loop costs an ELECT / R2UR / BRA.U.ANY waterfall per instruction), one elected lane issues.
+    {
       TR_DECL(1);
+      TR_ONLY(lane == 0);
+      const bool el = tc::elect_one();
       int prev_key = -1, stage_it = 0, nkeys = 0;
       for (int it = it0; it < it1; ++it) {
         const int key = it / NT, nt = it - key * NT;  // key = b * MP + mp
@@ -190,10 +196,12 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             TR(10);
             if (nkeys > 0) tc::mbar_wait(a_empty + kc, (uint32_t)((nkeys - 1) & 1));
             TR(11);
-            if (leader) tc::mbar_expect_tx(a_full + kc, 2 * P * CHUNK_BYTES);
-            for (int p = 0; p < P; ++p)
-              tc::tma_load_2d_2sm(p == 0 ? &tmA_hi : &tmA_lo, a_full + kc, sA + (p * NKC + kc) * CHUNK_BYTES, kc * KC,
-                                  row_base + (2 * mp + (int)cta_rank) * BM);
+            if (el) {
+              if (leader) tc::mbar_expect_tx(a_full + kc, 2 * P * CHUNK_BYTES);
+              for (int p = 0; p < P; ++p)
+                tc::tma_load_2d_2sm(p == 0 ? &tmA_hi : &tmA_lo, a_full + kc, sA + (p * NKC + kc) * CHUNK_BYTES, kc * KC,
+                                    row_base + (2 * mp + (int)cta_rank) * BM);
+            }
           }
           for (int p = 0; p < P; ++p, ++stage_it) {
             const int s = stage_it % NSTAGE;
@@ -201,9 +209,11 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             TR(12);
             tc::mbar_wait(b_empty + s, ph ^ 1);
             TR(13);
-            if (leader) tc::mbar_expect_tx(b_full + s, 2 * half * KC * 2);
-            const CUtensorMap* m = last ? (p == 0 ? &tmBl_hi : &tmBl_lo) : (p == 0 ? &tmB_hi : &tmB_lo);
-            tc::tma_load_2d_2sm(m, b_full + s, sB + s * CHUNK_BYTES, kc * KC, row_base + nt * BN + (int)cta_rank * half);
+            if (el) {
+              if (leader) tc::mbar_expect_tx(b_full + s, 2 * half * KC * 2);
+              const CUtensorMap* m = last ? (p == 0 ? &tmBl_hi : &tmBl_lo) : (p == 0 ? &tmB_hi : &tmB_lo);
+              tc::tma_load_2d_2sm(m, b_full + s, sB + s * CHUNK_BYTES, kc * KC, row_base + nt * BN + (int)cta_rank * half);
+            }
           }
         }
         if (newkey) { prev_key = key; ++nkeys; }
@@ -211,9 +221,12 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     }
     __syncwarp();
   } else if (warp == 9) {
-    // ------------------------------ MMA issuer (leader CTA) ------------------------------
-    if (lane == 0 && leader) {
+    // ------------------------------ MMA issuer (leader CTA; whole warp loops, one elected lane issues) ------------------------------
+    if (leader) {
       TR_DECL(0);
+      TR_ONLY(lane == 0);
+      const bool el = tc::elect_one();
+      if (tmem_base != 0u) __trap();  // all 512 columns were allocated: the base is column 0, used as a literal below
       const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
       int prev_key = -1, stage_it = 0, tcount = 0, nkeys = 0;
       for (int it = it0; it < it1; ++it, ++tcount) {
@@ -228,7 +241,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         tc::mbar_wait(t_empty + as, aph ^ 1);
         TR(3);
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = as * BN;
         uint32_t first = 1;
         for (int kc = 0; kc < NKC; ++kc) {
           if (newkey) {
@@ -248,15 +261,16 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             const uint64_t db = tc::smem_desc_sw128(sB_u + s * CHUNK_BYTES, 16, 1024);
             for (int pa = 0; pa < n_a; ++pa) {
               const uint64_t da = tc::smem_desc_sw128(sA_u + (pa * NKC + kc) * CHUNK_BYTES, 16, 1024);
-              tc::mma2_ss_x4(d_tmem, da, db, idesc, first ? 0u : 1u);  // 4 x (M256 N K16) over this 64-channel chunk
+              if (el) tc::mma2_ss_x4(d_tmem, da, db, idesc, first ? 0u : 1u);  // 4 x (M256 N K16) over this 64-channel chunk
               first = 0;
             }
-            tc::mma2_commit_mc(b_empty + s, (uint16_t)0x3);  // both producers: the pair is done with slot s
+            if (el) tc::mma2_commit_mc(b_empty + s, (uint16_t)0x3);  // both producers: the pair is done with slot s
             TR(6);
           }
-          if (last_of_key) tc::mma2_commit_mc(a_empty + kc, (uint16_t)0x3);  // A chunk kc may be replaced in both CTAs
+          if (last_of_key && el) tc::mma2_commit_mc(a_empty + kc, (uint16_t)0x3);  // A chunk kc may be replaced in both CTAs
         }
-        tc::mma2_commit_mc(t_full + as, (uint16_t)0x3);  // accumulator tile complete (both CTAs' epilogues)
+        if (el) tc::mma2_commit_mc(t_full + as, (uint16_t)0x3);  // accumulator tile complete (both CTAs' epilogues)
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -400,7 +414,8 @@ desc_bits_transpose_kernel(const uint32_t* __restrict__ bitsR, uint32_t* __restr
 constexpr int KT = 64;                       // cells (GEMM K) per stage
 constexpr int BG_PLANE_BYTES = KT * 128;     // one [64 cells x 64 channels] box = 8 KB (this CTA's half of the 128 channels)
 constexpr int BG_N = 128;                    // channels per work item (half of the descriptor)
-constexpr int BG_THREADS = 448;              // warps 0-3 expanders, 4-11 epilogue, 12 TMA producer, 13 MMA issuer
+constexpr int BG_THREADS = 576;              // warps 0-7 expanders (two sets), 8-15 epilogue, 16 TMA producer, 17 MMA issuer
+constexpr int BG_W_EPI = 8, BG_W_TMA = 16, BG_W_MMA = 17;
 constexpr int BG_NS = 8;                     // ring depth: TMEM holds 2 x 128 accumulator columns + 8 x 32 columns of A
 
 template <int P> struct BgCfg {
@@ -425,7 +440,7 @@ struct BgJob {
 template <int P>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, BgJob job0,
-                         BgJob job1, int njobs, int B, int Nc, int Nc_pad) {
+                         BgJob job1, int njobs, int B, int Nc, int Nc_pad, int dbg) {
   using Cfg = BgCfg<P>;
   constexpr int NS = BG_NS;
   static_assert(256 + 32 * NS <= 512, "TMEM A ring does not fit");
@@ -457,11 +472,11 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
     b = t / njobs;
   };
 
-  if (warp == 12 && lane == 0) {
+  if (warp == BG_W_TMA && lane == 0) {
     tc::prefetch_tmap(&tm0);
     if (njobs > 1) tc::prefetch_tmap(&tm1);
   }
-  if (warp == 13) {
+  if (warp == BG_W_MMA) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(a_full + s, 8); tc::mbar_init(s_free + s, 1); }
       for (int s = 0; s < 2; ++s) { tc::mbar_init(d_full + s, 1); tc::mbar_init(d_empty + s, 16); }
@@ -475,10 +490,12 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 12) {
-    // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
+  if (warp == BG_W_TMA) {
+    // ------------------------------ TMA producer (both CTAs; whole warp loops, one elected lane issues) ------------------------------
+    {
       TR_DECL(1);
+      TR_ONLY(lane == 0);
+      const bool el = tc::elect_one();
       int st_it = 0;
       for (int it = cid; it < T; it += ncluster) {
         int b, jb, mp, dh;
@@ -490,17 +507,22 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
           TR(12);
           tc::mbar_wait(s_free + s, ph ^ 1);
           TR(13);
-          if (leader) tc::mbar_expect_tx(b_full + s, 2 * Cfg::STAGE_BYTES);
-          // one box: [P planes x 64 cells x my 64 of the item's 128 channels]
-          tc::tma_load_3d_2sm(m, b_full + s, smem + s * Cfg::STAGE_BYTES, dh * BG_N + (int)cta_rank * 64, b * Nc_pad + kc * KT, 0);
+          if (el) {
+            if (leader) tc::mbar_expect_tx(b_full + s, 2 * Cfg::STAGE_BYTES);
+            // one box: [P planes x 64 cells x my 64 of the item's 128 channels]
+            tc::tma_load_3d_2sm(m, b_full + s, smem + s * Cfg::STAGE_BYTES, dh * BG_N + (int)cta_rank * 64, b * Nc_pad + kc * KT, 0);
+          }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 13) {
-    // ------------------------------ MMA issuer (leader CTA) ------------------------------
-    if (lane == 0 && leader) {
+  } else if (warp == BG_W_MMA) {
+    // ------------------------------ MMA issuer (leader CTA; whole warp loops, one elected lane issues) ------------------------------
+    if (leader) {
       TR_DECL(0);
+      TR_ONLY(lane == 0);
+      const bool el = tc::elect_one();
+      if (tmem_base != 0u) __trap();  // all 512 columns were allocated: the base is column 0, used as a literal below
       constexpr uint32_t idesc = tc::idesc_bf16_f32(2 * BM, BG_N, 0, 1);  // A K-major (TMEM), B MN-major
       const uint32_t smem_u = tc::smem_u32(smem);
       int st_it = 0, tcount = 0;
@@ -511,47 +533,45 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
         tc::mbar_wait(d_empty + as, aph ^ 1);
         TR(3);
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * BG_N;
+        const uint32_t d_tmem = as * BG_N;
         uint32_t first = 1;
         for (int kc = 0; kc < NK; ++kc, ++st_it) {
           const int s = st_it % NS;
           const uint32_t ph = (st_it / NS) & 1;
+          // dbg (SSP_BG_DEBUG, profiling only -- results are garbage): bit 0 skips the wait for the A stage, bit 1 the wait
+          // for the B stage, so the issue rate of the MMA thread can be measured with one of its feeds taken away
           TR(4);
-          tc::mbar_wait(b_full + s, ph);
+          if (!(dbg & 2)) tc::mbar_wait(b_full + s, ph);
           TR(5);
-          tc::mbar_wait(a_full + s, ph);
+          if (!(dbg & 1)) tc::mbar_wait(a_full + s, ph);
           TR(7);
           tc::fence_after_sync();
           for (int p = 0; p < P; ++p) {
             // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B per step); each CTA supplies one 64-channel
             // swizzle atom of the 128 channels; A advances 8 TMEM columns per step
             const uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * BG_PLANE_BYTES, BG_PLANE_BYTES, 1024);
-            tc::mma2_ts_x4(d_tmem, tmem_base + A_COL0 + s * 32, db, idesc, first ? 0u : 1u);
+            if (el) tc::mma2_ts_x4(d_tmem, A_COL0 + s * 32, db, idesc, first ? 0u : 1u);
             first = 0;
           }
-          tc::mma2_commit_mc(s_free + s, (uint16_t)0x3);
+          if (el) tc::mma2_commit_mc(s_free + s, (uint16_t)0x3);
           TR(6);
         }
-        tc::mma2_commit_mc(d_full + as, (uint16_t)0x3);
+        if (el) tc::mma2_commit_mc(d_full + as, (uint16_t)0x3);
+        __syncwarp();
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
+  } else if (warp < BG_W_EPI) {
     // ------------------------------ expanders (both CTAs): indicator bits -> bf16 A operand in TMEM ------------------------------
-    const int q = warp;
+    const int q = warp & 3, set = warp >> 2;  // TMEM lane quadrant; set 0 expands the even stages, set 1 the odd ones
     TR_DECL(2);
     TR_ONLY(warp == 0 && lane == 0);
-    int st_it = 0;
     // one ring stage: the 64 indicator bits (w0: cells 0..31, w1: cells 32..63 of the stage) of this row become 32 TMEM
     // columns of bf16 pairs.  Bit i of a word is cell 2i, bit 16+i is cell 2i+1 (DESC_BITPOS), so column i of a word is
     // ONE shift and ONE and: (w << (14 - i)) & 0x40004000 -- bf16 0x4000 = 2.0; the epilogue multiplies by 0.5.
-    auto expand_stage = [&](uint32_t w0, uint32_t w1) {
+    auto expand_stage = [&](int st_it, uint32_t w0, uint32_t w1) {
       const int s = st_it % NS;
       const uint32_t ph = (st_it / NS) & 1;
-      TR(20);
-      tc::mbar_wait(s_free + s, ph ^ 1);
-      TR(21);
-      tc::fence_after_sync();
       uint32_t r[32];
 #pragma unroll
       for (int i = 0; i < 15; ++i) {
@@ -560,54 +580,59 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
       }
       r[15] = (w0 >> 1) & 0x40004000u;
       r[31] = (w1 >> 1) & 0x40004000u;
-      TR(22);
+      TR(20);
+      tc::mbar_wait(s_free + s, ph ^ 1);
+      TR(21);
+      tc::fence_after_sync();
       tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_leader(a_full + s);
       TR(23);
-      ++st_it;
     };
-    // the indicator words run PF stages ahead of their use over the FLAT stage sequence of all items of this cluster, so
-    // neither the L2 latency inside an item nor the start of a new item is exposed
-    constexpr int PF = 8;
+    // the indicator words run PF of this set's stages ahead of their use over the FLAT stage sequence of all items of this
+    // cluster, so neither the L2 latency inside an item nor the start of a new item is exposed
+    constexpr int PF = 6;
     uint32_t wq0[PF], wq1[PF];
-    int itB = cid, kcB = 0;
+    int itB = cid, kcB = set;  // fetch cursor (stage `set` of the first item; NK >= 2 always holds for Nc > 64)
     const uint32_t* pB = nullptr;
+    bool newitem = true;
     auto fetch = [&](uint32_t& a, uint32_t& c) {
       if (itB < T) {
-        if (kcB == 0) {
+        if (newitem) {
           int b, jb, mp, dh;
           decode(itB, b, jb, mp, dh);
           const int row = (2 * mp + (int)cta_rank) * BM + q * 32 + lane;
           pB = (jb ? job1.bits : job0.bits) + (size_t)b * NW * Nc_pad + row;
+          newitem = false;
         }
         a = __ldg(pB + (size_t)(2 * kcB) * Nc_pad);
         c = __ldg(pB + (size_t)(2 * kcB + 1) * Nc_pad);
-        if (++kcB == NK) { kcB = 0; itB += ncluster; }
+        kcB += 2;
+        if (kcB >= NK) { kcB -= NK; itB += ncluster; newitem = true; }
       }
     };
 #pragma unroll
     for (int u = 0; u < PF; ++u) { wq0[u] = 0u; wq1[u] = 0u; fetch(wq0[u], wq1[u]); }
     const int nitems = cid < T ? (T - cid + ncluster - 1) / ncluster : 0;
-    const int total = nitems * NK;
-    for (int g0 = 0; g0 < total; g0 += PF) {
+    const int total = nitems * NK;  // global stage count of this cluster; this set owns g = set, set + 2, ...
+    for (int g0 = set; g0 < total; g0 += 2 * PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
-        if (g0 + u < total) {
-          expand_stage(wq0[u], wq1[u]);
+        if (g0 + 2 * u < total) {
+          expand_stage(g0 + 2 * u, wq0[u], wq1[u]);
           fetch(wq0[u], wq1[u]);
         }
       }
     }
   } else {
-    // ------------------------------ epilogue warps 4..11 (both CTAs) ------------------------------
+    // ------------------------------ epilogue warps 8..15 (both CTAs) ------------------------------
     // two warps per TMEM lane quadrant, each draining two of the four 32-column chunks of the accumulator
-    const int q = warp & 3, chalf = (warp - 4) >> 2;
+    const int q = warp & 3, chalf = (warp - BG_W_EPI) >> 2;
     int tcount = 0;
     TR_DECL(3);
-    TR_ONLY(warp == 4 && lane == 0);
+    TR_ONLY(warp == BG_W_EPI && lane == 0);
     for (int it = cid; it < T; it += ncluster, ++tcount) {
       int b, jb, mp, dh;
       decode(it, b, jb, mp, dh);
@@ -684,7 +709,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
 
   tc::fence_before_sync();
   tc::cluster_sync_all();
-  if (warp == 13) {
+  if (warp == BG_W_MMA) {
     tc::fence_after_sync();
     tc::tmem_dealloc2(tmem_base, 512);
   }
@@ -883,14 +908,15 @@ static int bits_gemm_tc_launch(const BgHostJob* jobs, int njobs, int B, int Nc, 
   int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
   int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
+  static const int dbg = [] { const char* e = getenv("SSP_BG_DEBUG"); return e ? atoi(e) : 0; }();
   if (jobs[0].Blo) {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
     if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, maps[0], maps[1], dj[0], dj[1], njobs,
-                              B, Nc, Nc_pad))) return rc;
+                              B, Nc, Nc_pad, dbg))) return rc;
   } else {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
     if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, maps[0], maps[1], dj[0], dj[1], njobs,
-                              B, Nc, Nc_pad))) return rc;
+                              B, Nc, Nc_pad, dbg))) return rc;
   }
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;

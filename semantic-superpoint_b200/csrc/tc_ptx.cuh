@@ -59,6 +59,19 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint64_t* b
       : "memory");
 }
 
+// one lane of the (converged) warp: used to predicate single-thread instructions inside warp-uniform loops, so that their
+// operands stay in uniform registers (a branch on lane == 0 around the whole loop makes ptxas emit an ELECT / R2UR /
+// BRA.U.ANY waterfall per tcgen05.mma: ~100 cycles of issue per instruction, measured)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------- clusters ----------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -145,7 +145,32 @@ def gen_warp_labels():
     save("warp_labels", pts=pts, H=Hs, **out)
 
 
+def gen_eval_keypoints():
+    """SURVEY 8a-a10, evaluation side: evaluations/detector_evaluation.py warp_keypoints (:139-150) and the repeatability
+    masks keep_true_keypoints / filter_keypoints (nested in compute_repeatability, :152-191), pinned through the module
+    function and through compute_repeatability's own return values on synthetic detections."""
+    import evaluations.detector_evaluation as DE
+    Hh, W = 480, 640
+    K = 1000
+    kp = np.stack([synth.uniform((K,), 141) * (W + 40) - 20, synth.uniform((K,), 142) * (Hh + 40) - 20,
+                   synth.uniform((K,), 143)], axis=1).astype(np.float64)
+    Hpix = np.array([[0.92, 0.06, 14.0], [-0.05, 1.07, -9.0], [1.1e-4, -1.7e-4, 1.0]])
+    warped = DE.warp_keypoints(kp[:, :2], Hpix)
+    # detections in the warped image: the true warps of 700 of the points plus noise, and 300 unrelated points
+    wk = np.concatenate([warped[:700] + (synth.uniform((700, 2), 144) - 0.5) * 4.0,
+                         np.stack([synth.uniform((300,), 145) * W, synth.uniform((300,), 146) * Hh], 1)], axis=0)
+    wk = np.concatenate([wk, synth.uniform((K, 1), 147)], axis=1).astype(np.float64)
+    data = {"image": np.zeros((Hh, W)), "homography": Hpix, "prob": kp.copy(), "warped_prob": wk.copy()}
+    rep, loc = DE.compute_repeatability(data, keep_k_points=300, distance_thresh=3)
+    data = {"image": np.zeros((Hh, W)), "homography": Hpix, "prob": kp.copy(), "warped_prob": wk.copy()}
+    rep1k, loc1k = DE.compute_repeatability(data, keep_k_points=1000, distance_thresh=3)
+    save("eval_keypoints", kp=kp, H=Hpix, warped=warped, warped_prob=wk, shape=np.array([Hh, W]),
+         repeatability=np.float64(rep), loc_err=np.float64(loc), repeatability_1000=np.float64(rep1k), loc_err_1000=np.float64(loc1k))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "eval_keypoints":
+        return gen_eval_keypoints()
     if len(sys.argv) > 1 and sys.argv[1] == "warp_labels":
         return gen_warp_labels()
     if len(sys.argv) > 1 and sys.argv[1] == "semantic":

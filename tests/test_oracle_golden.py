@@ -180,3 +180,15 @@ def test_warp_labels_oracle(golden):
         close(o["res"], g["res_%d" % i], atol=2e-5)
         close(o["labels_bi"], g["labels_bi_%d" % i], atol=2e-5)
         assert o["labels"].sum() <= o["warped_pnts"].shape[0]  # collisions keep one label per pixel
+
+
+def test_eval_keypoints_and_repeatability(golden):
+    """8a-a10 evaluation side: detector_evaluation.warp_keypoints and the repeatability masks, as run by the reference's own
+    compute_repeatability on synthetic detections (fixture generated from the live module)."""
+    g = golden("eval_keypoints")
+    shape = tuple(int(v) for v in g["shape"])
+    np.testing.assert_array_equal(O.warp_keypoints_f64(g["kp"][:, :2], g["H"]), g["warped"])
+    rep, loc = O.compute_repeatability(g["kp"], g["warped_prob"], g["H"], shape, keep_k_points=300)
+    assert rep == float(g["repeatability"]) and loc == float(g["loc_err"])
+    rep, loc = O.compute_repeatability(g["kp"], g["warped_prob"], g["H"], shape, keep_k_points=1000)
+    assert rep == float(g["repeatability_1000"]) and loc == float(g["loc_err_1000"])
