@@ -135,7 +135,9 @@ int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const void* Bhi, con
 /* overflow (optional) = &colcnt[B*Nc_pad], the counter of positive pairs that did not fit the sparse lists: non-zero
  * makes loss / pos_sum NaN (loud without a host sync) */
 int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg, const double* mv_part,
-                      int nmv, int B, int Hc, int Wc, const int* overflow, float* out8, void* stream);
+                      int nmv, int B, int Hc, int Wc, const int* overflow, float* out8,
+                      const float* det0 /*or NULL*/, const float* det1, float lambda_loss, float* total /*or NULL: fused
+                      loss step, total = det0.loss + det1.loss + lambda_loss * loss_desc*/, void* stream);
 int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,
                        void* stream);
 int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)*/, const float* out8, int B,
@@ -221,6 +223,7 @@ int ssp_xchg_free(void* buf);
 int ssp_xchg_status(const void* local_buf, void* stream);
 int ssp_loss_exchange(const void* const* bufs_host /*[world] device pointers, own buffer at [rank]*/, int rank, int world,
                       float* det0, float* det1, float* desc8, float* sem0, float* sem1, int B_local, int Hc, int Wc,
+                      float lambda_loss, float* total /*or NULL: det0.loss + det1.loss + lambda_loss * desc.loss*/,
                       double timeout_s, void* stream);
 
 /* ---- profiling aid (not on the product path): timeline trace of the two tcgen05 kernels.  Only a library built with

@@ -4,6 +4,7 @@
 #   tests[:EXPR]   pytest -m gpu (optionally -k EXPR)          micro     isolation timings of the tcgen05 kernels
 #   bench[:ARGS]   bench.py (1 GPU) with extra ARGS             trace     timeline trace (SSP_TRACE build)
 #   smoke          __graft_entry__.smoke()                      ref       bench.py --impl reference
+#   launches       ncu launch list of bench.py --no-graph       ncufull:REGEX  ncu --set full of the matching kernels
 mkdir -p gpurun_out
 for step in "$@"; do
   name=${step%%:*}; arg=""; [[ "$step" == *:* ]] && arg=${step#*:}
@@ -14,6 +15,14 @@ for step in "$@"; do
     trace) SSP_TRACE=1 timeout 300 python scripts/trace_desc.py gpurun_out/trace.npz > gpurun_out/trace.log 2>&1; echo "trace rc=$?"; tail -3 gpurun_out/trace.log ;;
     bench) timeout 600 python bench.py $arg > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; python scripts/show_bench.py gpurun_out/bench.json 2>/dev/null | head -24 ;;
     ref)   timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json | cut -c1-300 ;;
+    launches) # per-launch device times of two graph-free steps (ncu serialises kernels: compare SHARES, not absolutes)
+           timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+             python bench.py --steps 2 --warmup 1 --no-cpu --no-adapt --no-semantic --no-graph > gpurun_out/launches.log 2>&1
+           echo "launches rc=$?"; python scripts/launch_table.py gpurun_out/launches.csv | head -40 ;;
+    ncufull) # --set full capture of the kernels matching regex $arg
+           timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$arg" -s 4 -c 6 -f -o gpurun_out/prof_full \
+             python bench.py --steps 2 --warmup 1 --no-cpu --no-adapt --no-semantic --no-graph > gpurun_out/ncufull.log 2>&1
+           echo "ncufull rc=$?"; ls -la gpurun_out/prof_full.ncu-rep ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log ;;
     *) echo "unknown step $step" ;;
   esac

@@ -54,7 +54,7 @@ SIGNATURES = {
     "ssp_desc_pack2": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ssp_desc_dense_tc_nblocks": (_I, [_I, _I]),
     "ssp_desc_dense_fwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
-    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "ssp_desc_finalize": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
     "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
     "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "ssp_desc_pos_coef": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P]),
@@ -78,7 +78,7 @@ SIGNATURES = {
     "ssp_xchg_close": (_I, [_P]),
     "ssp_xchg_free": (_I, [_P]),
     "ssp_xchg_status": (_I, [_P, _P]),
-    "ssp_loss_exchange": (_I, [_c.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _D, _P]),
+    "ssp_loss_exchange": (_I, [_c.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _D, _P]),
 }
 
 _lib = None

@@ -380,7 +380,8 @@ extern "C" int ssp_desc_pos_fwd_planes(const void* Ahi, const void* Alo, const v
 __global__ void __launch_bounds__(1024)
 desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double* __restrict__ neg_part, int nneg,
                      const double* __restrict__ mv_part, int nmv, int B, int Hc, int Wc, const int* __restrict__ overflow,
-                     float* __restrict__ out4) {
+                     float* __restrict__ out4, const float* __restrict__ det0, const float* __restrict__ det1,
+                     float lambda_loss, float* __restrict__ total) {
   __shared__ double sh[32];
   double pu = 0, pw = 0, nu = 0, nw = 0, sm = 0;
   double cu = 0, cw = 0;  // negative-hinge contribution of the positive pairs, contained in the dense sums
@@ -435,17 +436,23 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
     out4[5] = (float)pu;
     out4[6] = (float)nu;
     out4[7] = (float)sm;
+    // fused loss step: total = loss_det + loss_det_warp + lambda_loss * loss_desc (Train_model_heatmap_all.py:361-365),
+    // same fp32 operation order as the torch expression it replaces
+    if (total) *total = (det0[0] + det1[0]) + lambda_loss * out4[0];
   }
 }
 
-// overflow (optional): the list-overflow counter colcnt[B * Nc_pad] of the pos kernels; non-zero poisons loss and pos with NaN
+// overflow (optional): the list-overflow counter colcnt[B * Nc_pad] of the pos kernels; non-zero poisons loss and pos with NaN.
+// total (optional, with det0 / det1 = the out3 triples of the two detector losses): the weighted sum of the fused loss step.
 extern "C" int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, int nneg,
                                  const double* mv_part, int nmv, int B, int Hc, int Wc, const int* overflow, float* out4,
-                                 void* stream) {
+                                 const float* det0, const float* det1, float lambda_loss, float* total, void* stream) {
   SSP_REQUIRE(pos_part && neg_part && mv_part && out4, "ssp_desc_finalize: null pointer");
   SSP_REQUIRE(npos >= 0 && nneg >= 0 && nmv >= 0 && B > 0 && Hc > 0 && Wc > 0, "ssp_desc_finalize: bad sizes");
   SSP_REQUIRE((((uintptr_t)pos_part | (uintptr_t)neg_part) & 15) == 0, "ssp_desc_finalize: partial-sum arrays must be 16-byte aligned");
-  desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_part, nmv, B, Hc, Wc, overflow, out4);
+  SSP_REQUIRE(!total || (det0 && det1), "ssp_desc_finalize: the step total needs both detector triples");
+  desc_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_part, npos, neg_part, nneg, mv_part, nmv, B, Hc, Wc, overflow, out4,
+                                                             det0, det1, lambda_loss, total);
   SSP_CUDA_CHECK_LAUNCH("desc_finalize_kernel");
   return SSP_OK;
 }

@@ -13,7 +13,8 @@
 //
 // Forward kernel, work item = (pair b, 256-row tile, 256-column tile; the last column tile is as narrow as Nc needs):
 //   warp 8      TMA producer (both CTAs): own 128 A rows (all 256 channels, resident, reloaded chunk by chunk while the
-//               last item of the previous row tile still runs), B ring of 16 KB stages = own half of a [N x 64 ch] chunk
+//               last item of the previous row tile still runs), B ring of stages = own half of a [N x 64 ch] chunk, all
+//               planes in one 3-D box
 //   warp 9      MMA issuer (leader): tcgen05.mma.cta_group::2 kind::f16 M=256 N<=256 K=16 into a double-buffered
 //               TMEM accumulator (2 x 256 columns)
 //   warps 0-7   epilogue: tcgen05.ld 32x32b, hinge, mask_valid weighting (packed fp32x2 math), running sums and the
@@ -41,7 +42,8 @@
 #define TRACE_CAP 4096
 #ifdef SSP_TRACE
 __device__ long long* g_trace_buf = nullptr;
-#define TR_DECL(role) long long* tr_ = g_trace_buf ? g_trace_buf + ((size_t)blockIdx.x * 4 + (role)) * TRACE_CAP : nullptr; int trn_ = 0
+__device__ int g_trace_roles = 0xF;  // bit r: role r records (tracing a role costs it ~40 cycles per record)
+#define TR_DECL(role) long long* tr_ = (g_trace_buf && ((g_trace_roles >> (role)) & 1)) ? g_trace_buf + ((size_t)blockIdx.x * 4 + (role)) * TRACE_CAP : nullptr; int trn_ = 0
 #define TR_ONLY(cond) do { if (!(cond)) tr_ = nullptr; } while (0)
 #define TR(tag) do { if (tr_ && trn_ < TRACE_CAP) tr_[trn_++] = (clock64() << 8) | (long long)(tag); } while (0)
 #else
@@ -61,10 +63,13 @@ constexpr int CHUNK_BYTES = BM * KC * 2;  // 16 KB: [128 rows x 64 channels], al
 constexpr int FWD_THREADS = 320;
 constexpr int BAR_BYTES = 1024;  // mbarriers, TMEM pointer
 
+// A B stage = this CTA's half of one 64-channel chunk of a column tile, ALL planes: [P][<=128 cells][64 ch] = P x 16 KB, so that
+// the issuing thread pays one barrier wait and one commit per 12 (bf16x3) / 4 (bf16) MMAs.
 template <int P> struct FwdCfg {
   static constexpr int A_BYTES = P * NKC * CHUNK_BYTES;
-  static constexpr int NSTAGE = (P == 1) ? 10 : 6;
-  static constexpr int B_BYTES = NSTAGE * CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = P * CHUNK_BYTES;
+  static constexpr int NSTAGE = (P == 1) ? 10 : 3;
+  static constexpr int B_BYTES = NSTAGE * STAGE_BYTES;
   static constexpr int SMEM = A_BYTES + B_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
@@ -119,15 +124,14 @@ __device__ __forceinline__ double f32_to_f64_bits(float f) {
 
 // Persistent forward kernel.  Work item = (pair b, 256-row tile mp, column tile nt); the flattened item range is split
 // evenly over the clusters, items of a cluster are contiguous in nt so the A rows are reloaded only when (b, mp) changes.
-// Per-item, per-warp partial sums go to partials[((item*2 + rank)*8 + warp)*2 + {0,1}].
+// Every epilogue warp keeps its partial sums over all its items (double) and writes ONE pair at the end:
+// partials[(cta * 8 + warp) * 2 + {0,1}] -- 1184 entries for the finalize kernel instead of one per item and warp.
 // mvbits != NULL ("fold"): the indicator words drop the columns whose mask_valid is 0, so the dD GEMM of the
 // backward can run on the unscaled forward planes of Dw (alpha_c = s * mv_c for a binary mask and g_neg = 0).
 template <int P, bool BITS>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const __grid_constant__ CUtensorMap tmBl_hi, const __grid_constant__ CUtensorMap tmBl_lo,
-                         const float* __restrict__ mv_pad, const uint32_t* __restrict__ mvbits, DescGeom g, int n_last,
+desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ mv_pad, const uint32_t* __restrict__ mvbits, DescGeom g, int n_last,
                          double* __restrict__ partials, uint32_t* __restrict__ bitsR, float* __restrict__ dbgS) {
   using Cfg = FwdCfg<P>;
   constexpr int NSTAGE = Cfg::NSTAGE;
@@ -153,10 +157,9 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   const int it0 = (int)(T * cid / ncluster), it1 = (int)(T * (cid + 1) / ncluster);
 
   if (warp == 8 && lane == 0) {
-    tc::prefetch_tmap(&tmA_hi);
-    tc::prefetch_tmap(&tmB_hi);
-    tc::prefetch_tmap(&tmBl_hi);
-    if (P == 2) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); tc::prefetch_tmap(&tmBl_lo); }
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&tmBl);
   }
   if (warp == 9) {
     if (lane == 0) {
@@ -196,23 +199,22 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             TR(10);
             if (nkeys > 0) tc::mbar_wait(a_empty + kc, (uint32_t)((nkeys - 1) & 1));
             TR(11);
-            if (el) {
+            if (el) {  // one box: all planes of chunk kc of my 128 rows
               if (leader) tc::mbar_expect_tx(a_full + kc, 2 * P * CHUNK_BYTES);
-              for (int p = 0; p < P; ++p)
-                tc::tma_load_2d_2sm(p == 0 ? &tmA_hi : &tmA_lo, a_full + kc, sA + (p * NKC + kc) * CHUNK_BYTES, kc * KC,
-                                    row_base + (2 * mp + (int)cta_rank) * BM);
+              tc::tma_load_3d_2sm(&tmA, a_full + kc, sA + kc * P * CHUNK_BYTES, kc * KC, row_base + (2 * mp + (int)cta_rank) * BM, 0);
             }
           }
-          for (int p = 0; p < P; ++p, ++stage_it) {
+          {
             const int s = stage_it % NSTAGE;
             const uint32_t ph = (stage_it / NSTAGE) & 1;
+            ++stage_it;
             TR(12);
             tc::mbar_wait(b_empty + s, ph ^ 1);
             TR(13);
-            if (el) {
-              if (leader) tc::mbar_expect_tx(b_full + s, 2 * half * KC * 2);
-              const CUtensorMap* m = last ? (p == 0 ? &tmBl_hi : &tmBl_lo) : (p == 0 ? &tmB_hi : &tmB_lo);
-              tc::tma_load_2d_2sm(m, b_full + s, sB + s * CHUNK_BYTES, kc * KC, row_base + nt * BN + (int)cta_rank * half);
+            if (el) {  // one box: all planes of chunk kc of my half of the tile's columns
+              if (leader) tc::mbar_expect_tx(b_full + s, 2 * P * half * KC * 2);
+              tc::tma_load_3d_2sm(last ? &tmBl : &tmB, b_full + s, sB + s * Cfg::STAGE_BYTES, kc * KC,
+                                  row_base + nt * BN + (int)cta_rank * half, 0);
             }
           }
         }
@@ -234,7 +236,8 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const bool newkey = key != prev_key;
         if (newkey) { prev_key = key; ++nkeys; }
         const bool last_of_key = (it + 1 == it1) || ((it + 1) / NT != key);
-        const uint32_t idesc = tc::idesc_bf16_f32(2 * BM, nt == NT - 1 ? n_last : BN, 0, 0);
+        const int ncols = nt == NT - 1 ? n_last : BN;
+        const uint32_t idesc = tc::idesc_bf16_f32(2 * BM, ncols, 0, 0);
         const int as = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
         TR(2);
@@ -249,22 +252,29 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             tc::mbar_wait(a_full + kc, (uint32_t)((nkeys - 1) & 1));
             TR(8);
           }
-          for (int p = 0; p < P; ++p, ++stage_it) {
+          {
             const int s = stage_it % NSTAGE;
             const uint32_t ph = (stage_it / NSTAGE) & 1;
+            ++stage_it;
             TR(4);
             tc::mbar_wait(b_full + s, ph);
             TR(5);
             tc::fence_after_sync();
-            // B plane p (0 = hi, 1 = lo) meets A hi; B hi additionally meets A lo (lo*lo is dropped)
-            const int n_a = (P == 2 && p == 0) ? 2 : 1;
-            const uint64_t db = tc::smem_desc_sw128(sB_u + s * CHUNK_BYTES, 16, 1024);
-            for (int pa = 0; pa < n_a; ++pa) {
-              const uint64_t da = tc::smem_desc_sw128(sA_u + (pa * NKC + kc) * CHUNK_BYTES, 16, 1024);
-              if (el) tc::mma2_ss_x4(d_tmem, da, db, idesc, first ? 0u : 1u);  // 4 x (M256 N K16) over this 64-channel chunk
-              first = 0;
+            // hi*hi, then (bf16x3) A lo * B hi and A hi * B lo (lo*lo is dropped); plane p of a B stage starts
+            // (ncols / 2) * 128 bytes after plane p - 1
+            const uint64_t da_hi = tc::smem_desc_sw128(sA_u + (kc * P) * CHUNK_BYTES, 16, 1024);
+            const uint64_t db_hi = tc::smem_desc_sw128(sB_u + s * Cfg::STAGE_BYTES, 16, 1024);
+            if (el) {
+              tc::mma2_ss_x4(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);  // 4 x (M256 N K16) over this 64-channel chunk
+              if (P == 2) {
+                const uint64_t da_lo = tc::smem_desc_sw128(sA_u + (kc * P + 1) * CHUNK_BYTES, 16, 1024);
+                const uint64_t db_lo = tc::smem_desc_sw128(sB_u + s * Cfg::STAGE_BYTES + (ncols >> 1) * (KC * 2), 16, 1024);
+                tc::mma2_ss_x4(d_tmem, da_lo, db_hi, idesc, 1u);
+                tc::mma2_ss_x4(d_tmem, da_hi, db_lo, idesc, 1u);
+              }
+              tc::mma2_commit_mc(b_empty + s, (uint16_t)0x3);  // both producers: the pair is done with slot s
             }
-            if (el) tc::mma2_commit_mc(b_empty + s, (uint16_t)0x3);  // both producers: the pair is done with slot s
+            first = 0;
             TR(6);
           }
           if (last_of_key && el) tc::mma2_commit_mc(a_empty + kc, (uint16_t)0x3);  // A chunk kc may be replaced in both CTAs
@@ -280,6 +290,7 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     const int NW = g.Nc_pad / 32;
     const bool fold = mvbits != nullptr;
     int tcount = 0;
+    double su_all = 0.0, sw_all = 0.0;
     TR_DECL(2 + (warp == 7 ? 1 : 0));
     TR_ONLY((warp == 0 || warp == 7) && lane == 0);
     for (int it = it0; it < it1; ++it, ++tcount) {
@@ -344,12 +355,15 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       float sa, sb, wa, wb;
       tc::unpack2(su2, sa, sb);
       tc::unpack2(sw2, wa, wb);
-      const float su_t = warp_sum(sa + sb), sw_t = warp_sum(wa + wb);
-      if (lane == 0) {
-        const size_t slot = (((size_t)it * 2 + cta_rank) * 8 + warp) * 2;
-        partials[slot] = f32_to_f64_bits(su_t);
-        partials[slot + 1] = f32_to_f64_bits(sw_t);
-      }
+      su_all += f32_to_f64_bits(sa + sb);  // per-thread, per-item fp32 sums (<= 128 entries) enter a double accumulator
+      sw_all += f32_to_f64_bits(wa + wb);
+    }
+    su_all = warp_sum_d(su_all);
+    sw_all = warp_sum_d(sw_all);
+    if (lane == 0) {
+      const size_t slot = ((size_t)blockIdx.x * 8 + warp) * 2;
+      partials[slot] = su_all;
+      partials[slot + 1] = sw_all;
     }
   }
 
@@ -411,12 +425,15 @@ desc_bits_transpose_kernel(const uint32_t* __restrict__ bitsR, uint32_t* __restr
 // ------------------------------------------------------------------------------------------------
 // indicator GEMM (backward)
 // ------------------------------------------------------------------------------------------------
-constexpr int KT = 64;                       // cells (GEMM K) per stage
-constexpr int BG_PLANE_BYTES = KT * 128;     // one [64 cells x 64 channels] box = 8 KB (this CTA's half of the 128 channels)
+constexpr int KT = 128;                      // cells (GEMM K) per stage: 8 K=16 steps per plane, i.e. up to 16 MMAs behind ONE pair
+                                             // of barrier waits and one commit of the issuing thread (with 64-cell stages that
+                                             // thread, not the tensor pipe, set the pace: ~900 cycles per 512 cycles of MMA)
+constexpr int BG_PLANE_BYTES = KT * 128;     // one [128 cells x 64 channels] box = 16 KB (this CTA's half of the 128 channels)
 constexpr int BG_N = 128;                    // channels per work item (half of the descriptor)
 constexpr int BG_THREADS = 576;              // warps 0-7 expanders (two sets), 8-15 epilogue, 16 TMA producer, 17 MMA issuer
 constexpr int BG_W_EPI = 8, BG_W_TMA = 16, BG_W_MMA = 17;
-constexpr int BG_NS = 8;                     // ring depth: TMEM holds 2 x 128 accumulator columns + 8 x 32 columns of A
+constexpr int BG_NS = 4;                     // ring depth: TMEM holds 2 x 128 accumulator columns + 4 x 64 columns of A
+constexpr int BG_ACOLS = KT / 2;             // TMEM columns of one A stage (two bf16 per column)
 
 template <int P> struct BgCfg {
   static constexpr int STAGE_BYTES = P * BG_PLANE_BYTES;
@@ -443,7 +460,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
                          BgJob job1, int njobs, int B, int Nc, int Nc_pad, int dbg) {
   using Cfg = BgCfg<P>;
   constexpr int NS = BG_NS;
-  static_assert(256 + 32 * NS <= 512, "TMEM A ring does not fit");
+  static_assert(256 + BG_ACOLS * NS <= 512, "TMEM A ring does not fit");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
@@ -456,11 +473,12 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MP = Nc_pad / (2 * BM), NK = (Nc + KT - 1) / KT, NW = Nc_pad / 32;
+  const int NKS = (Nc + 15) / 16;  // K=16 steps that hold real cells: the last stage issues only its share of them
   const uint32_t cta_rank = tc::cluster_ctarank();
   const bool leader = cta_rank == 0;
   const int ncluster = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const int T = B * njobs * MP * 2;
-  constexpr uint32_t A_COL0 = 256;  // TMEM: accumulators at columns [0,128) and [128,256), then NS x 32 columns of A
+  constexpr uint32_t A_COL0 = 256;  // TMEM: accumulators at columns [0,128) and [128,256), then NS x 64 columns of A
 
   // item -> (b, job, mp, dh)
   auto decode = [&](int it, int& b, int& jb, int& mp, int& dh) {
@@ -509,7 +527,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
           TR(13);
           if (el) {
             if (leader) tc::mbar_expect_tx(b_full + s, 2 * Cfg::STAGE_BYTES);
-            // one box: [P planes x 64 cells x my 64 of the item's 128 channels]
+            // one box: [P planes x 128 cells x my 64 of the item's 128 channels]
             tc::tma_load_3d_2sm(m, b_full + s, smem + s * Cfg::STAGE_BYTES, dh * BG_N + (int)cta_rank * 64, b * Nc_pad + kc * KT, 0);
           }
         }
@@ -546,12 +564,15 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
           if (!(dbg & 1)) tc::mbar_wait(a_full + s, ph);
           TR(7);
           tc::fence_after_sync();
+          const int nks = min(KT / 16, NKS - kc * (KT / 16));  // K=16 steps of this stage that hold real cells
           for (int p = 0; p < P; ++p) {
-            // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B per step); each CTA supplies one 64-channel
-            // swizzle atom of the 128 channels; A advances 8 TMEM columns per step
+            // per K=16 step: 16 cells = two 8-row groups (SBO 1024 B, +2048 B = 128 descriptor units per step); each CTA
+            // supplies one 64-channel swizzle atom of the 128 channels; A advances 8 TMEM columns per step
             const uint64_t db = tc::smem_desc_sw128(smem_u + s * Cfg::STAGE_BYTES + p * BG_PLANE_BYTES, BG_PLANE_BYTES, 1024);
-            if (el) tc::mma2_ts_x4(d_tmem, A_COL0 + s * 32, db, idesc, first ? 0u : 1u);
-            first = 0;
+            for (int j = 0; j < nks; ++j) {
+              if (el) tc::mma2_ts(d_tmem, A_COL0 + s * BG_ACOLS + 8 * j, db + (uint64_t)(128 * j), idesc, first ? 0u : 1u);
+              first = 0;
+            }
           }
           if (el) tc::mma2_commit_mc(s_free + s, (uint16_t)0x3);
           TR(6);
@@ -566,13 +587,10 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
     const int q = warp & 3, set = warp >> 2;  // TMEM lane quadrant; set 0 expands the even stages, set 1 the odd ones
     TR_DECL(2);
     TR_ONLY(warp == 0 && lane == 0);
-    // one ring stage: the 64 indicator bits (w0: cells 0..31, w1: cells 32..63 of the stage) of this row become 32 TMEM
-    // columns of bf16 pairs.  Bit i of a word is cell 2i, bit 16+i is cell 2i+1 (DESC_BITPOS), so column i of a word is
-    // ONE shift and ONE and: (w << (14 - i)) & 0x40004000 -- bf16 0x4000 = 2.0; the epilogue multiplies by 0.5.
-    auto expand_stage = [&](int st_it, uint32_t w0, uint32_t w1) {
-      const int s = st_it % NS;
-      const uint32_t ph = (st_it / NS) & 1;
-      uint32_t r[32];
+    // one ring stage: the 128 indicator bits (four words) of this row become 64 TMEM columns of bf16 pairs.  Bit i of a word
+    // is cell 2i, bit 16+i is cell 2i+1 (DESC_BITPOS), so column i of a word is ONE shift and ONE and:
+    // (w << (14 - i)) & 0x40004000 -- bf16 0x4000 = 2.0; the epilogue multiplies by 0.5.
+    auto expand_words = [&](uint32_t w0, uint32_t w1, uint32_t (&r)[32]) {
 #pragma unroll
       for (int i = 0; i < 15; ++i) {
         r[i] = (w0 << (14 - i)) & 0x40004000u;
@@ -580,11 +598,20 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
       }
       r[15] = (w0 >> 1) & 0x40004000u;
       r[31] = (w1 >> 1) & 0x40004000u;
+    };
+    auto expand_stage = [&](int st_it, const uint32_t (&w)[4]) {
+      const int s = st_it % NS;
+      const uint32_t ph = (st_it / NS) & 1;
+      uint32_t r[32];
+      expand_words(w[0], w[1], r);
       TR(20);
       tc::mbar_wait(s_free + s, ph ^ 1);
       TR(21);
       tc::fence_after_sync();
-      tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * 32, r);
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + s * BG_ACOLS;
+      tc::tmem_st32(t0, r);
+      expand_words(w[2], w[3], r);
+      tc::tmem_st32(t0 + 32, r);
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
@@ -593,12 +620,13 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
     };
     // the indicator words run PF of this set's stages ahead of their use over the FLAT stage sequence of all items of this
     // cluster, so neither the L2 latency inside an item nor the start of a new item is exposed
-    constexpr int PF = 6;
-    uint32_t wq0[PF], wq1[PF];
-    int itB = cid, kcB = set;  // fetch cursor (stage `set` of the first item; NK >= 2 always holds for Nc > 64)
+    constexpr int PF = 4;
+    uint32_t wq[PF][4];
+    int itB = cid, kcB = set;  // fetch cursor (stage `set` of the first item)
     const uint32_t* pB = nullptr;
     bool newitem = true;
-    auto fetch = [&](uint32_t& a, uint32_t& c) {
+    auto fetch = [&](uint32_t (&w)[4]) {
+      while (itB < T && kcB >= NK) { kcB -= NK; itB += ncluster; newitem = true; }  // NK may be 1 (tiny inputs)
       if (itB < T) {
         if (newitem) {
           int b, jb, mp, dh;
@@ -607,22 +635,25 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
           pB = (jb ? job1.bits : job0.bits) + (size_t)b * NW * Nc_pad + row;
           newitem = false;
         }
-        a = __ldg(pB + (size_t)(2 * kcB) * Nc_pad);
-        c = __ldg(pB + (size_t)(2 * kcB + 1) * Nc_pad);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = __ldg(pB + (size_t)(4 * kcB + u) * Nc_pad);
         kcB += 2;
-        if (kcB >= NK) { kcB -= NK; itB += ncluster; newitem = true; }
       }
     };
 #pragma unroll
-    for (int u = 0; u < PF; ++u) { wq0[u] = 0u; wq1[u] = 0u; fetch(wq0[u], wq1[u]); }
+    for (int u = 0; u < PF; ++u) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) wq[u][v] = 0u;
+      fetch(wq[u]);
+    }
     const int nitems = cid < T ? (T - cid + ncluster - 1) / ncluster : 0;
     const int total = nitems * NK;  // global stage count of this cluster; this set owns g = set, set + 2, ...
     for (int g0 = set; g0 < total; g0 += 2 * PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         if (g0 + 2 * u < total) {
-          expand_stage(g0 + 2 * u, wq0[u], wq1[u]);
-          fetch(wq0[u], wq1[u]);
+          expand_stage(g0 + 2 * u, wq[u]);
+          fetch(wq[u]);
         }
       }
     }
@@ -734,21 +765,6 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// packed plane [rows, 256] bf16 -> 2-D map with a [box_rows x 64] SWIZZLE_128B box
-int make_plane_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_tiled();
-  if (!enc) { ssp_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return SSP_EUNSUPPORTED; }
-  cuuint64_t dims[2] = {(cuuint64_t)KD, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)KD * 2};
-  cuuint32_t box[2] = {(cuuint32_t)KC, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { ssp_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SSP_EARG; }
-  return SSP_OK;
-}
-
 // hi (+ lo) planes [rows, 256] bf16 as ONE 3-D tensor {256 channels, rows, planes}: a [64 ch x box_rows x planes] box brings
 // the same cells of both planes with one TMA instruction.  The planes may live anywhere as long as lo is above hi and the
 // distance is a multiple of 16 bytes (the Python host allocates them back to back).
@@ -760,7 +776,7 @@ int make_planes_map3(CUtensorMap* m, const void* hi, const void* lo, uint64_t ro
   if (lo) {
     if ((uintptr_t)lo <= (uintptr_t)hi || (((uintptr_t)lo - (uintptr_t)hi) & 15) || ((uintptr_t)lo - (uintptr_t)hi) < plane_bytes ||
         ((uintptr_t)lo - (uintptr_t)hi) >= (1ull << 40)) {
-      ssp_set_error("ssp_desc_bits_gemm_tc: the lo plane must lie above the hi plane (distance a multiple of 16 bytes)");
+      ssp_set_error("tcgen05 descriptor kernels: the lo plane must lie above the hi plane (distance a multiple of 16 bytes)");
       return SSP_EARG;
     }
     pstride = (uintptr_t)lo - (uintptr_t)hi;
@@ -811,6 +827,9 @@ extern "C" int ssp_debug_trace(void* buf) {
 #ifdef SSP_TRACE
   long long* p = reinterpret_cast<long long*>(buf);
   SSP_CUDA_CALL(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
+  const char* e = getenv("SSP_TRACE_ROLES");  // bit mask of the roles that record (default all four)
+  int roles = e ? atoi(e) : 0xF;
+  SSP_CUDA_CALL(cudaMemcpyToSymbol(g_trace_roles, &roles, sizeof(roles)));
   return SSP_OK;
 #else
   (void)buf;
@@ -820,10 +839,12 @@ extern "C" int ssp_debug_trace(void* buf) {
 }
 extern "C" int ssp_debug_trace_cap(void) { return TRACE_CAP; }
 
-// partial-sum slots of the forward kernel: one per (item, cluster rank, epilogue warp)
+// partial-sum slots of the forward kernel: one per (CTA, epilogue warp) of the persistent grid
 extern "C" int ssp_desc_dense_tc_nblocks(int B, int Nc) {
   int ncp = desc_nc_pad(Nc);
-  return B * (ncp / (2 * BM)) * (ncp / BN) * 2 * 8;
+  long long items = (long long)B * (ncp / (2 * BM)) * (ncp / BN);
+  int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
+  return 2 * nclusters * 8;
 }
 
 // Ahi/Alo: packed planes of `descriptors`, Bhi/Blo: packed planes of `descriptors_warped` ([B, Nc_pad, 256] bf16).
@@ -846,14 +867,11 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
   const int NT = g.Nc_pad / BN;
   const int n_last = ((g.Nc - (NT - 1) * BN) + 15) / 16 * 16;  // width of the last column tile: 16..256, multiple of 16
   uint64_t rows = (uint64_t)B * g.Nc_pad;
-  CUtensorMap mAh, mAl, mBh, mBl, mLh, mLl;
+  CUtensorMap mA, mB, mL;
   int rc;
-  if ((rc = make_plane_map(&mAh, Ahi, rows, BM))) return rc;
-  if ((rc = make_plane_map(&mAl, Alo ? Alo : Ahi, rows, BM))) return rc;
-  if ((rc = make_plane_map(&mBh, Bhi, rows, BN / 2))) return rc;  // each CTA of a pair supplies half of the tile's columns
-  if ((rc = make_plane_map(&mBl, Blo ? Blo : Bhi, rows, BN / 2))) return rc;
-  if ((rc = make_plane_map(&mLh, Bhi, rows, n_last / 2))) return rc;
-  if ((rc = make_plane_map(&mLl, Blo ? Blo : Bhi, rows, n_last / 2))) return rc;
+  if ((rc = make_planes_map3(&mA, Ahi, Alo, rows, BM))) return rc;
+  if ((rc = make_planes_map3(&mB, Bhi, Blo, rows, BN / 2))) return rc;  // each CTA of a pair supplies half of the tile's columns
+  if ((rc = make_planes_map3(&mL, Bhi, Blo, rows, n_last / 2))) return rc;
   // persistent: one 2-CTA cluster per SM pair (or fewer when there is less work)
   long long items = (long long)B * (g.Nc_pad / (2 * BM)) * NT;
   int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
@@ -862,8 +880,8 @@ extern "C" int ssp_desc_dense_fwd_tc(const void* Ahi, const void* Alo, const voi
 #define LAUNCH_FWD(PP, BB)                                                                                       \
   do {                                                                                                           \
     if ((rc = set_smem(desc_dense_fwd_tc_kernel<PP, BB>, FwdCfg<PP>::SMEM))) return rc;                          \
-    if ((rc = launch_cluster2(desc_dense_fwd_tc_kernel<PP, BB>, grid, FWD_THREADS, FwdCfg<PP>::SMEM, st, mAh, mAl, mBh, mBl, \
-                              mLh, mLl, mv_pad, mvbits, g, n_last, partials, bitsR, dbgS))) return rc;           \
+    if ((rc = launch_cluster2(desc_dense_fwd_tc_kernel<PP, BB>, grid, FWD_THREADS, FwdCfg<PP>::SMEM, st, mA, mB, mL,         \
+                              mv_pad, mvbits, g, n_last, partials, bitsR, dbgS))) return rc;                     \
   } while (0)
   if (Alo) { if (bitsR) LAUNCH_FWD(2, true); else LAUNCH_FWD(2, false); }
   else     { if (bitsR) LAUNCH_FWD(1, true); else LAUNCH_FWD(1, false); }

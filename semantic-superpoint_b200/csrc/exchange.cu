@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __global__ void __launch_bounds__(32)
 loss_exchange_kernel(XchgPeers peers, int rank, int world, float* __restrict__ det0, float* __restrict__ det1,
                      float* __restrict__ desc8, float* __restrict__ sem0, float* __restrict__ sem1, float B_local,
-                     float Hc, float Wc, unsigned long long spin_ns) {
+                     float Hc, float Wc, float lambda_loss, float* __restrict__ total, unsigned long long spin_ns) {
   const int lane = threadIdx.x;
   XchgBuf* L = peers.buf[rank];
   unsigned int seq = 0;
@@ -135,6 +135,8 @@ loss_exchange_kernel(XchgPeers peers, int rank, int world, float* __restrict__ d
     }
     if (sem0) { sem0[1] = s[9]; sem0[2] = s[10]; sem0[0] = s[9] / s[10]; }
     if (sem1) { sem1[1] = s[11]; sem1[2] = s[12]; sem1[0] = s[11] / s[12]; }
+    // fused loss step: the weighted total of the GLOBAL-batch losses (same expression as desc_finalize on one GPU)
+    if (total && det0 && det1 && desc8) *total = (det0[0] + det1[0]) + lambda_loss * desc8[0];
   }
 }
 
@@ -194,10 +196,12 @@ extern "C" int ssp_xchg_status(const void* local_buf, void* stream) {
 
 // bufs_host[world]: device pointers of every rank's exchange buffer as seen from THIS process (own buffer at [rank]).
 // det0 / det1: out3 of the detector losses {loss, numerator, sum(mask)+1e-5}; desc8: out8 of ssp_desc_finalize;
-// sem0 / sem1: out3 of the semantic losses {loss, sum, count}.  Any of them may be NULL.  All are rewritten in place
+// sem0 / sem1: out3 of the semantic losses {loss, sum, count}.  Any of them may be NULL.  total (optional, needs det0, det1
+// and desc8): det0.loss + det1.loss + lambda_loss * desc.loss of the global batch.  All are rewritten in place
 // with the global-batch values.  B_local = pairs of this rank (ranks may hold different shard sizes).
 extern "C" int ssp_loss_exchange(const void* const* bufs_host, int rank, int world, float* det0, float* det1, float* desc8,
-                                 float* sem0, float* sem1, int B_local, int Hc, int Wc, double timeout_s, void* stream) {
+                                 float* sem0, float* sem1, int B_local, int Hc, int Wc, float lambda_loss, float* total,
+                                 double timeout_s, void* stream) {
   SSP_REQUIRE(bufs_host, "ssp_loss_exchange: null pointer");
   SSP_REQUIRE(world >= 1 && world <= XCHG_MAXR && rank >= 0 && rank < world, "ssp_loss_exchange: bad rank %d / world %d (max %d)",
               rank, world, XCHG_MAXR);
@@ -210,7 +214,7 @@ extern "C" int ssp_loss_exchange(const void* const* bufs_host, int rank, int wor
   }
   if (!(timeout_s > 0.0)) timeout_s = 30.0;
   loss_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peers, rank, world, det0, det1, desc8, sem0, sem1, (float)B_local,
-                                                            (float)Hc, (float)Wc, (unsigned long long)(timeout_s * 1e9));
+                                                            (float)Hc, (float)Wc, lambda_loss, total, (unsigned long long)(timeout_s * 1e9));
   SSP_CUDA_CHECK_LAUNCH("loss_exchange_kernel");
   return SSP_OK;
 }

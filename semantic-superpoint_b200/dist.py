@@ -122,7 +122,7 @@ class LossExchange(object):
                        "loss exchange")
 
     # -- the one entry point ----------------------------------------------------------------------
-    def run(self, det0=None, det1=None, desc8=None, sem0=None, sem1=None, B_local=0, Hc=1, Wc=1):
+    def run(self, det0=None, det1=None, desc8=None, sem0=None, sem1=None, B_local=0, Hc=1, Wc=1, lambda_loss=1.0, total=None):
         ts = [t for t in (det0, det1, desc8, sem0, sem1) if t is not None]
         if not ts:
             return
@@ -132,7 +132,8 @@ class LossExchange(object):
                 if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                     raise RuntimeError("loss exchange (p2p): the scalars must be contiguous fp32 CUDA tensors")
             _lib.call("ssp_loss_exchange", self.table, self.rank, self.world, _lib.ptr(det0), _lib.ptr(det1), _lib.ptr(desc8),
-                      _lib.ptr(sem0), _lib.ptr(sem1), int(B_local), int(Hc), int(Wc), self.timeout_s, _lib.stream_of(ts[0]))
+                      _lib.ptr(sem0), _lib.ptr(sem1), int(B_local), int(Hc), int(Wc), float(lambda_loss), _lib.ptr(total),
+                      self.timeout_s, _lib.stream_of(ts[0]))
             return
         # torch.distributed fallback: same payload, same fix-ups, one all-reduce
         with torch.no_grad():
@@ -163,6 +164,8 @@ class LossExchange(object):
                 if d is not None:
                     d[1:3] = pay[i:i + 2]
                     d[0] = pay[i] / pay[i + 1]
+            if total is not None:
+                total.copy_(((det0[0] + det1[0]) + float(lambda_loss) * desc8[0]).reshape(total.shape))
 
 
 _exchanges = {}

@@ -240,7 +240,9 @@ class DescriptorLossFn(torch.autograd.Function):
     differentiable w.r.t. descriptors and descriptors_warped, wpts (warped cell centres) is not."""
 
     @staticmethod
-    def forward(ctx, D, Dw, Hm, mv, cell, lamda, dist, engine, dist_group=None, debug_S=None, fold_alpha=False):
+    def forward(ctx, D, Dw, Hm, mv, cell, lamda, dist, engine, dist_group=None, debug_S=None, fold_alpha=False, step_total=None):
+        # step_total (LossStepFn only): (det_out [2,3], lambda_loss, total [1]) -- the finalize kernel also writes the weighted
+        # sum of the fused step, so no torch add / mul kernels are needed for it
         lib = _lib.load()
         dev = D.device
         Dc = f32c(D.detach(), dev)
@@ -320,8 +322,13 @@ class DescriptorLossFn(torch.autograd.Function):
                 planes = (Ahi, None, Bhi, None)
             fork.join()
 
-        call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(overflow),
-             ptr(out8), st)
+        if step_total is not None:
+            det_out, lam_loss, total = step_total
+            call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(overflow),
+                 ptr(out8), ptr(det_out[0]), ptr(det_out[1]), float(lam_loss), ptr(total), st)
+        else:
+            call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(overflow),
+                 ptr(out8), None, None, 0.0, None, st)
         if CHECK_LIST_OVERFLOW and int(overflow[0]) != 0:  # host sync: debugging / tests only (the NaN above is the product signal)
             raise RuntimeError("descriptor_loss: %d positive pairs overflowed the sparse lists" % int(overflow[0]))
         if dist_group is not None:
@@ -409,7 +416,7 @@ class DescriptorLossFn(torch.autograd.Function):
             f1.join()
             call("ssp_desc_pos_apply", ptr(rowcol), ptr(coefs[0]), ptr(colrow_sorted), ptr(coefs[1]), ptr(Dc), ptr(Dwc), B, Dch, Nc, 0,
                  ptr(dD), ptr(dDw), st)
-        return dD, dDw, None, None, None, None, None, None, None, None, None
+        return dD, dDw, None, None, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -444,14 +451,17 @@ class LossStepFn(torch.autograd.Function):
         l0, l1, cellmask = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
         B, _, Hc, Wc = semi.shape
         c2 = _Ctx((ctx.needs_input_grad[6], ctx.needs_input_grad[7]) + (False,) * 8)
+        total = torch.empty((1,), dtype=torch.float32, device=semi.device)
         ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine,
-                                                       None, None, FOLD_ALPHA)
+                                                       None, None, FOLD_ALPHA, (c1.out, lambda_loss, total))
         if dist_group is not None:
             # multi-GPU: ONE exchange kernel turns the three local results into global-batch values in place (the scalars
-            # above are views of c1.out / c2.out8); the backward kernels read the global normalisers from the same buffers
+            # above are views of c1.out / c2.out8) and rewrites the weighted total; the backward kernels read the global
+            # normalisers from the same buffers
             from .dist import get_exchange
-            get_exchange(dist_group).run(det0=c1.out[0], det1=c1.out[1], desc8=c2.out8, B_local=B, Hc=Hc, Wc=Wc)
-        loss = (l0 + l1).add_(ld, alpha=lambda_loss)
+            get_exchange(dist_group).run(det0=c1.out[0], det1=c1.out[1], desc8=c2.out8, B_local=B, Hc=Hc, Wc=Wc,
+                                         lambda_loss=lambda_loss, total=total)
+        loss = total[0]
         ctx.c1, ctx.c2, ctx.lambda_loss = c1, c2, float(lambda_loss)
         ctx.mark_non_differentiable(l0, l1, ld, pos, neg)
         ctx.set_materialize_grads(False)  # no zero-filled gradient tensors for the five logging outputs

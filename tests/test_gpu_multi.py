@@ -44,12 +44,13 @@ def test_exchange_kernel_two_ranks_one_process():
                 loc.append((det0, det1, d8, sem))
             ref = [[t.clone().cpu().numpy().astype(np.float64) for t in l] for l in loc]
             Bl = (3, 2)
+            totals = [torch.zeros(1, device=dev) for _ in range(2)]
             torch.cuda.synchronize()
             for r in range(2):
                 with torch.cuda.stream(streams[r]):
                     det0, det1, d8, sem = loc[r]
                     _lib.call("ssp_loss_exchange", table, r, 2, _lib.ptr(det0), _lib.ptr(det1), _lib.ptr(d8), _lib.ptr(sem), None,
-                              Bl[r], HC, WC, 10.0, ctypes.c_void_p(streams[r].cuda_stream))
+                              Bl[r], HC, WC, 0.25, _lib.ptr(totals[r]), 10.0, ctypes.c_void_p(streams[r].cuda_stream))
             torch.cuda.synchronize()
             for r in range(2):
                 _lib.check(lib.ssp_xchg_status(ctypes.c_void_p(bufs[r]), None), "exchange status")
@@ -70,10 +71,13 @@ def test_exchange_kernel_two_ranks_one_process():
                 np.testing.assert_allclose(got[4:], sums, rtol=1e-6)
                 np.testing.assert_allclose(loc[r][3].cpu().numpy(), [ssem[0] / ssem[1], ssem[0], ssem[1]], rtol=2e-6)
             assert torch.equal(loc[0][2], loc[1][2])  # bit-identical on both ranks (same summation order)
+            for r in range(2):  # weighted total of the fused step: det0 + det1 + lambda_loss * desc
+                want = float(loc[r][0][0]) + float(loc[r][1][0]) + 0.25 * float(loc[r][2][0])
+                np.testing.assert_allclose(float(totals[r]), want, rtol=1e-6)
         # world = 1 degenerates to the local fix-up
         d8 = torch.tensor([0, 0, 0, 0, 10.0, 4.0, 6.0, 7.0], dtype=torch.float32, device=dev)
         one = (ctypes.c_void_p * 1)(bufs[0])
-        _lib.call("ssp_loss_exchange", one, 0, 1, None, None, _lib.ptr(d8), None, None, 2, 3, 4, 10.0, None)
+        _lib.call("ssp_loss_exchange", one, 0, 1, None, None, _lib.ptr(d8), None, None, 2, 3, 4, 1.0, None, 10.0, None)
         norm = 2.0 * 8.0 * 12.0
         np.testing.assert_allclose(d8.cpu().numpy(), [10 / norm, 4 / norm, 6 / norm, norm, 10, 4, 6, 7], rtol=1e-6)
     finally:
@@ -92,7 +96,7 @@ def test_exchange_timeout_poisons_instead_of_hanging():
         bufs.append(p.value)
     table = (ctypes.c_void_p * 2)(*bufs)
     det0 = torch.ones(3, device="cuda")
-    _lib.call("ssp_loss_exchange", table, 0, 2, _lib.ptr(det0), None, None, None, None, 1, HC, WC, 0.05, None)
+    _lib.call("ssp_loss_exchange", table, 0, 2, _lib.ptr(det0), None, None, None, None, 1, HC, WC, 1.0, None, 0.05, None)
     torch.cuda.synchronize()
     assert torch.isnan(det0).all()
     assert lib.ssp_xchg_status(ctypes.c_void_p(bufs[0]), None) != 0
