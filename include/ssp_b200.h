@@ -35,7 +35,9 @@ int ssp_warp_keypoints_f64(const double* kp /*[K,2] x,y pixels*/, int K, const d
 
 /* ---- a2: inv_warp_image_batch / inv_warp_image (utils/utils.py:347-405).
  *      xs[W], ys[H] = the normalised sampling grid (torch.linspace(-1,1,n) of the reference, :375).
- *      mode 0 = bilinear, 1 = nearest; zeros padding, align_corners=True. ---- */
+ *      mode 0 = bilinear, 1 = nearest; zeros padding, align_corners=True.  Default kernel: 32x32 output tiles whose
+ *      source footprint is staged through shared memory with 16-byte cp.async; mode + 2 forces the per-pixel gather
+ *      kernel (also taken automatically for W % 4 != 0 or a misaligned image).  Same results either way. ---- */
 int ssp_inv_warp_image(const float* img /*[B,C,H,W]*/, int B, int C, int H, int W, const float* Hinv /*[B,3,3]*/,
                        const float* xs, const float* ys, int mode, float* out /*[B,C,H,W]*/, void* stream);
 
@@ -80,6 +82,19 @@ int ssp_combine_heatmap(const float* heat /*[I,N,H,W]*/, const float* mask /*[I,
  * 240x320 (see heatmap.cu). */
 int ssp_combine_heatmap_tiled(const float* heat, const float* mask, const float* Hinv, int I, int N, int H, int W,
                               const float* xs, const float* ys, float* out, void* stream);
+
+/* Bit-mask form of the same aggregation (default of the batched export path): the 0/1 valid masks of homography adaptation
+ * (compute_valid_mask, datasets/Coco.py:284-288) as one bit per pixel, bits [rows, ceil(W/32)], bit x&31 of word x>>5.
+ * ssp_mask_pack_bits converts float masks (flag, a zeroed device int, is set on a value other than 0/1 and makes the
+ * aggregation return NaN); ssp_valid_mask_bits is compute_valid_mask(erosion_radius=0) straight to bits.  Results are
+ * bit-identical to ssp_combine_heatmap on binary masks. */
+size_t ssp_mask_bits_words(int rows, int W);
+int ssp_mask_pack_bits(const float* mask /*[rows,W]*/, long long rows, int W, uint32_t* bits, int* flag, void* stream);
+int ssp_valid_mask_bits(int B, int H, int W, const float* Hinv /*[B,3,3]*/, const float* xs, const float* ys,
+                        uint32_t* bits /*[B,H,ceil(W/32)]*/, void* stream);
+int ssp_combine_heatmap_bits(const float* heat /*[I,N,H,W]*/, const uint32_t* mbits /*[I,N,H,ceil(W/32)]*/,
+                             const float* Hinv /*[I,N,3,3]*/, int I, int N, int H, int W, const float* xs, const float* ys,
+                             const int* flag /*or NULL*/, float* out /*[I,H,W]*/, void* stream);
 
 /* ---- a8 / a9: getPtsFromHeatmap + nms_fast (utils/utils.py:581-609, 653-712), box_nms (:612-650).
  *      stencil: device (2R+1)^2 bytes, 1 = suppressed offset.  pts: [I,3,capacity] float64 rows x,y,conf,

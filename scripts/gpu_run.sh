@@ -19,6 +19,13 @@ for step in "$@"; do
            timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
              python bench.py --steps 2 --warmup 1 --no-cpu --no-adapt --no-semantic --no-graph > gpurun_out/launches.log 2>&1
            echo "launches rc=$?"; python scripts/launch_table.py gpurun_out/launches.csv | head -40 ;;
+    launches_adapt) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_adapt.csv \
+             python scripts/prof_adapt.py > gpurun_out/launches_adapt.log 2>&1
+           echo "launches_adapt rc=$?"; python scripts/launch_table.py gpurun_out/launches_adapt.csv | head -30 ;;
+    ncufull_adapt) # --set full of the warp / aggregation kernels matching regex $arg (scripts/prof_adapt.py, 4 source images)
+           ADAPT_I=4 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$arg" -c 12 -f -o gpurun_out/prof_adapt \
+             python scripts/prof_adapt.py > gpurun_out/ncufull_adapt.log 2>&1
+           echo "ncufull_adapt rc=$?"; ls -la gpurun_out/prof_adapt.ncu-rep ;;
     ncufull) # --set full capture of the kernels matching regex $arg
            timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$arg" -s 4 -c 6 -f -o gpurun_out/prof_full \
              python bench.py --steps 2 --warmup 1 --no-cpu --no-adapt --no-semantic --no-graph > gpurun_out/ncufull.log 2>&1

@@ -81,6 +81,132 @@ combine_heatmap_kernel(const float* __restrict__ heat, const float* __restrict__
 
 
 // ----------------------------------------------------------------------------------------------
+// Bit-mask variant (the default of the batched export path).  The valid masks of homography adaptation are 0/1 images
+// (compute_valid_mask, datasets/Coco.py:284-288); as floats they are half of the aggregation's traffic and half of its
+// gather instructions.  Packed to one bit per pixel (40 bytes per row at W = 320) a warp's mask taps fall into 2-3 cache
+// lines instead of ~6 per load, and the two taps of a row come out of ONE word load.  Arithmetic is unchanged
+// (m in {0.0f, 1.0f}), so results are bit-identical to the float-mask kernel.
+// ----------------------------------------------------------------------------------------------
+// float mask -> bits; flag[0] is set when a value other than 0 / 1 is seen (the aggregation then returns NaN: loud)
+__global__ void __launch_bounds__(256)
+mask_pack_bits_kernel(const float* __restrict__ mask, size_t rows, int W, int WP, uint32_t* __restrict__ bits,
+                      int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per (row, word)
+  if (warp >= rows * WP) return;
+  const size_t row = warp / WP;
+  const int wi = (int)(warp - row * WP), x = wi * 32 + lane;
+  float m = 0.f;
+  if (x < W) m = __ldg(mask + row * W + x);
+  const uint32_t word = __ballot_sync(0xffffffffu, m != 0.f);
+  const bool odd = __any_sync(0xffffffffu, m != 0.f && m != 1.f);
+  if (lane == 0) {
+    bits[warp] = word;
+    if (odd) *flag = 1;
+  }
+}
+
+// compute_valid_mask(erosion_radius = 0) straight to bits: nearest warp of an all-ones image = in-bounds predicate of the
+// rounded source coordinate (same arithmetic as valid_mask_kernel in warp.cu); nothing but 1 bit per pixel reaches HBM
+__global__ void __launch_bounds__(256)
+valid_mask_bits_kernel(int H, int W, int WP, const float* __restrict__ Hinv, const float* __restrict__ xs,
+                       const float* __restrict__ ys, uint32_t* __restrict__ bits) {
+  __shared__ float h[9];
+  const int b = blockIdx.z;
+  if (threadIdx.x < 9) h[threadIdx.x] = Hinv[b * 9 + threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wi = blockIdx.x, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (y >= H) return;
+  const int x = wi * 32 + lane;
+  bool v = false;
+  if (x < W) {
+    float nx, ny;
+    homography_apply(h, __ldg(xs + x), __ldg(ys + y), nx, ny);
+    const float ix = ((nx + 1.f) / 2.f) * (float)(W - 1), iy = ((ny + 1.f) / 2.f) * (float)(H - 1);
+    const float rx = rintf(ix), ry = rintf(iy);
+    v = rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H;
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, v);
+  if (lane == 0) bits[((size_t)b * H + y) * WP + wi] = word;
+}
+
+__global__ void __launch_bounds__(CH_PIX * CH_GROUPS)
+combine_heatmap_bits_kernel(const float* __restrict__ heat, const uint32_t* __restrict__ mbits,
+                            const float* __restrict__ Hinv, int N, int H, int W, int WP, const float* __restrict__ xs,
+                            const float* __restrict__ ys, const int* __restrict__ flag, float* __restrict__ out) {
+  extern __shared__ float sh[];  // N*9 homographies, then 2*CH_PIX*CH_GROUPS partial sums
+  float* hs = sh;
+  float* part = sh + N * 9;
+  heat += (size_t)blockIdx.y * N * H * W;
+  mbits += (size_t)blockIdx.y * N * H * WP;
+  Hinv += (size_t)blockIdx.y * N * 9;
+  out += (size_t)blockIdx.y * H * W;
+  for (int i = threadIdx.x; i < N * 9; i += blockDim.x) hs[i] = Hinv[i];
+  __syncthreads();
+  int lp = threadIdx.x % CH_PIX, g = threadIdx.x / CH_PIX;
+  int tiles_x = (W + 7) / 8;
+  int x = (blockIdx.x % tiles_x) * 8 + (lp & 7), y = (blockIdx.x / tiles_x) * 8 + (lp >> 3);
+  bool inside = x < W && y < H;
+  int pix = y * W + x;
+  float sum_h = 0.f, sum_m = 0.f;
+  if (inside) {
+    float gx = __ldg(xs + x), gy = __ldg(ys + y);
+    size_t plane = (size_t)H * W;
+    for (int n = g; n < N; n += CH_GROUPS) {
+      const float* h = hs + n * 9;
+      float nx, ny;
+      homography_apply(h, gx, gy, nx, ny);
+      float ix = ((nx + 1.f) / 2.f) * (float)(W - 1);
+      float iy = ((ny + 1.f) / 2.f) * (float)(H - 1);
+      float fx = floorf(ix), fy = floorf(iy);
+      if (!(fx >= -1.f && fx < (float)W && fy >= -1.f && fy < (float)H)) continue;
+      int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+      float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+      float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+      bool xin0 = x0 >= 0, xin1 = x1 < W, yin0 = y0 >= 0, yin1 = y1 < H;
+      const float* hp = heat + n * plane;
+      const uint32_t* mp = mbits + (size_t)n * H * WP;
+      const int xa = xin0 ? x0 : x1;  // a column inside the image: its word holds both taps unless they straddle a word
+      const bool straddle = xin0 && xin1 && (x1 & 31) == 0;
+      float ah = 0.f, am = 0.f;
+      if (yin0) {
+        const uint32_t* mr = mp + (size_t)y0 * WP;
+        const uint32_t wa = __ldg(mr + (xa >> 5));
+        const uint32_t wb = straddle ? __ldg(mr + (x1 >> 5)) : wa;
+        size_t r = (size_t)y0 * W;
+        if (xin0) { float m = (float)((wa >> (x0 & 31)) & 1u), w = wx0 * wy0; am += m * w; ah += (__ldg(hp + r + x0) * m) * w; }
+        if (xin1) { float m = (float)((wb >> (x1 & 31)) & 1u), w = wx1 * wy0; am += m * w; ah += (__ldg(hp + r + x1) * m) * w; }
+      }
+      if (yin1) {
+        const uint32_t* mr = mp + (size_t)y1 * WP;
+        const uint32_t wa = __ldg(mr + (xa >> 5));
+        const uint32_t wb = straddle ? __ldg(mr + (x1 >> 5)) : wa;
+        size_t r = (size_t)y1 * W;
+        if (xin0) { float m = (float)((wa >> (x0 & 31)) & 1u), w = wx0 * wy1; am += m * w; ah += (__ldg(hp + r + x0) * m) * w; }
+        if (xin1) { float m = (float)((wb >> (x1 & 31)) & 1u), w = wx1 * wy1; am += m * w; ah += (__ldg(hp + r + x1) * m) * w; }
+      }
+      sum_h += ah;
+      sum_m += am;
+    }
+  }
+  part[threadIdx.x] = sum_h;
+  part[CH_PIX * CH_GROUPS + threadIdx.x] = sum_m;
+  __syncthreads();
+  if (g == 0 && inside) {
+    float th = 0.f, tm = 0.f;
+#pragma unroll
+    for (int q = 0; q < CH_GROUPS; ++q) {
+      th += part[q * CH_PIX + lp];
+      tm += part[CH_PIX * CH_GROUPS + q * CH_PIX + lp];
+    }
+    float v = th / tm;  // 0/0 -> NaN exactly like the reference when no view covers the pixel
+    if (flag && *flag) v = __int_as_float(0x7fc00000);  // the packed mask was not binary
+    out[pix] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Tiled variant: shared-memory staging of the source footprint.
 // The gather kernel above is bound by L1 wavefronts: a warp's 8x4 output patch lands on ~8 different 128 B lines per
 // load under rotation, 8 loads per (pixel, view).  Here a block owns a 32x32 output tile; for every view the source
@@ -303,4 +429,46 @@ extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const f
 extern "C" int ssp_combine_heatmap_tiled(const float* heat, const float* mask, const float* Hinv, int I, int N, int H,
                                          int W, const float* xs, const float* ys, float* out, void* stream) {
   return combine_launch(1, heat, mask, Hinv, I, N, H, W, xs, ys, out, stream);
+}
+
+// ---- bit-mask path ----
+extern "C" size_t ssp_mask_bits_words(int rows, int W) { return (size_t)rows * ((W + 31) / 32); }
+
+// mask [rows, W] float 0/1 -> bits [rows, ceil(W/32)] (bit x & 31 of word x >> 5).  flag (device int, zeroed by the caller) is set
+// when a value other than 0 / 1 was seen.
+extern "C" int ssp_mask_pack_bits(const float* mask, long long rows, int W, uint32_t* bits, int* flag, void* stream) {
+  SSP_REQUIRE(mask && bits && flag, "ssp_mask_pack_bits: null pointer");
+  SSP_REQUIRE(rows > 0 && W > 0, "ssp_mask_pack_bits: bad sizes");
+  const int WP = (W + 31) / 32;
+  const size_t warps = (size_t)rows * WP;
+  SSP_REQUIRE((warps + 7) / 8 <= 0x7fffffffull, "ssp_mask_pack_bits: too many rows");
+  mask_pack_bits_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(mask, (size_t)rows, W, WP, bits, flag);
+  SSP_CUDA_CHECK_LAUNCH("mask_pack_bits_kernel");
+  return SSP_OK;
+}
+
+// compute_valid_mask(image_shape, inv_homography, erosion_radius = 0) as bits [B, H, ceil(W/32)]
+extern "C" int ssp_valid_mask_bits(int B, int H, int W, const float* Hinv, const float* xs, const float* ys, uint32_t* bits,
+                                   void* stream) {
+  SSP_REQUIRE(Hinv && xs && ys && bits, "ssp_valid_mask_bits: null pointer");
+  SSP_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "ssp_valid_mask_bits: bad sizes");
+  const int WP = (W + 31) / 32;
+  dim3 grid(WP, ssp_ceil_div(H, 8), B);
+  valid_mask_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, WP, Hinv, xs, ys, bits);
+  SSP_CUDA_CHECK_LAUNCH("valid_mask_bits_kernel");
+  return SSP_OK;
+}
+
+// combine_heatmap with the valid masks given as bits (flag: optional device int from ssp_mask_pack_bits)
+extern "C" int ssp_combine_heatmap_bits(const float* heat, const uint32_t* mbits, const float* Hinv, int I, int N, int H, int W,
+                                        const float* xs, const float* ys, const int* flag, float* out, void* stream) {
+  SSP_REQUIRE(heat && mbits && Hinv && xs && ys && out, "ssp_combine_heatmap_bits: null pointer");
+  SSP_REQUIRE(I > 0 && I <= 65535 && N > 0 && H > 0 && W > 0, "ssp_combine_heatmap_bits: bad sizes I=%d N=%d H=%d W=%d", I, N, H, W);
+  size_t smem = ((size_t)N * 9 + 2 * CH_PIX * CH_GROUPS) * sizeof(float);
+  SSP_REQUIRE(smem <= 48 * 1024, "ssp_combine_heatmap_bits: N=%d views exceed the shared-memory table (max ~1100)", N);
+  dim3 nblk(ssp_ceil_div(W, 8) * ssp_ceil_div(H, 8), I);
+  combine_heatmap_bits_kernel<<<nblk, CH_PIX * CH_GROUPS, smem, (cudaStream_t)stream>>>(heat, mbits, Hinv, N, H, W, (W + 31) / 32, xs,
+                                                                                          ys, flag, out);
+  SSP_CUDA_CHECK_LAUNCH("combine_heatmap_bits_kernel");
+  return SSP_OK;
 }

@@ -121,6 +121,33 @@ def test_inv_warp_240x320():
             assert_only_rounding_ties(out, ref, Hinv)
 
 
+def test_inv_warp_staged_equals_gather():
+    """The shared-memory staged kernel (default) and the per-pixel gather kernel are the same function, bit for bit:
+    multi-channel images, strong warps (footprints that overflow the staging buffer fall back per tile), identity,
+    and a width that is not a multiple of 4 (always gather)."""
+    rng = np.random.default_rng(5)
+    _, Hinv = homographies(6, 13)
+    Hinv[0] = np.eye(3)
+    Hinv[1] = np.array([[0.3, 0, 0], [0, 0.3, 0], [0, 0, 1]], np.float32)      # 3.3x magnification of the sampled region... footprint small
+    Hinv[2] = np.array([[3.0, 0.4, 0.1], [-0.5, 2.5, 0], [0.2, 0.1, 1]], np.float32)  # minification: footprint overflows the buffer
+    img = synth.uniform((6, 2, 240, 320), 6)
+    for mode in ("bilinear", "nearest"):
+        a = S.inv_warp_image_batch(cu(img), cu(Hinv), device=DEV, mode=mode)
+        b = S.inv_warp_image_batch(cu(img), cu(Hinv), device=DEV, mode=mode, staged=False)
+        assert torch.equal(a, b), mode
+    odd = synth.uniform((2, 1, 47, 61), 7)
+    a = S.inv_warp_image_batch(cu(odd), cu(Hinv[3:5]), device=DEV)
+    close(a, O.inv_warp_image_batch(odd, Hinv[3:5], "bilinear"), atol=1e-5)
+
+
+def test_inv_warp_100x240x320_oracle():
+    """BASELINE size of the warp (100 views of 240x320), bilinear, against the oracle."""
+    _, Hinv = homographies(100, 14)
+    img = synth.uniform((100, 1, 240, 320), 8)
+    out = S.inv_warp_image_batch(cu(img), cu(Hinv), device=DEV).cpu().numpy()
+    close(out, O.inv_warp_image_batch(img, Hinv, "bilinear"), atol=1e-4)
+
+
 # ------------------------------------------------------------------ a3
 def test_valid_mask(golden):
     g = golden("valid_mask")
@@ -226,6 +253,30 @@ def test_combine_heatmap_n100():
     tiled = S.combine_heatmap_batch(cu(np.stack([heat[:, 0], heat[::-1, 0]])), cu(np.stack([Hs, Hs[::-1]])),
                                     cu(np.stack([mask[:, 0], mask[::-1, 0]])), tiled=True).cpu().numpy()
     close(tiled, both, atol=2e-6)
+
+
+def test_combine_heatmap_bit_masks():
+    """Bit-mask aggregation (default of the export path) == float-mask aggregation, bit for bit, at N = 100; masks generated
+    directly as bits from the homographies == compute_valid_mask(r=0) packed; a non-binary mask is refused loudly (NaN)."""
+    I, N = 2, 100
+    Hs, Hinv = homographies(I * N, 31, identity_first=True)
+    heat = synth.uniform((I, N, 240, 320), 9)
+    mask = S.compute_valid_mask(torch.tensor([240, 320]), cu(Hinv), device=DEV).reshape(I, N, 240, 320)
+    Hw = cu(Hs).reshape(I, N, 3, 3)
+    ref = S.combine_heatmap_batch(cu(heat), Hw, mask)
+    bits = S.combine_heatmap_batch(cu(heat), Hw, mask, binary_mask=True)
+    auto = S.combine_heatmap_batch(cu(heat), Hw, None, mask_homographies=cu(Hinv).reshape(I, N, 3, 3))
+    assert torch.equal(torch.nan_to_num(ref, nan=-1.0), torch.nan_to_num(bits, nan=-1.0))
+    assert torch.equal(torch.nan_to_num(ref, nan=-1.0), torch.nan_to_num(auto, nan=-1.0))
+    soft = mask * 0.5
+    assert torch.isnan(S.combine_heatmap_batch(cu(heat), Hw, soft, binary_mask=True)).all()
+    # narrow image: a row of bits does not fill its last word
+    h2 = synth.uniform((1, 5, 24, 40), 10)
+    H2s, H2i = homographies(5, 32)
+    m2 = S.compute_valid_mask(torch.tensor([24, 40]), cu(H2i), device=DEV).reshape(1, 5, 24, 40)
+    a = S.combine_heatmap_batch(cu(h2), cu(H2s).reshape(1, 5, 3, 3), m2)
+    b = S.combine_heatmap_batch(cu(h2), cu(H2s).reshape(1, 5, 3, 3), m2, binary_mask=True)
+    assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
 
 
 # ------------------------------------------------------------------ a8 / a9
