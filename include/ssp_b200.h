@@ -218,6 +218,17 @@ int ssp_sample_desc(const float* coarse, const double* pts, int K, int D, int Hc
 int ssp_nn_match(const float* desc1 /*[D,K1]*/, const float* desc2 /*[D,K2]*/, int D, int K1, int K2,
                  unsigned long long* best1 /*[K1]*/, unsigned long long* best2 /*[K2]*/, void* stream);
 
+/* ---- label warping of the warped training pair: datasets/data_tools.py:37-63 warpLabels (+ :6-34
+ * get_labels_bi), call sites datasets/Coco.py:330,367.  pnts [B,Pmax,2] (x, y) fp32, counts[b] valid points per image
+ * (device), Hpix [B,3,3] = homography_scaling_torch(homography, H, W) (pixel coordinates, computed by the host like the
+ * reference).  labels [B,1,H,W], res [B,H,W,2], labels_bi [B,1,H,W] (bilinear != 0), warped [B,Pmax,2] holding kept[b]
+ * in-bounds warped points in their original order.  Duplicate targets: the last point wins, like the reference's
+ * sequential index_put.  ws: ssp_warp_labels_ws_bytes(). ---- */
+size_t ssp_warp_labels_ws_bytes(int B, int H, int W);
+int ssp_warp_labels(const float* pnts, const int* counts, int B, int Pmax, int H, int W, const float* Hpix, int bilinear,
+                    float* labels, float* res, float* labels_bi /*or NULL*/, float* warped, int* kept, void* ws,
+                    size_t ws_bytes, void* stream);
+
 /* ---- multi-GPU: exchange of the global-batch normalisers of the loss step as ONE kernel over peer memory.
  * The reference is single-GPU; what has to agree with it on a batch sharded by pair is the whole-batch divisors of
  * detector_loss (Train_model_heatmap_all.py:178), descriptor_loss (utils/utils.py:886-887) and sem_loss (:181-193).

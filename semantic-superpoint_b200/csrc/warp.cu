@@ -130,31 +130,83 @@ __device__ __forceinline__ void src_coord(const float* h, float gx, float gy, in
   iy = ((ny + 1.f) / 2.f) * (float)(H - 1);
 }
 
-// Gather kernel (fallback: unaligned images, footprints that do not fit the staging buffer).  8x4-pixel warp patches keep
-// the source footprint of a warp compact under rotation; still ~6 L1 wavefronts per tap load.
+// Gather kernel.  One pixel per thread, 8x4-pixel warp patches (compact source footprint of a warp under rotation).
+// The profile of the first version (ncu, 100 x 240 x 320) showed an INSTRUCTION-bound kernel (~190 SASS instructions per
+// pixel, issue slots 65-85 % busy, DRAM 3 %): everything here is therefore about instruction count -- 32-bit index
+// arithmetic against a per-image base pointer, bounds folded into four predicates, the homography in registers.
+#define IWG_PX 4  // pixels per thread (rows y, y+8, y+16, y+24): 16 independent tap loads in flight per thread
 template <int MODE>  // 0 bilinear, 1 nearest
 __global__ void __launch_bounds__(256)
 inv_warp_gather_kernel(const float* __restrict__ img, int C, int H, int W, const float* __restrict__ Hinv,
                        const float* __restrict__ xs, const float* __restrict__ ys, float* __restrict__ out) {
-  int b = blockIdx.z;
-  __shared__ float h[9];
-  if (threadIdx.x < 9 && threadIdx.y == 0) h[threadIdx.x] = Hinv[b * 9 + threadIdx.x];
-  __syncthreads();
-  int tid = threadIdx.y * 32 + threadIdx.x, wrp = tid >> 5, lane = tid & 31;
-  int x = blockIdx.x * 32 + (wrp & 3) * 8 + (lane & 7);
-  int y = blockIdx.y * 8 + (wrp >> 2) * 4 + (lane >> 3);
-  if (x >= W || y >= H) return;
-  float ix, iy;
-  src_coord(h, __ldg(xs + x), __ldg(ys + y), H, W, ix, iy);
-  size_t plane = (size_t)H * W;
-  for (int c = 0; c < C; ++c) {
-    const float* im = img + ((size_t)b * C + c) * plane;
-    float v = MODE == 0 ? bilinear_zero(im, H, W, ix, iy) : nearest_zero(im, H, W, ix, iy);
-    out[((size_t)b * C + c) * plane + (size_t)y * W + x] = v;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.y * 32 + threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+  const int x = blockIdx.x * 32 + (wrp & 3) * 8 + (lane & 7);
+  const int yb = blockIdx.y * (8 * IWG_PX) + (wrp >> 2) * 4 + (lane >> 3);
+  if (x >= W) return;
+  float h[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h[i] = __ldg(Hinv + b * 9 + i);  // uniform address: one broadcast transaction each
+  const float gx = __ldg(xs + x);
+  const int plane = H * W;
+  const float fW = (float)W, fH = (float)H;
+  int off[IWG_PX][4];    // tap offsets, -1 = tap outside the image (contributes zero)
+  float wgt[IWG_PX][4];
+#pragma unroll
+  for (int k = 0; k < IWG_PX; ++k) {
+    const int y = yb + 8 * k;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { off[k][t] = -1; wgt[k][t] = 0.f; }
+    if (y >= H) continue;
+    float ix, iy;
+    src_coord(h, gx, __ldg(ys + y), H, W, ix, iy);
+    if (MODE == 0) {
+      const float fx = floorf(ix), fy = floorf(iy);
+      if (!(fx >= -1.f && fx < fW && fy >= -1.f && fy < fH)) continue;  // all four taps outside (keeps the int casts in range)
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+      const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
+      const int o = y0 * W + x0;
+      // tap order and arithmetic of ATen's grid_sampler: nw, ne, sw, se
+      if (yin0 && xin0) off[k][0] = o;
+      if (yin0 && xin1) off[k][1] = o + 1;
+      if (yin1 && xin0) off[k][2] = o + W;
+      if (yin1 && xin1) off[k][3] = o + W + 1;
+      wgt[k][0] = wx0 * wy0; wgt[k][1] = wx1 * wy0; wgt[k][2] = wx0 * wy1; wgt[k][3] = wx1 * wy1;
+    } else {
+      const float rx = rintf(ix), ry = rintf(iy);  // std::nearbyint under the default rounding mode = round half to even
+      if (rx >= 0.f && rx < fW && ry >= 0.f && ry < fH) { off[k][0] = (int)ry * W + (int)rx; wgt[k][0] = 1.f; }
+    }
+  }
+  const float* im = img + (size_t)b * C * plane;
+  float* op = out + (size_t)b * C * plane + x;
+  for (int c = 0; c < C; ++c, im += plane, op += plane) {
+    float v[IWG_PX][4];
+#pragma unroll
+    for (int k = 0; k < IWG_PX; ++k)
+#pragma unroll
+      for (int t = 0; t < (MODE == 0 ? 4 : 1); ++t) v[k][t] = off[k][t] >= 0 ? __ldg(im + off[k][t]) : 0.f;
+#pragma unroll
+    for (int k = 0; k < IWG_PX; ++k) {
+      const int y = yb + 8 * k;
+      if (y >= H) continue;
+      float acc;
+      if (MODE == 0) {
+        acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (off[k][t] >= 0) acc += v[k][t] * wgt[k][t];
+      } else {
+        acc = v[k][0];
+      }
+      op[y * W] = acc;
+    }
   }
 }
 
-// Staged kernel (the default): a block owns a 32x32 output tile of one image.  The source footprint of the tile (bounding
+// Staged kernel (north_star's "float4 reads with shared-memory tile staging"; measured on B200 at 100 x 240 x 320: 103 us against
+// 53 us for the gather kernel above -- the warp is instruction-bound, not memory-bound -- so it is opt-in): a block owns a
+// 32x32 output tile of one image.  The source footprint of the tile (bounding
 // box of its four warped corners -- a homography with Z > 0 maps the tile to a convex quadrilateral -- widened to 16-byte
 // columns, +-2 pixels of slack) is copied row by row with 16-byte cp.async (fully coalesced 128-bit reads), the taps
 // come from shared memory, and every output row is one coalesced 128-byte store per warp.  Source coordinates are computed
@@ -283,7 +335,7 @@ extern "C" int ssp_inv_warp_image(const float* img, int B, int C, int H, int W, 
   // 16-byte staging needs rows that start on 16-byte boundaries; anything else takes the gather kernel
   const bool force_gather = (mode & 2) != 0;
   mode &= 1;
-  const bool staged = !force_gather && W % 4 == 0 && (((uintptr_t)img) & 15) == 0;
+  const bool staged = !force_gather && W % 4 == 0 && (((uintptr_t)img) & 15) == 0;  // host side: staged only on request
   if (staged) {
     dim3 grid(ssp_ceil_div(W, IW_TILE), ssp_ceil_div(H, IW_TILE), B);
     if (mode == 0)
@@ -294,7 +346,7 @@ extern "C" int ssp_inv_warp_image(const float* img, int B, int C, int H, int W, 
     return SSP_OK;
   }
   dim3 block(32, 8);
-  dim3 grid(ssp_ceil_div(W, 32), ssp_ceil_div(H, 8), B);
+  dim3 grid(ssp_ceil_div(W, 32), ssp_ceil_div(H, 8 * IWG_PX), B);
   if (mode == 0)
     inv_warp_gather_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(img, C, H, W, Hinv, xs, ys, out);
   else
@@ -367,6 +419,25 @@ valid_mask_kernel(int H, int W, const float* __restrict__ Hinv, const float* __r
   }
 }
 
+// erosion_radius = 0 (homography-adaptation export, datasets/Coco.py:284-288 with the default margin): the mask is the
+// in-bounds predicate itself.  Lean streaming kernel: one pixel per thread, coalesced rows, no tile / halo machinery (the
+// general kernel above spends ~140 instructions per pixel on it).
+__global__ void __launch_bounds__(256)
+valid_mask_r0_kernel(int H, int W, const float* __restrict__ Hinv, const float* __restrict__ xs,
+                     const float* __restrict__ ys, float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  float h[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h[i] = __ldg(Hinv + b * 9 + i);
+  float ix, iy;
+  src_coord(h, __ldg(xs + x), __ldg(ys + y), H, W, ix, iy);
+  const float rx = rintf(ix), ry = rintf(iy);
+  const bool v = rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H;
+  out[((size_t)b * H + y) * W + x] = v ? 1.f : 0.f;
+}
+
 extern "C" int ssp_valid_mask(int B, int H, int W, const float* Hinv, const float* xs, const float* ys,
                               const uint8_t* kern, int kh, int kw, int ax, int ay, float* out, void* stream) {
   SSP_REQUIRE(Hinv && xs && ys && out, "ssp_valid_mask: null pointer");
@@ -375,6 +446,12 @@ extern "C" int ssp_valid_mask(int B, int H, int W, const float* Hinv, const floa
                                        ay >= 0 && ay < kh),
               "ssp_valid_mask: bad structuring element kh=%d kw=%d anchor=(%d,%d)", kh, kw, ax, ay);
   dim3 block(32, 8);
+  if (kh == 0 && kw == 0) {
+    dim3 grid0(ssp_ceil_div(W, 32), ssp_ceil_div(H, 8), B);
+    valid_mask_r0_kernel<<<grid0, block, 0, (cudaStream_t)stream>>>(H, W, Hinv, xs, ys, out);
+    SSP_CUDA_CHECK_LAUNCH("valid_mask_r0_kernel");
+    return SSP_OK;
+  }
   dim3 grid(ssp_ceil_div(W, VM_TILE), ssp_ceil_div(H, VM_TILE), B);
   valid_mask_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(H, W, Hinv, xs, ys, kern, kh, kw, ax, ay, out);
   SSP_CUDA_CHECK_LAUNCH("valid_mask_kernel");

@@ -93,6 +93,29 @@ def adaptation_step(semi, inv_homographies, mask_2D=None, conf_thresh=0.015, nms
     return out
 
 
+@torch.no_grad()
+def collate_warped_pair(img, pnts_list, homographies, erosion_radius=3, bilinear=True):
+    """The warped half of a training batch, built on the device from the unwarped images and their keypoints -- what
+    datasets/Coco.py:341-392 does per sample in the DataLoader workers (inv_warp_image, warpLabels, compute_valid_mask):
+    img [B,1,H,W], pnts_list = B arrays [P,2] (x, y), homographies [B,3,3] (normalised coordinates, already inverted as in
+    Coco.py:345).  Returns the batch keys of the reference: warped_img, warped_labels, warped_res [B,2,H,W],
+    warped_labels_bi, warped_valid_mask [B,1,H,W], homographies, inv_homographies.  (Photometric augmentation and the
+    gaussian label blur are imgaug calls and stay where they are.)"""
+    dev = img.device
+    B, _, H, W = img.shape
+    Hm = torch.as_tensor(homographies, dtype=torch.float32).reshape(B, 3, 3)
+    Hinv = torch.inverse(Hm.cpu()).to(dev)  # the reference inverts on the CPU (np.linalg.inv / torch.inverse per sample)
+    Hm = Hm.to(dev)
+    warped_img = U.inv_warp_image_batch(img, Hinv, device=dev, mode="bilinear")
+    lab = U.warp_labels_batch(pnts_list, H, W, Hm, bilinear=bilinear, device=dev)
+    mask = U.compute_valid_mask(torch.tensor([H, W]), Hinv, device=dev, erosion_radius=erosion_radius).unsqueeze(1)
+    out = {"warped_img": warped_img, "warped_labels": lab["labels"], "warped_res": lab["res"].permute(0, 3, 1, 2).contiguous(),
+           "warped_valid_mask": mask, "homographies": Hm, "inv_homographies": Hinv, "warped_pnts": lab["warped_pnts"]}
+    if bilinear:
+        out["warped_labels_bi"] = lab["labels_bi"]
+    return out
+
+
 class GraphedLossStep(object):
     """loss_step forward + backward captured once into a CUDA graph and replayed (the step is a chain of ~25 short
     kernels; replay removes the per-launch host cost).  Inputs are copied into static buffers; outputs (loss

@@ -19,7 +19,7 @@ __all__ = [
     "warp_points", "filter_points", "warp_points_filter", "warp_keypoints", "inv_warp_image_batch", "inv_warp_image",
     "compute_valid_mask", "ellipse_kernel", "labels2Dto3D", "getMasks", "detector_loss", "flattenDetection",
     "combine_heatmap", "getPtsFromHeatmap", "nms_fast", "box_nms", "descriptor_loss", "normPts", "denormPts",
-    "homography_scaling_torch", "homography_scaling",
+    "homography_scaling_torch", "homography_scaling", "warpLabels", "warp_labels_batch",
 ]
 
 _grid_cache = {}
@@ -164,9 +164,9 @@ def denormPts(pts, shape):
 # ------------------------------------------------------------------------------------------------
 # a2 / a3  image warps
 # ------------------------------------------------------------------------------------------------
-def inv_warp_image_batch(img, mat_homo_inv, device="cpu", mode="bilinear", staged=True):
+def inv_warp_image_batch(img, mat_homo_inv, device="cpu", mode="bilinear", staged=False):
     """reference: utils/utils.py:347-385.  img [B,C,H,W] (2-D/3-D viewed as [1,1,H,W]), H^-1 [B,3,3] / [3,3].
-    staged=False forces the per-pixel gather kernel instead of the shared-memory staged one (same results)."""
+    staged=True selects the shared-memory staged kernel instead of the per-pixel gather (same results, measured slower)."""
     if img.dim() == 2 or img.dim() == 3:
         img = img.view(1, 1, img.shape[0], img.shape[1])
     if mat_homo_inv.dim() == 2:
@@ -182,7 +182,7 @@ def inv_warp_image_batch(img, mat_homo_inv, device="cpu", mode="bilinear", stage
         raise RuntimeError("inv_warp_image_batch: %d images but %d homographies" % (B, Hm.shape[0]))
     out = torch.empty_like(x)
     call("ssp_inv_warp_image", ptr(x), B, C, H, W, ptr(Hm), ptr(_linspace_grid(W, dev)), ptr(_linspace_grid(H, dev)),
-         (0 if mode == "bilinear" else 1) + (0 if staged else 2), ptr(out), stream_of(out))
+         (0 if mode == "bilinear" else 1) + (0 if staged else 2), ptr(out), stream_of(out))  # +2: gather kernel
     return out.to(out_dev)
 
 
@@ -585,3 +585,51 @@ def nn_match_two_way(desc1, desc2, nn_thresh):
     matches[1, :] = idx[keep]
     matches[2, :] = scores[keep]
     return matches
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f rank 4: label warping of the warped training pair (dataset side, moved to the device)
+# ------------------------------------------------------------------------------------------------
+def warp_labels_batch(pnts_list, H, W, homographies, bilinear=False, device="cuda"):
+    """warpLabels for a batch of images in one launch (the GPU-collate form).
+
+    pnts_list: list of B arrays / tensors [P_b, 2] (x, y); homographies [B,3,3] in normalised coordinates.
+    Returns dict(labels [B,1,H,W], res [B,H,W,2], warped_pnts = list of [M_b,2] tensors[, labels_bi [B,1,H,W]]), on the device."""
+    dev = _cuda_device(device, homographies if isinstance(homographies, torch.Tensor) else None)
+    B = len(pnts_list)
+    Hn = torch.as_tensor(homographies, dtype=torch.float32).reshape(B, 3, 3).cpu()
+    # homography_scaling_torch on the host, op for op as the reference (utils/utils.py:297-300): 3x3 matrices
+    Hpix = torch.stack([homography_scaling_torch(Hn[b], H, W) for b in range(B)]).to(dev).contiguous()
+    counts_h = [int(len(p)) for p in pnts_list]
+    Pmax = max(max(counts_h), 1)
+    pts = torch.zeros((B, Pmax, 2), dtype=torch.float32)
+    for b, p in enumerate(pnts_list):
+        if counts_h[b]:
+            pts[b, :counts_h[b]] = torch.as_tensor(np.asarray(p)[:, :2] if not isinstance(p, torch.Tensor) else p[:, :2].cpu(),
+                                                   dtype=torch.float32)
+    pts = pts.to(dev)
+    counts = torch.tensor(counts_h, dtype=torch.int32, device=dev)
+    labels = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    res = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
+    lbi = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if bilinear else None
+    warped = torch.empty((B, Pmax, 2), dtype=torch.float32, device=dev)
+    kept = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = _lib.load().ssp_warp_labels_ws_bytes(B, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    call("ssp_warp_labels", ptr(pts), ptr(counts), B, Pmax, int(H), int(W), ptr(Hpix), 1 if bilinear else 0, ptr(labels),
+         ptr(res), ptr(lbi), ptr(warped), ptr(kept), ptr(ws), nbytes, stream_of(labels))
+    kept_h = kept.cpu().tolist()  # the reference returns the filtered point list: its length is data dependent (one sync)
+    out = {"labels": labels, "res": res, "warped_pnts": [warped[b, :kept_h[b]] for b in range(B)]}
+    if bilinear:
+        out["labels_bi"] = lbi
+    return out
+
+
+def warpLabels(pnts, H, W, homography, bilinear=False):
+    """reference: datasets/data_tools.py:37-63 (same signature and dict of results: labels [1,H,W], res [H,W,2], warped_pnts
+    [M,2] and, with bilinear=True, labels_bi [1,H,W]); results are returned on the CPU like the reference's."""
+    o = warp_labels_batch([pnts], H, W, torch.as_tensor(homography, dtype=torch.float32).reshape(1, 3, 3), bilinear)
+    out = {"labels": o["labels"][0].cpu(), "res": o["res"][0].cpu(), "warped_pnts": o["warped_pnts"][0].cpu()}
+    if bilinear:
+        out["labels_bi"] = o["labels_bi"][0].cpu()
+    return out

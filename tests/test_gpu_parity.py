@@ -132,7 +132,7 @@ def test_inv_warp_staged_equals_gather():
     Hinv[2] = np.array([[3.0, 0.4, 0.1], [-0.5, 2.5, 0], [0.2, 0.1, 1]], np.float32)  # minification: footprint overflows the buffer
     img = synth.uniform((6, 2, 240, 320), 6)
     for mode in ("bilinear", "nearest"):
-        a = S.inv_warp_image_batch(cu(img), cu(Hinv), device=DEV, mode=mode)
+        a = S.inv_warp_image_batch(cu(img), cu(Hinv), device=DEV, mode=mode, staged=True)
         b = S.inv_warp_image_batch(cu(img), cu(Hinv), device=DEV, mode=mode, staged=False)
         assert torch.equal(a, b), mode
     odd = synth.uniform((2, 1, 47, 61), 7)
@@ -666,3 +666,57 @@ def test_loss_step_and_adaptation_step():
     assert pts.shape == ref.shape
     # aggregated heat values differ in the last ulp between CPU and GPU summation: compare the sets
     assert np.array_equal(pts[:, :2], ref[:, :2]) or len(set(map(tuple, pts[:, :2])) ^ set(map(tuple, ref[:, :2]))) <= 4
+
+
+# ------------------------------------------------------------------ 8f rank 4: label warping / GPU collate
+def test_warp_labels_golden(golden):
+    """datasets/data_tools.warpLabels of the live reference (fixture), single image and batched, incl. the bilinear label map
+    and the last-wins rule for points that land on one pixel."""
+    g = golden("warp_labels")
+    for i in range(2):
+        o = S.warpLabels(g["pts"], 48, 64, torch.from_numpy(g["H"][i]), bilinear=True)
+        assert np.array_equal(o["labels"].numpy(), g["labels_%d" % i])
+        close(o["warped_pnts"], g["warped_pnts_%d" % i], atol=2e-5)
+        close(o["res"], g["res_%d" % i], atol=2e-5)
+        close(o["labels_bi"], g["labels_bi_%d" % i], atol=2e-5)
+    both = S.warp_labels_batch([g["pts"], g["pts"][:50]], 48, 64, torch.from_numpy(g["H"]), bilinear=True)
+    assert np.array_equal(both["labels"][0].cpu().numpy(), g["labels_0"])
+    ref1 = O.warp_labels(g["pts"][:50], 48, 64, g["H"][1], bilinear=True)
+    assert np.array_equal(both["labels"][1].cpu().numpy(), ref1["labels"])
+    close(both["labels_bi"][1], ref1["labels_bi"], atol=2e-5)
+    close(both["res"][1], ref1["res"], atol=2e-5)
+    close(both["warped_pnts"][1], ref1["warped_pnts"], atol=2e-5)
+
+
+def test_warp_labels_240x320_collisions_and_collate():
+    """BASELINE-size images with 600 keypoints each (top_k of the export) and deliberate duplicates: same maps as the oracle;
+    the collate helper returns the reference's batch keys with the right shapes."""
+    B, H, W = 4, 240, 320
+    Hs, Hinv = homographies(B, 41)
+    pts = []
+    for b in range(B):
+        p = np.stack([np.floor(synth.uniform((600,), 50 + b) * W), np.floor(synth.uniform((600,), 60 + b) * H)], 1)
+        p[300:320] = p[:20]  # duplicates: the later copy wins (same value here, but exercises the winner path)
+        p[320:330] = p[100:110] + np.array([0.4, 0.3])  # truncated to the same integer pixel as the originals
+        pts.append(p)
+    out = S.warp_labels_batch(pts, H, W, torch.from_numpy(Hs), bilinear=True)
+    for b in range(B):
+        ref = O.warp_labels(pts[b], H, W, Hs[b], bilinear=True)
+        wp = ref["warped_pnts"].astype(np.float64)
+        close(out["warped_pnts"][b], ref["warped_pnts"], atol=2e-4)
+        # a warped coordinate within 1e-3 of k + 0.5 (rounding tie) or of an integer (truncation tie of the bilinear base) may
+        # legitimately land one pixel over between two fp32 evaluations of the pixel homography: such points are excused
+        frac = wp - np.floor(wp)
+        ties = int(((np.abs(frac - 0.5) < 1e-3) | (frac < 1e-3) | (frac > 1 - 1e-3)).any(axis=1).sum())
+        lab = out["labels"][b].cpu().numpy()
+        assert (lab != ref["labels"]).sum() <= 2 * ties
+        same = (lab == ref["labels"])[0]
+        assert (np.abs(out["res"][b].cpu().numpy() - ref["res"]).max(axis=2)[same] < 2e-4).all()
+        bad_bi = np.abs(out["labels_bi"][b].cpu().numpy() - ref["labels_bi"]) > 2e-4
+        assert bad_bi.sum() <= 8 * ties
+    img = cu(synth.uniform((B, 1, H, W), 70))
+    col = S.step.collate_warped_pair(img, pts, torch.from_numpy(Hs), erosion_radius=3, bilinear=True)
+    assert col["warped_img"].shape == (B, 1, H, W) and col["warped_res"].shape == (B, 2, H, W)
+    assert col["warped_valid_mask"].shape == (B, 1, H, W) and col["warped_labels_bi"].shape == (B, 1, H, W)
+    close(col["warped_img"], O.inv_warp_image_batch(img.cpu().numpy(), np.linalg.inv(Hs).astype(np.float32), "bilinear"), atol=1e-4)
+    assert torch.equal(col["warped_labels"], out["labels"])
