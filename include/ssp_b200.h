@@ -218,6 +218,21 @@ int ssp_sample_desc(const float* coarse, const double* pts, int K, int D, int Hc
 int ssp_nn_match(const float* desc1 /*[D,K1]*/, const float* desc2 /*[D,K2]*/, int D, int K1, int K2,
                  unsigned long long* best1 /*[K1]*/, unsigned long long* best2 /*[K2]*/, void* stream);
 
+/* ---- sparse descriptor loss: utils/loss_functions/sparse_loss.py:65-284 with
+ * pixelwise_contrastive_loss.py:140-265 (dist "cos", method "1d").  The reference samples K matches and Kn non-matches per
+ * image on the host; the lists ia / ib [B, K+Kn] (int32 cell indices into `descriptors` / `descriptors_warped`, matches
+ * first) are inputs.  Dt / Dwt are the descriptors in cell-major layout [B, Nc, Dch] (ssp_transpose_batched of NCHW).
+ * out3 = batch means {loss, match, nonmatch}; dots [B,K+Kn] and stats [B,4] {match, nonmatch, loss, hard count} feed the
+ * backward, which scatters into cell-major gradients dDt / dDwt (zeroed by the call; fp32 atomics). ---- */
+int ssp_transpose_batched(const float* src /*[B,rows,cols]*/, int B, int rows, int cols, float* dst /*[B,cols,rows]*/,
+                          void* stream);
+int ssp_sparse_desc_loss_fwd(const float* Dt, const float* Dwt, const int* ia, const int* ib, int B, int Nc, int Dch, int K,
+                             int Kn, float lamda, float mpos, float mneg, float* dots, float* stats, float* out3,
+                             void* stream);
+int ssp_sparse_desc_loss_bwd(const float* Dt, const float* Dwt, const int* ia, const int* ib, const float* dots,
+                             const float* stats, const float* g3 /*device [3]*/, int B, int Nc, int Dch, int K, int Kn,
+                             float lamda, float mpos, float mneg, float* dDt, float* dDwt, void* stream);
+
 /* ---- label warping of the warped training pair: datasets/data_tools.py:37-63 warpLabels (+ :6-34
  * get_labels_bi), call sites datasets/Coco.py:330,367.  pnts [B,Pmax,2] (x, y) fp32, counts[b] valid points per image
  * (device), Hpix [B,3,3] = homography_scaling_torch(homography, H, W) (pixel coordinates, computed by the host like the

@@ -655,3 +655,46 @@ def warp_labels(pnts, H, W, homography, bilinear=False):
     outs["res"] = _scatter_last_wins(H, W, warped, (warped - np.round(warped)).astype(f32), channels=2)
     outs["warped_pnts"] = warped
     return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f rank 2: sparse descriptor loss, evaluation half (the sampled index lists are inputs)
+# ------------------------------------------------------------------------------------------------
+def sparse_descriptor_loss(descriptors, descriptors_warped, matches_a, matches_b, non_matches_a, non_matches_b, lamda_d=250,
+                           grad=None):
+    """utils/loss_functions/sparse_loss.py:65-284 with pixelwise_contrastive_loss.py:140-265 (dist="cos", method="1d"), given
+    the index lists the reference samples: [B,K] matches and [B,K*n] non-matches (cell index u + v*Wc in each image).
+      match_b = 1/K sum max(1 - dot, 0);  nonmatch_b = sum max(dot - 0.2, 0) / (#nonzero + 1);  loss_b = lamda_d match_b + nonmatch_b
+    Returns the batch means (loss, match, nonmatch); grad = (g_loss, g_match, g_nonmatch) adds d/d descriptors, d/d descriptors_warped
+    (torch.clamp passes the gradient at the bound; the hard-negative count is a constant)."""
+    D = np.asarray(descriptors, dtype=np.float64)
+    Dw = np.asarray(descriptors_warped, dtype=np.float64)
+    B, Dch, Hc, Wc = D.shape
+    Nc = Hc * Wc
+    A, Bm = D.reshape(B, Dch, Nc), Dw.reshape(B, Dch, Nc)
+    ma, mb, na, nb = (np.asarray(x, dtype=np.int64) for x in (matches_a, matches_b, non_matches_a, non_matches_b))
+    K = ma.shape[1]
+    loss, match, non = [], [], []
+    if grad is not None:
+        gl, gm, gn = (float(g) for g in grad)
+        dD, dDw = np.zeros_like(A), np.zeros_like(Bm)
+    for b in range(B):
+        dm = (A[b][:, ma[b]] * Bm[b][:, mb[b]]).sum(0).astype(f32)
+        dn = (A[b][:, na[b]] * Bm[b][:, nb[b]]).sum(0).astype(f32)
+        tm = np.maximum(f32(1.0) - dm, f32(0))
+        tn = np.maximum(dn - f32(0.2), f32(0))
+        hard = int(np.count_nonzero(tn))
+        m_b = f32(1.0 / K) * tm.sum(dtype=f32)
+        n_b = tn.sum(dtype=f32) / f32(hard + 1)
+        match.append(m_b); non.append(n_b); loss.append(f32(lamda_d) * m_b + n_b)
+        if grad is not None:
+            cm = np.where(f32(1.0) - dm >= 0, -(gl * lamda_d + gm) / (K * B), 0.0)
+            cn = np.where(dn - f32(0.2) >= 0, (gl + gn) / ((hard + 1) * B), 0.0)
+            np.add.at(dD[b].T, ma[b], (cm[None, :] * Bm[b][:, mb[b]]).T)
+            np.add.at(dDw[b].T, mb[b], (cm[None, :] * A[b][:, ma[b]]).T)
+            np.add.at(dD[b].T, na[b], (cn[None, :] * Bm[b][:, nb[b]]).T)
+            np.add.at(dDw[b].T, nb[b], (cn[None, :] * A[b][:, na[b]]).T)
+    out = (f32(np.mean(np.array(loss, f32))), f32(np.mean(np.array(match, f32))), f32(np.mean(np.array(non, f32))))
+    if grad is not None:
+        return out + (dD.reshape(D.shape).astype(f32), dDw.reshape(D.shape).astype(f32))
+    return out

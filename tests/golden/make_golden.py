@@ -168,7 +168,48 @@ def gen_eval_keypoints():
          repeatability=np.float64(rep), loc_err=np.float64(loc), repeatability_1000=np.float64(rep1k), loc_err_1000=np.float64(loc1k))
 
 
+def gen_sparse():
+    """utils/loss_functions/sparse_loss.batch_descriptor_loss_sparse of the unmodified reference on CPU.  The
+    index lists it samples internally are captured by wrapping the two PixelwiseContrastiveLoss static methods (they are called
+    with the lists); losses and gradients are the reference's own autograd results.  Image 1 uses a strongly shrinking
+    homography so that fewer than num_matching_attempts cells match (the padding branch of crop_or_pad_choice)."""
+    import utils.loss_functions.sparse_loss as SL
+    from utils.loss_functions.pixelwise_contrastive_loss import PixelwiseContrastiveLoss as P
+    cap = {"m": [], "n": []}
+    om, on = P.match_loss, P.non_match_descriptor_loss
+
+    def wm(a, b, ma, mb, **kw):
+        cap["m"].append((ma.clone(), mb.clone()))
+        return om(a, b, ma, mb, **kw)
+
+    def wn(a, b, na, nb, **kw):
+        cap["n"].append((na.clone(), nb.clone()))
+        return on(a, b, na, nb, **kw)
+
+    P.match_loss, P.non_match_descriptor_loss = staticmethod(wm), staticmethod(wn)
+    B, Hc, Wc, Dch = 3, 30, 40, 256
+    Hs, _ = ref_homographies(B, 17)
+    Hs[1] = np.array([[2.2, 0.1, 0.05], [-0.1, 2.4, -0.02], [0.0, 0.0, 1.0]], np.float32)  # maps ~1/5 of the cells into the image
+    D = torch.from_numpy(synth.unit_descriptors(B, Dch, Hc, Wc, 151, smooth=0.3)).requires_grad_(True)
+    Dw = torch.from_numpy(synth.unit_descriptors(B, Dch, Hc, Wc, 152, smooth=0.3)).requires_grad_(True)
+    torch.manual_seed(123)
+    np.random.seed(321)
+    loss, _none, pos, neg = SL.batch_descriptor_loss_sparse(D, Dw, torch.from_numpy(Hs), device="cpu", lamda_d=250,
+                                                             num_matching_attempts=1000, num_masked_non_matches_per_match=10)
+    g = np.array([1.0, 0.5, 0.25], np.float32)
+    (g[0] * loss + g[1] * pos + g[2] * neg).backward()
+    save("sparse_loss", H=Hs, seed_torch=np.int64(123), seed_numpy=np.int64(321), g=g,
+         matches_a=torch.stack([m[0] for m in cap["m"]]).numpy(), matches_b=torch.stack([m[1] for m in cap["m"]]).numpy(),
+         non_a=torch.stack([n[0] for n in cap["n"]]).numpy().astype(np.int32), non_b=torch.stack([n[1] for n in cap["n"]]).numpy().astype(np.int32),
+         loss=loss.detach().numpy(), pos=pos.detach().numpy(), neg=neg.detach().numpy(),
+         dD_sample=D.grad.numpy()[:, :, ::3, ::4].copy(), dDw_sample=Dw.grad.numpy()[:, :, ::3, ::4].copy(),
+         dD_abs_sum=np.float64(np.abs(D.grad.numpy()).sum()), dDw_abs_sum=np.float64(np.abs(Dw.grad.numpy()).sum()))
+    P.match_loss, P.non_match_descriptor_loss = staticmethod(om), staticmethod(on)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sparse":
+        return gen_sparse()
     if len(sys.argv) > 1 and sys.argv[1] == "eval_keypoints":
         return gen_eval_keypoints()
     if len(sys.argv) > 1 and sys.argv[1] == "warp_labels":

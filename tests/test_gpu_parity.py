@@ -720,3 +720,46 @@ def test_warp_labels_240x320_collisions_and_collate():
     assert col["warped_valid_mask"].shape == (B, 1, H, W) and col["warped_labels_bi"].shape == (B, 1, H, W)
     close(col["warped_img"], O.inv_warp_image_batch(img.cpu().numpy(), np.linalg.inv(Hs).astype(np.float32), "bilinear"), atol=1e-4)
     assert torch.equal(col["warped_labels"], out["labels"])
+
+
+# ------------------------------------------------------------------ 8f rank 2: sparse descriptor loss
+def test_sparse_descriptor_loss_golden(golden):
+    """Kernels on the index lists of the live reference: its losses and (sampled) gradients; then the drop-in
+    batch_descriptor_loss_sparse under the reference's RNG seeds returns the reference's own numbers."""
+    g = golden("sparse_loss")
+    D = synth.unit_descriptors(3, 256, 30, 40, 151, smooth=0.3)
+    Dw = synth.unit_descriptors(3, 256, 30, 40, 152, smooth=0.3)
+    Dt, Dwt = cu(D).requires_grad_(True), cu(Dw).requires_grad_(True)
+    loss, pos, neg = S.sparse.sparse_loss_from_lists(Dt, Dwt, g["matches_a"], g["matches_b"], g["non_a"], g["non_b"], 250)
+    close(loss, g["loss"]); close(pos, g["pos"]); close(neg, g["neg"])
+    gv = g["g"]
+    (float(gv[0]) * loss + float(gv[1]) * pos + float(gv[2]) * neg).backward()
+    scale = np.abs(g["dD_sample"]).max()
+    close(Dt.grad[:, :, ::3, ::4], g["dD_sample"], atol=1e-4 * scale); close(Dwt.grad[:, :, ::3, ::4], g["dDw_sample"], atol=1e-4 * scale)
+    np.testing.assert_allclose(float(Dt.grad.abs().sum()), float(g["dD_abs_sum"]), rtol=1e-4)
+    torch.manual_seed(int(g["seed_torch"]))
+    np.random.seed(int(g["seed_numpy"]))
+    l2, none, p2, n2 = S.batch_descriptor_loss_sparse(cu(D), cu(Dw), torch.from_numpy(g["H"]), device=DEV, lamda_d=250)
+    assert none is None
+    close(l2, g["loss"]); close(p2, g["pos"]); close(n2, g["neg"])
+    l1 = S.descriptor_loss_sparse(cu(D[0]), cu(Dw[0]), torch.from_numpy(g["H"][0]), device=DEV)
+    assert len(l1) == 3 and float(l1[0]) > 0
+
+
+def test_sparse_descriptor_loss_b32_oracle():
+    """BASELINE batch (32 pairs, 30x40 cells, 1000 matches x 10 non-matches each) against the oracle, with gradients."""
+    B = 32
+    D = synth.unit_descriptors(B, 256, 30, 40, 161, smooth=0.3)
+    Dw = synth.unit_descriptors(B, 256, 30, 40, 162, smooth=0.3)
+    Hs, _ = homographies(B, 51)
+    torch.manual_seed(5)
+    np.random.seed(6)
+    lists = [S.sparse.sample_correspondences(torch.from_numpy(Hs[i]), 30, 40) for i in range(B)]
+    ma, mb, na, nb = (torch.stack([l[j] for l in lists]).numpy() for j in range(4))
+    ref = O.sparse_descriptor_loss(D, Dw, ma, mb, na, nb, 250, grad=(1.0, 0.5, 0.25))
+    Dt, Dwt = cu(D).requires_grad_(True), cu(Dw).requires_grad_(True)
+    loss, pos, neg = S.sparse.sparse_loss_from_lists(Dt, Dwt, ma, mb, na, nb, 250)
+    close(loss, ref[0]); close(pos, ref[1]); close(neg, ref[2])
+    (loss + 0.5 * pos + 0.25 * neg).backward()
+    for got, want in ((Dt.grad, ref[3]), (Dwt.grad, ref[4])):
+        close(got, want, atol=1e-4 * np.abs(want).max())

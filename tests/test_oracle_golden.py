@@ -192,3 +192,25 @@ def test_eval_keypoints_and_repeatability(golden):
     assert rep == float(g["repeatability"]) and loc == float(g["loc_err"])
     rep, loc = O.compute_repeatability(g["kp"], g["warped_prob"], g["H"], shape, keep_k_points=1000)
     assert rep == float(g["repeatability_1000"]) and loc == float(g["loc_err_1000"])
+
+
+def test_sparse_descriptor_loss_oracle_and_sampler(golden):
+    """8f rank 2: the oracle's evaluation of the sparse loss on the index lists the live reference sampled (captured inside its own
+    call), incl. gradients; and the product's host-side sampler reproduces those lists call for call under the same RNG
+    state (torch + numpy seeds), including the padding branch (image 1 matches only 232 distinct cells)."""
+    import torch
+    from ssp_b200 import sparse, synth
+    g = golden("sparse_loss")
+    D = synth.unit_descriptors(3, 256, 30, 40, 151, smooth=0.3)
+    Dw = synth.unit_descriptors(3, 256, 30, 40, 152, smooth=0.3)
+    r = O.sparse_descriptor_loss(D, Dw, g["matches_a"], g["matches_b"], g["non_a"], g["non_b"], 250, grad=tuple(g["g"]))
+    close(r[0], g["loss"], rtol=1e-6); close(r[1], g["pos"], rtol=1e-6); close(r[2], g["neg"], rtol=1e-6)
+    close(r[3][:, :, ::3, ::4], g["dD_sample"], atol=1e-6); close(r[4][:, :, ::3, ::4], g["dDw_sample"], atol=1e-6)
+    np.testing.assert_allclose(np.abs(r[3]).sum(), float(g["dD_abs_sum"]), rtol=1e-5)
+    torch.manual_seed(int(g["seed_torch"]))
+    np.random.seed(int(g["seed_numpy"]))
+    for i in range(3):
+        l = sparse.sample_correspondences(torch.from_numpy(g["H"][i]), 30, 40, 1000, 10)
+        for got, key in zip(l, ("matches_a", "matches_b", "non_a", "non_b")):
+            assert np.array_equal(got.numpy(), g[key][i]), (i, key)
+    assert len(np.unique(g["matches_a"][1])) < 1000  # the padded image
