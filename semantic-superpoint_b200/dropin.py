@@ -14,13 +14,37 @@ import sys
 
 from . import utils as _u
 
-# reference attribute -> replacement
-UTILS_NAMES = [
-    "warp_points", "filter_points", "inv_warp_image_batch", "inv_warp_image", "compute_valid_mask", "labels2Dto3D",
-    "flattenDetection", "getPtsFromHeatmap", "nms_fast", "box_nms", "descriptor_loss", "normPts", "denormPts",
-    "homography_scaling_torch",
-]
+# reference attribute -> replacement.
+# TRAINER_NAMES are called from the training / export process itself.  DATASET_NAMES are the ones the reference datasets capture
+# in `init_var` and call from `__getitem__` (datasets/Coco.py:99-111, Coco_sem.py:120-123, SyntheticDataset_gaussian.py:181,
+# data_tools.py:38-40), i.e. inside forked DataLoader workers, where CUDA cannot be initialised: they are bound to wrappers that
+# run the CUDA kernel in the main process and hand the call back to the saved reference function inside a worker, so `install()` is safe with `workers_train > 0`.
+TRAINER_NAMES = ["labels2Dto3D", "flattenDetection", "getPtsFromHeatmap", "nms_fast", "box_nms", "descriptor_loss", "normPts",
+                 "denormPts", "homography_scaling_torch"]
+DATASET_NAMES = ["warp_points", "filter_points", "inv_warp_image_batch", "inv_warp_image", "compute_valid_mask"]
+UTILS_NAMES = DATASET_NAMES + TRAINER_NAMES
 _saved = []
+
+
+def _in_worker():
+    """True inside a DataLoader worker process -- the one place the reference's own CPU function is handed the call back
+    (a forked worker cannot create a CUDA context).  Everywhere else the CUDA path runs, and fails loudly without a GPU."""
+    import torch.utils.data as tud
+    return tud.get_worker_info() is not None
+
+
+def _worker_safe(ours, theirs):
+    """`ours` in the main process, the reference's own CPU function inside DataLoader workers."""
+    if theirs is None:
+        return ours
+
+    def f(*a, **k):
+        return theirs(*a, **k) if _in_worker() else ours(*a, **k)
+
+    f.__name__ = getattr(ours, "__name__", "f")
+    f.__doc__ = ours.__doc__
+    f.__wrapped__ = ours
+    return f
 
 
 def _bind(obj, name, fn, bound):
@@ -30,16 +54,20 @@ def _bind(obj, name, fn, bound):
     bound.append("%s.%s" % (getattr(obj, "__name__", type(obj).__name__), name))
 
 
-def install(utils_module=None, trainer_class=None, frontend_class=None, export_module=None, tracker_class=None):
+def install(utils_module=None, trainer_class=None, frontend_class=None, export_module=None, tracker_class=None,
+            sparse_module=None, data_tools_module=None):
     """Patch `utils.utils` (imported from sys.path unless given) and, when passed, the trainer class
     (`Train_model_heatmap_all`: detector_loss, getMasks, sem_loss), the inference front-end class
     (`SuperPointFrontend_torch`: getPtsFromHeatmap, nms_fast, sample_desc_from_points), the tracker class
-    (`PointTracker`: nn_match_two_way) and the `export` module (combine_heatmap)."""
+    (`PointTracker`: nn_match_two_way), the `export` module (combine_heatmap), `utils.loss_functions.sparse_loss`
+    (batch_descriptor_loss_sparse / descriptor_loss_sparse) and `datasets.data_tools` (warpLabels)."""
     bound = []
     if utils_module is None:
         utils_module = importlib.import_module("utils.utils")
-    for n in UTILS_NAMES:
+    for n in TRAINER_NAMES:
         _bind(utils_module, n, getattr(_u, n), bound)
+    for n in DATASET_NAMES:
+        _bind(utils_module, n, _worker_safe(getattr(_u, n), getattr(utils_module, n, None)), bound)
     if trainer_class is not None:
         _bind(trainer_class, "detector_loss",
               lambda self, input, target, mask=None, loss_type="softmax": _u.detector_loss(input, target, mask, loss_type), bound)
@@ -60,6 +88,16 @@ def install(utils_module=None, trainer_class=None, frontend_class=None, export_m
             return self.mscores
 
         _bind(tracker_class, "nn_match_two_way", _nn, bound)
+    if sparse_module is None:
+        sparse_module = sys.modules.get("utils.loss_functions.sparse_loss")
+    if sparse_module is not None:
+        from . import sparse as _sp
+        _bind(sparse_module, "batch_descriptor_loss_sparse", _sp.batch_descriptor_loss_sparse, bound)
+        _bind(sparse_module, "descriptor_loss_sparse", _sp.descriptor_loss_sparse, bound)
+    if data_tools_module is None:
+        data_tools_module = sys.modules.get("datasets.data_tools")
+    if data_tools_module is not None:
+        _bind(data_tools_module, "warpLabels", _worker_safe(_u.warpLabels, getattr(data_tools_module, "warpLabels", None)), bound)
     if export_module is None:
         export_module = sys.modules.get("export")
     if export_module is not None:

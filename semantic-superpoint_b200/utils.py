@@ -61,8 +61,18 @@ def _linspace_grid(n, dev):
 # ------------------------------------------------------------------------------------------------
 # a1 / a10  point warps
 # ------------------------------------------------------------------------------------------------
+def _no_grad_inputs(name, *tensors):
+    """The reference's versions of these are chains of differentiable torch ops; the kernels are forward-only (nothing in the
+    reference back-propagates through them: they sit on the data / label side).  Refuse instead of silently cutting a graph."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError("ssp_b200.%s is forward-only (no autograd); detach() the input or call under torch.no_grad()" % name)
+
+
 def warp_points(points, homographies, device="cpu"):
     """reference: utils/utils.py:315-343.  points [P,2] (x,y), homographies [3,3] or [B,3,3] -> [P,2] / [B,P,2]."""
+    _no_grad_inputs("warp_points", points, homographies)
     no_batches = homographies.dim() == 2
     dev = _cuda_device(device, points, homographies)
     out_dev = _out_device(device, dev, points, homographies)
@@ -167,6 +177,7 @@ def denormPts(pts, shape):
 def inv_warp_image_batch(img, mat_homo_inv, device="cpu", mode="bilinear", staged=False):
     """reference: utils/utils.py:347-385.  img [B,C,H,W] (2-D/3-D viewed as [1,1,H,W]), H^-1 [B,3,3] / [3,3].
     staged=True selects the shared-memory staged kernel instead of the per-pixel gather (same results, measured slower)."""
+    _no_grad_inputs("inv_warp_image_batch", img, mat_homo_inv)
     if img.dim() == 2 or img.dim() == 3:
         img = img.view(1, 1, img.shape[0], img.shape[1])
     if mat_homo_inv.dim() == 2:
@@ -309,6 +320,10 @@ def sem_loss(pred, label, device="cpu", ignore_index=133, dist_group=None):
 # ------------------------------------------------------------------------------------------------
 def flattenDetection(semi, tensor=False):
     """reference: utils/utils.py:515-560.  [B,65,Hc,Wc] -> [B,1,8Hc,8Wc]; [65,Hc,Wc] -> [1,8Hc,8Wc]."""
+    # forward-only: the reference's trainers call this on logits that require grad (Train_model_frontend_all.py:668,
+    # Train_model_heatmap_all.py:371) but only to log / extract points -- nothing back-propagates through it, so the result
+    # is a detached tensor rather than an error.
+    semi = semi.detach()
     batch = semi.dim() == 4
     dev = _cuda_device(None, semi)
     x = f32c(semi if batch else semi.unsqueeze(0), dev)
@@ -461,8 +476,11 @@ def nms_fast(in_corners, H, W, dist_thresh):
     dev = _cuda_device("cuda")
     grid = np.full((H, W), np.nan, dtype=np.float32)
     inds = np.zeros((H, W), dtype=np.int64)
-    # first visit (highest confidence) decides the NMS; the index map keeps the last writer, as the reference
-    grid[rc[1, ::-1], rc[0, ::-1]] = corners[2, ::-1].astype(np.float32)
+    # first visit (highest confidence) decides the NMS; the index map keeps the last writer, as the reference.  The
+    # priority handed to the device is the point's RANK in the reference's own fp64 ordering (exact in fp32 for
+    # n < 2^24), not the confidence: two confidences that differ only beyond fp32 still order the way the reference does.
+    assert n < (1 << 24)
+    grid[rc[1, ::-1], rc[0, ::-1]] = -np.arange(n - 1, -1, -1, dtype=np.float32)
     inds[rc[1], rc[0]] = np.arange(n)
     heat = torch.from_numpy(grid).to(dev).reshape(1, H, W)
     R = int(dist_thresh)

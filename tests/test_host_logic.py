@@ -55,8 +55,22 @@ def test_dropin_binds_and_restores():
     bound = S.dropin.install(utils_module=fake, trainer_class=Trainer)
     assert fake.descriptor_loss is S.utils.descriptor_loss and fake.labels2Dto3D is S.utils.labels2Dto3D
     assert any(b.endswith("detector_loss") for b in bound)
+    # dataset-side names: ours in the main process, the reference's own function inside a DataLoader worker (no CUDA there)
+    assert fake.warp_points.__wrapped__ is S.utils.warp_points
+    import torch.utils.data as tud
+    orig_info = tud.get_worker_info
+    tud.get_worker_info = lambda: object()
+    try:
+        assert fake.warp_points(torch.zeros(4, 2), torch.eye(3)) == "ref"
+    finally:
+        tud.get_worker_info = orig_info
+    sparse_mod = types.ModuleType("fake_sparse")
+    sparse_mod.batch_descriptor_loss_sparse = lambda *a, **k: "ref"
+    bound = S.dropin.install(utils_module=fake, sparse_module=sparse_mod)
+    assert sparse_mod.batch_descriptor_loss_sparse is S.sparse.batch_descriptor_loss_sparse
     S.dropin.uninstall()
-    assert fake.descriptor_loss() == "ref" and Trainer().detector_loss() == "ref"
+    assert fake.descriptor_loss() == "ref" and Trainer().detector_loss() == "ref" and fake.warp_points() == "ref"
+    assert sparse_mod.batch_descriptor_loss_sparse() == "ref"
 
 
 def test_signatures_mirror_reference():
