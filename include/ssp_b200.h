@@ -156,7 +156,8 @@ int ssp_desc_finalize(const double* pos_part, int npos, const double* neg_part, 
 int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int cell, float dist, float* mask /*[B,Nc,Nc]*/,
                        void* stream);
 int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)*/, const float* out8, int B,
-                   int Nc_pad, float* alpha /*[B,Nc_pad]*/, void* stream);
+                   int Nc_pad, float* alpha /*[B,Nc_pad]*/, float* srow /*or NULL: [B,Nc_pad], alpha for mask_valid = 1*/,
+                   void* stream);
 /* backward coefficients of the positive pairs (and removal of their negative term).  colrow_sorted receives the column
  * lists ordered by row index (deterministic summation order) with their coefficients in colcoef; the forward's lists
  * are left untouched, so a second backward over the same graph sees the same inputs */

@@ -62,13 +62,16 @@ extern "C" int ssp_desc_geometry(const float* Hm, const float* mask_valid, int B
   return SSP_OK;
 }
 
-// candidate window of cell indices whose centre can be within `dist` of (wx, wy); +-1 cell of slack,
-// the exact predicate decides.
+// candidate window of cell indices whose centre can be within `dist` of (wx, wy): a centre k*cell + half qualifies only if
+// |k*cell + half - w| <= dist, i.e. k in [(w - dist - half)/cell, (w + dist - half)/cell]; the window is that interval
+// widened by 0.01 cell (0.08 px at cell = 8: three orders of magnitude above the fp32 rounding of pixel coordinates), the
+// exact predicate decides.  <= 2 x 2 candidates for dist <= cell/2, <= 3 x 3 for dist <= cell (it used to be 5 x 5, and
+// the scan was two thirds of the instructions of the pos kernels).
 __device__ __forceinline__ void pos_window(float wx, float wy, float dist, int Hc, int Wc, int cell, int& k0,
                                            int& k1, int& l0, int& l1) {
   float half = (float)(cell / 2), fc = (float)cell;
-  float a = floorf((wy - dist - half) / fc) - 1.f, b = ceilf((wy + dist - half) / fc) + 1.f;
-  float c = floorf((wx - dist - half) / fc) - 1.f, d = ceilf((wx + dist - half) / fc) + 1.f;
+  float a = ceilf((wy - dist - half) / fc - 0.01f), b = floorf((wy + dist - half) / fc + 0.01f);
+  float c = ceilf((wx - dist - half) / fc - 0.01f), d = floorf((wx + dist - half) / fc + 0.01f);
   // clamp in float first: far-away / non-finite points give an empty window
   k0 = (int)fmaxf(a, 0.f);
   k1 = (int)fminf(b, (float)(Hc - 1));
@@ -249,7 +252,8 @@ extern "C" int ssp_desc_pos_fwd(const float* D, const float* Dw, const float* wp
 // value for the pair, which is what the negative-hinge correction must cancel.
 // partials: 4 doubles per block, as above.  Same lists.
 // ----------------------------------------------------------------------------------------------
-#define POSP_WARPS 8
+#define POSP_ROWS 64      // rows per block
+#define POSP_THREADS 256  // phase 2: 8 lanes per row, 32 rows per pass
 __device__ __forceinline__ void bf16x8_sum(const uint4& h, const uint4& l, float (&v)[8]) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
@@ -259,72 +263,93 @@ __device__ __forceinline__ void bf16x8_sum(const uint4& h, const uint4& l, float
   }
 }
 
-__global__ void __launch_bounds__(POSP_WARPS * 32)
+// Block = 64 rows.  Phase 1: one thread per row scans its candidate window sequentially (k-major, l-minor: the order of
+// the lists) -- a few cells for descriptor_dist <= cell.  Phase 2: EIGHT lanes per row, each covering 32 channels = 4 + 4
+// 16-byte loads per side, all 16 issued before the first use: the kernel is a chain of dependent latencies (point ->
+// window -> partner -> planes -> atomics), so what matters is how many bytes every warp has in flight (8 KB here; the
+// previous one-warp-per-row version had 1 KB and ran at 27 us for 150 MB of L2-resident planes).
+__global__ void __launch_bounds__(POSP_THREADS)
 desc_pos_fwd_planes_kernel(const uint4* __restrict__ Ahi, const uint4* __restrict__ Alo, const uint4* __restrict__ Bhi,
                            const uint4* __restrict__ Blo, const float2* __restrict__ wpts,
                            const float* __restrict__ mv_pad, DescGeom g, double* __restrict__ partials,
                            int* __restrict__ rowcol, float* __restrict__ rowdot, int* __restrict__ colcnt,
                            int* __restrict__ colrow, float* __restrict__ coldot) {
-  __shared__ double sacc[POSP_WARPS][4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y, r = blockIdx.x * POSP_WARPS + warp;  // grid.x covers Nc_pad rows
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  // ---- candidate scan, lanes in parallel
-  int mycol = -1, cnt = 0;  // lane n < cnt holds the n-th partner
-  if (r < g.Nc) {
-    const float2 w = wpts[(size_t)b * g.Nc_pad + r];
-    int k0, k1, l0, l1;
-    pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
-    const int nl = l1 - l0 + 1, ncand = (k1 >= k0 && nl > 0) ? (k1 - k0 + 1) * nl : 0;
-    int nhit = 0;
-    for (int base = 0; base < ncand; base += 32) {
-      const int i = base + lane;
-      bool hit = false;
-      int c = -1;
-      if (i < ncand) {
-        c = (k0 + i / nl) * g.Wc + (l0 + i % nl);
-        float cx, cy;
-        cell_center(c, g.Wc, g.cell, cx, cy);
-        hit = pair_positive(w.x, w.y, cx, cy, g.dist);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
-      // hand the hit of this lane to lane `slot`
-#pragma unroll 1
-      for (unsigned m = bal; m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        const int s = __shfl_sync(0xffffffffu, slot, src), cc = __shfl_sync(0xffffffffu, c, src);
-        if (lane == s && s < DESC_MAXP) mycol = cc;
-      }
-      nhit += __popc(bal);
-      cnt = min(nhit, DESC_MAXP);
+  __shared__ int scol[POSP_ROWS][DESC_MAXP + 1];
+  __shared__ int scnt[POSP_ROWS];
+  __shared__ double sred[32];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, r0 = blockIdx.x * POSP_ROWS;  // grid.x covers Nc_pad rows
+  if (tid < POSP_ROWS) {
+    const int r = r0 + tid;
+    int cnt = 0;
+    if (r < g.Nc) {
+      const float2 w = wpts[(size_t)b * g.Nc_pad + r];
+      int k0, k1, l0, l1;
+      pos_window(w.x, w.y, g.dist, g.Hc, g.Wc, g.cell, k0, k1, l0, l1);
+      int dropped = 0;
+      for (int k = k0; k <= k1; ++k)
+        for (int l = l0; l <= l1; ++l) {
+          const int c = k * g.Wc + l;
+          float cx, cy;
+          cell_center(c, g.Wc, g.cell, cx, cy);
+          if (pair_positive(w.x, w.y, cx, cy, g.dist)) {
+            if (cnt < DESC_MAXP) scol[tid][cnt++] = c;
+            else ++dropped;
+          }
+        }
+      if (dropped) atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, dropped);  // overflow counter: finalize turns it into NaN
     }
-    if (nhit > DESC_MAXP && lane == 0) atomicAdd(colcnt + (size_t)g.B * g.Nc_pad, nhit - DESC_MAXP);  // overflow counter
+    scnt[tid] = cnt;
+    int4* rc = reinterpret_cast<int4*>(rowcol + ((size_t)b * g.Nc_pad + r) * DESC_MAXP);
+#pragma unroll
+    for (int n = 0; n < DESC_MAXP; n += 4)
+      rc[n / 4] = make_int4(n < cnt ? scol[tid][n] : -1, n + 1 < cnt ? scol[tid][n + 1] : -1,
+                            n + 2 < cnt ? scol[tid][n + 2] : -1, n + 3 < cnt ? scol[tid][n + 3] : -1);
   }
-  if (r < g.Nc_pad && lane < DESC_MAXP) rowcol[((size_t)b * g.Nc_pad + r) * DESC_MAXP + lane] = lane < cnt ? mycol : -1;
-  if (cnt) {
-    const size_t ra = ((size_t)b * g.Nc_pad + r) * 32 + lane;  // uint4 index: 256 bf16 = 32 x 16 B per cell
-    float a[8];
-    bf16x8_sum(__ldg(Ahi + ra), __ldg(Alo + ra), a);
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int sub = tid & 7;  // lane within the row's group of eight: channels [32 sub, 32 sub + 32)
+#pragma unroll 1
+  for (int pass = 0; pass < POSP_ROWS / 32; ++pass) {
+    const int lr = pass * 32 + (tid >> 3), r = r0 + lr;
+    const int cnt = scnt[lr];
+    if (cnt == 0) continue;  // the eight lanes of a group agree; shuffles below stay inside the group
+    const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+    const uint4* pa_h = Ahi + ((size_t)b * g.Nc_pad + r) * 32 + sub * 4;
+    const uint4* pa_l = Alo + ((size_t)b * g.Nc_pad + r) * 32 + sub * 4;
+    uint4 ah[4], al[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { ah[t] = __ldg(pa_h + t); al[t] = __ldg(pa_l + t); }
     for (int n = 0; n < cnt; ++n) {
-      const int c = __shfl_sync(0xffffffffu, mycol, n);
-      const size_t rb = ((size_t)b * g.Nc_pad + c) * 32 + lane;
-      float w8[8];
-      bf16x8_sum(__ldg(Bhi + rb), __ldg(Blo + rb), w8);
+      const int c = scol[lr][n];
+      const uint4* pb_h = Bhi + ((size_t)b * g.Nc_pad + c) * 32 + sub * 4;
+      const uint4* pb_l = Blo + ((size_t)b * g.Nc_pad + c) * 32 + sub * 4;
+      uint4 bh[4], bl[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { bh[t] = __ldg(pb_h + t); bl[t] = __ldg(pb_l + t); }
       float part = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) part = fmaf(a[i], w8[i], part);
-      const float dot = warp_sum(part);
-      if (lane == 0) {
-        float mv = mv_pad[(size_t)b * g.Nc_pad + c];
-        float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
-        float negc = fmaxf(dot - g.mneg, 0.f);
+      for (int t = 0; t < 4; ++t) {
+        float a[8], w8[8];
+        bf16x8_sum(ah[t], al[t], a);
+        bf16x8_sum(bh[t], bl[t], w8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part = fmaf(a[i], w8[i], part);
+      }
+      part += __shfl_xor_sync(gmask, part, 4);
+      part += __shfl_xor_sync(gmask, part, 2);
+      part += __shfl_xor_sync(gmask, part, 1);
+      if (sub == 0) {
+        const float dot = part;
+        const float mv = mv_pad[(size_t)b * g.Nc_pad + c];
+        const float pos = g.lamda * fmaxf(g.mpos - dot, 0.f);
+        const float negc = fmaxf(dot - g.mneg, 0.f);
         acc[0] += (double)pos;
         acc[1] += (double)(pos * mv);
         acc[2] += (double)negc;
         acc[3] += (double)(negc * mv);
         rowdot[((size_t)b * g.Nc_pad + r) * DESC_MAXP + n] = dot;
-        int slot = atomicAdd(colcnt + (size_t)b * g.Nc_pad + c, 1);
+        const int slot = atomicAdd(colcnt + (size_t)b * g.Nc_pad + c, 1);
         if (slot < DESC_MAXP) {
           colrow[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = r;
           coldot[((size_t)b * g.Nc_pad + c) * DESC_MAXP + slot] = dot;
@@ -334,20 +359,14 @@ desc_pos_fwd_planes_kernel(const uint4* __restrict__ Ahi, const uint4* __restric
       }
     }
   }
-  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sacc[warp][i] = acc[i];
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < POSP_WARPS; ++w) v += sacc[w][threadIdx.x];
-    partials[4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + threadIdx.x] = v;
+  for (int i = 0; i < 4; ++i) {
+    const double v = block_sum_d(acc[i], sred);  // fixed tree: deterministic
+    if (tid == 0) partials[4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + i] = v;
   }
 }
 
-extern "C" int ssp_desc_pos_planes_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / POSP_WARPS); }
+extern "C" int ssp_desc_pos_planes_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / POSP_ROWS); }
 
 // Same contract as ssp_desc_pos_fwd, reading the packed hi/lo planes [B, Nc_pad, 256] of D (A*) and Dw (B*).
 extern "C" int ssp_desc_pos_fwd_planes(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo,
@@ -365,8 +384,8 @@ extern "C" int ssp_desc_pos_fwd_planes(const void* Ahi, const void* Alo, const v
               dist, cell, DESC_MAXP);
   cudaStream_t st = (cudaStream_t)stream;
   SSP_CUDA_CALL(cudaMemsetAsync(colcnt, 0, ((size_t)B * g.Nc_pad + 1) * sizeof(int), st));
-  dim3 grid(g.Nc_pad / POSP_WARPS, B);
-  desc_pos_fwd_planes_kernel<<<grid, POSP_WARPS * 32, 0, st>>>(
+  dim3 grid(g.Nc_pad / POSP_ROWS, B);
+  desc_pos_fwd_planes_kernel<<<grid, POSP_THREADS, 0, st>>>(
       (const uint4*)Ahi, (const uint4*)Alo, (const uint4*)Bhi, (const uint4*)Blo, reinterpret_cast<const float2*>(wpts), mv_pad, g,
       partials, rowcol, rowdot, colcnt, colrow, coldot);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_fwd_planes_kernel");
@@ -382,44 +401,47 @@ desc_finalize_kernel(const double* __restrict__ pos_part, int npos, const double
                      const double* __restrict__ mv_part, int nmv, int B, int Hc, int Wc, const int* __restrict__ overflow,
                      float* __restrict__ out4, const float* __restrict__ det0, const float* __restrict__ det1,
                      float lambda_loss, float* __restrict__ total) {
-  __shared__ double sh[32];
+  __shared__ double sh[7][32];
   double pu = 0, pw = 0, nu = 0, nw = 0, sm = 0;
   double cu = 0, cw = 0;  // negative-hinge contribution of the positive pairs, contained in the dense sums
-  // the loops are a chain of L2 round trips per thread unless several loads are in flight: batches of 4 vector loads
-  {
-    const double2* p2 = reinterpret_cast<const double2*>(pos_part);  // {pos_u, pos_w}, {negcorr_u, negcorr_w}
-    for (int i0 = threadIdx.x; i0 < npos; i0 += 4 * blockDim.x) {
-      double2 a[4], c[4];
+  // One block, so the kernel is a chain of L2 round trips unless the loads of all three arrays are in flight together:
+  // the first batch of each array is issued before anything is summed (at the headline sizes there is no second batch).
+  const double2* p2 = reinterpret_cast<const double2*>(pos_part);  // {pos_u, pos_w}, {negcorr_u, negcorr_w}
+  const double2* n2 = reinterpret_cast<const double2*>(neg_part);
+  const int T = blockDim.x, t = threadIdx.x;
+  const double2 z2 = make_double2(0.0, 0.0);
+  for (int base = 0; base < npos || base < nneg || base < nmv; base += 2 * T) {
+    double2 a[2], c[2], n[2];
+    double m[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int i = i0 + u * blockDim.x;
-        bool ok = i < npos;
-        a[u] = ok ? p2[2 * (size_t)i] : make_double2(0.0, 0.0);
-        c[u] = ok ? p2[2 * (size_t)i + 1] : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { pu += a[u].x; pw += a[u].y; cu += c[u].x; cw += c[u].y; }
+    for (int u = 0; u < 2; ++u) {
+      const int i = base + u * T + t;
+      a[u] = i < npos ? p2[2 * (size_t)i] : z2;
+      c[u] = i < npos ? p2[2 * (size_t)i + 1] : z2;
+      n[u] = i < nneg ? n2[i] : z2;
+      m[u] = i < nmv ? mv_part[i] : 0.0;
     }
-    const double2* n2 = reinterpret_cast<const double2*>(neg_part);
-    for (int i0 = threadIdx.x; i0 < nneg; i0 += 8 * blockDim.x) {
-      double2 a[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int i = i0 + u * blockDim.x;
-        a[u] = i < nneg ? n2[i] : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { nu += a[u].x; nw += a[u].y; }
+    for (int u = 0; u < 2; ++u) {
+      pu += a[u].x; pw += a[u].y; cu += c[u].x; cw += c[u].y; nu += n[u].x; nw += n[u].y; sm += m[u];
     }
-    for (int i = threadIdx.x; i < nmv; i += blockDim.x) sm += mv_part[i];
   }
-  pu = block_sum_d(pu, sh);
-  pw = block_sum_d(pw, sh);
-  nu = block_sum_d(nu, sh);
-  nw = block_sum_d(nw, sh);
-  sm = block_sum_d(sm, sh);
-  cu = block_sum_d(cu, sh);
-  cw = block_sum_d(cw, sh);
+  // seven block sums behind ONE pair of barriers (fixed tree: deterministic)
+  {
+    double v[7] = {pu, pw, nu, nw, sm, cu, cw};
+    const int lane = t & 31, w = t >> 5, nwarps = (T + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      v[k] = warp_sum_d(v[k]);
+      if (lane == 0) sh[k][w] = v[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) v[k] = warp_sum_d(lane < nwarps ? sh[k][lane] : 0.0);
+    }
+    pu = v[0]; pw = v[1]; nu = v[2]; nw = v[3]; sm = v[4]; cu = v[5]; cw = v[6];
+  }
   if (threadIdx.x == 0) {
     nu -= cu;
     nw -= cw;
@@ -486,17 +508,22 @@ extern "C" int ssp_desc_pair_mask(const float* wpts, int B, int Hc, int Wc, int 
 // ----------------------------------------------------------------------------------------------
 // backward scales: alpha[b,c] = (g_loss * mv[b,c] + g_neg) / norm   (coefficient of the negative hinge)
 // ----------------------------------------------------------------------------------------------
+// srow (optional) = the same coefficient for mv = 1: the row scale of the folded backward (mask already inside the bits)
 __global__ void desc_alpha_kernel(const float* __restrict__ mv_pad, const float* __restrict__ g3,
-                                  const float* __restrict__ out4, size_t n, float* __restrict__ alpha) {
+                                  const float* __restrict__ out4, size_t n, float* __restrict__ alpha,
+                                  float* __restrict__ srow) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) alpha[i] = (g3[0] * mv_pad[i] + g3[2]) / out4[3];
+  if (i < n) {
+    alpha[i] = (g3[0] * mv_pad[i] + g3[2]) / out4[3];
+    if (srow) srow[i] = (g3[0] * 1.0f + g3[2]) / out4[3];
+  }
 }
 
 extern "C" int ssp_desc_alpha(const float* mv_pad, const float* g3, const float* out4, int B, int Nc_pad,
-                              float* alpha, void* stream) {
+                              float* alpha, float* srow, void* stream) {
   SSP_REQUIRE(mv_pad && g3 && out4 && alpha, "ssp_desc_alpha: null pointer");
   size_t n = (size_t)B * Nc_pad;
-  desc_alpha_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mv_pad, g3, out4, n, alpha);
+  desc_alpha_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mv_pad, g3, out4, n, alpha, srow);
   SSP_CUDA_CHECK_LAUNCH("desc_alpha_kernel");
   return SSP_OK;
 }
@@ -702,36 +729,65 @@ extern "C" int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const
 // 32 cells x Dch tile transposed through shared memory; reads are 128 B per warp per channel, writes
 // are contiguous bf16 rows.
 // ----------------------------------------------------------------------------------------------
-#define PK_CELLS 32
+#define PK_CELLS 64   // cells per block: 256 contiguous bytes of every channel row
+#define PK_CH 128     // channels per block (the grid's z also splits the descriptor): 32 KB tile, 6 blocks per SM
 __global__ void __launch_bounds__(256)
 desc_pack_kernel(const float* __restrict__ src0, const float* __restrict__ src1, const float* __restrict__ scale,
                  int Dch, int Nc, int Nc_pad, __nv_bfloat16* __restrict__ hi0, __nv_bfloat16* __restrict__ lo0,
                  __nv_bfloat16* __restrict__ hi1, __nv_bfloat16* __restrict__ lo1) {
-  extern __shared__ float tile[];  // [PK_CELLS][Dch + 1]
-  // blockIdx.z selects one of up to two tensors packed by the same launch
-  const float* __restrict__ src = blockIdx.z ? src1 : src0;
-  __nv_bfloat16* __restrict__ hi = blockIdx.z ? hi1 : hi0;
-  __nv_bfloat16* __restrict__ lo = blockIdx.z ? lo1 : lo0;
-  int b = blockIdx.y;
-  int c0 = blockIdx.x * PK_CELLS;
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int ld = Dch + 1;
-  int c = c0 + lane;
-  float s = 1.f;
-  if (scale && c < Nc) s = scale[(size_t)b * Nc_pad + c];
-  for (int d = w; d < Dch; d += 8) {
-    float v = 0.f;
-    if (c < Nc) v = __ldg(src + ((size_t)b * Dch + d) * Nc + c) * s;
-    tile[lane * ld + d] = v;
+  __shared__ float tile[PK_CH][PK_CELLS + 1];  // [channel][cell]: both phases conflict-free (row stride 65 = 1 mod 32)
+  // blockIdx.z = (tensor, channel block)
+  const int nchb = (Dch + PK_CH - 1) / PK_CH;
+  const int which = blockIdx.z / nchb, d0 = (blockIdx.z - which * nchb) * PK_CH;
+  const float* __restrict__ src = which ? src1 : src0;
+  __nv_bfloat16* __restrict__ hi = which ? hi1 : hi0;
+  __nv_bfloat16* __restrict__ lo = which ? lo1 : lo0;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * PK_CELLS;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // ---- phase 1: warp = one channel row at a time, lanes = cells (lane, lane + 32); 8 rows = 16 loads in flight per thread
+  const int ca = c0 + lane, cb = ca + 32;
+  float sa = 1.f, sb = 1.f;
+  if (scale) {
+    if (ca < Nc) sa = scale[(size_t)b * Nc_pad + ca];
+    if (cb < Nc) sb = scale[(size_t)b * Nc_pad + cb];
+  }
+#pragma unroll 1
+  for (int i0 = 0; i0 < PK_CH / 8; i0 += 8) {
+    float va[8], vb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int d = d0 + w + 8 * (i0 + u);
+      const float* row = src + ((size_t)b * Dch + d) * Nc;
+      va[u] = (d < Dch && ca < Nc) ? __ldg(row + ca) : 0.f;
+      vb[u] = (d < Dch && cb < Nc) ? __ldg(row + cb) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int dl = w + 8 * (i0 + u);
+      tile[dl][lane] = va[u] * sa;
+      tile[dl][lane + 32] = vb[u] * sb;
+    }
   }
   __syncthreads();
+  // ---- phase 2: warp = one cell at a time, lane = channel pairs (2 lane, 2 lane + 1) + 64 j: one packed conversion
+  // (cvt.rn.bf16x2.f32) per pair for hi, one for lo, and 4-byte stores: 128 contiguous bytes per warp store.
+  // (The two scalar LDS per pair are 2-way bank conflicted; the kernel is bound by issued instructions, not by LDS.)
+#pragma unroll 2
   for (int cc = w; cc < PK_CELLS; cc += 8) {
-    size_t o = ((size_t)b * Nc_pad + c0 + cc) * Dch;
-    for (int d = lane; d < Dch; d += 32) {
-      float v = tile[cc * ld + d];
-      __nv_bfloat16 h = __float2bfloat16_rn(v);
-      hi[o + d] = h;
-      if (lo) lo[o + d] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t o = ((size_t)b * Nc_pad + c0 + cc) * Dch + d0;
+#pragma unroll
+    for (int j = 0; j < PK_CH / 64; ++j) {
+      const int d = 2 * lane + 64 * j;
+      const float v0 = tile[d][cc], v1 = tile[d + 1][cc];
+      uint32_t h2, l2;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(v1), "f"(v0));  // low half = v0
+      const float r0 = v0 - __uint_as_float(h2 << 16), r1 = v1 - __uint_as_float(h2 & 0xffff0000u);
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(r1), "f"(r0));
+      if (d0 + d < Dch) {
+        *reinterpret_cast<uint32_t*>(hi + o + d) = h2;
+        if (lo) *reinterpret_cast<uint32_t*>(lo + o + d) = l2;
+      }
     }
   }
 }
@@ -740,13 +796,13 @@ desc_pack_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
 extern "C" int ssp_desc_pack2(const float* src0, const float* src1, const float* scale, int B, int Dch, int Nc, void* hi0,
                               void* lo0, void* hi1, void* lo1, void* stream) {
   SSP_REQUIRE(src0 && hi0 && (!src1 || hi1), "ssp_desc_pack: null pointer");
-  SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Nc > 0, "ssp_desc_pack: bad sizes");
+  SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Dch % 2 == 0 && Nc > 0, "ssp_desc_pack: bad sizes (Dch must be even)");
   int Nc_pad = desc_nc_pad(Nc);
-  size_t smem = (size_t)PK_CELLS * (Dch + 1) * sizeof(float);
-  SSP_REQUIRE(smem <= 48 * 1024, "ssp_desc_pack: descriptor dim %d too large", Dch);
-  dim3 grid(Nc_pad / PK_CELLS, B, src1 ? 2 : 1);
-  desc_pack_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src0, src1, scale, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi0,
-                                                              (__nv_bfloat16*)lo0, (__nv_bfloat16*)hi1, (__nv_bfloat16*)lo1);
+  const int nchb = (Dch + PK_CH - 1) / PK_CH;
+  SSP_REQUIRE(2 * nchb <= 65535, "ssp_desc_pack: descriptor dim %d too large", Dch);
+  dim3 grid(Nc_pad / PK_CELLS, B, (src1 ? 2 : 1) * nchb);
+  desc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src0, src1, scale, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi0,
+                                                           (__nv_bfloat16*)lo0, (__nv_bfloat16*)hi1, (__nv_bfloat16*)lo1);
   SSP_CUDA_CHECK_LAUNCH("desc_pack_kernel");
   return SSP_OK;
 }

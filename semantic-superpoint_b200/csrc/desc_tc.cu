@@ -457,7 +457,7 @@ struct BgJob {
 template <int P>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, BgJob job0,
-                         BgJob job1, int njobs, int B, int Nc, int Nc_pad, int dbg) {
+                         BgJob job1, int njobs, int B, int Nc, int Nc_pad) {
   using Cfg = BgCfg<P>;
   constexpr int NS = BG_NS;
   static_assert(256 + BG_ACOLS * NS <= 512, "TMEM A ring does not fit");
@@ -556,12 +556,10 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
         for (int kc = 0; kc < NK; ++kc, ++st_it) {
           const int s = st_it % NS;
           const uint32_t ph = (st_it / NS) & 1;
-          // dbg (SSP_BG_DEBUG, profiling only -- results are garbage): bit 0 skips the wait for the A stage, bit 1 the wait
-          // for the B stage, so the issue rate of the MMA thread can be measured with one of its feeds taken away
           TR(4);
-          if (!(dbg & 2)) tc::mbar_wait(b_full + s, ph);
+          tc::mbar_wait(b_full + s, ph);
           TR(5);
-          if (!(dbg & 1)) tc::mbar_wait(a_full + s, ph);
+          tc::mbar_wait(a_full + s, ph);
           TR(7);
           tc::fence_after_sync();
           const int nks = min(KT / 16, NKS - kc * (KT / 16));  // K=16 steps of this stage that hold real cells
@@ -926,15 +924,14 @@ static int bits_gemm_tc_launch(const BgHostJob* jobs, int njobs, int B, int Nc, 
   int nclusters = (int)std::min<long long>(items, std::max(1, ssp_num_sms() / 2));
   int grid = 2 * nclusters;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int dbg = [] { const char* e = getenv("SSP_BG_DEBUG"); return e ? atoi(e) : 0; }();
   if (jobs[0].Blo) {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<2>, BgCfg<2>::SMEM))) return rc;
     if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<2>, grid, BG_THREADS, BgCfg<2>::SMEM, st, maps[0], maps[1], dj[0], dj[1], njobs,
-                              B, Nc, Nc_pad, dbg))) return rc;
+                              B, Nc, Nc_pad))) return rc;
   } else {
     if ((rc = set_smem(desc_bits_gemm_tc_kernel<1>, BgCfg<1>::SMEM))) return rc;
     if ((rc = launch_cluster2(desc_bits_gemm_tc_kernel<1>, grid, BG_THREADS, BgCfg<1>::SMEM, st, maps[0], maps[1], dj[0], dj[1], njobs,
-                              B, Nc, Nc_pad, dbg))) return rc;
+                              B, Nc, Nc_pad))) return rc;
   }
   SSP_CUDA_CHECK_LAUNCH("desc_bits_gemm_tc_kernel");
   return SSP_OK;

@@ -362,16 +362,17 @@ class DescriptorLossFn(torch.autograd.Function):
             g3 = torch.stack([(g if g is not None else zero).reshape(()).to(torch.float32) for g in (g_loss, g_pos, g_neg)])
             g3 = g3.contiguous()
         # alpha[b,c] = (g_loss * mv[c] + g_neg) / norm: coefficient of the negative hinge of column c
+        tc_engine = engine != "fp32"
+        fold = tc_engine and getattr(ctx, "fold_alpha", False)
         alpha = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
-        call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), st)
+        srow = torch.empty((B, Ncp), dtype=torch.float32, device=dev) if fold else None  # folded backward: s = alpha at mv = 1
+        call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), ptr(srow), st)
         rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2]
         rowdot, coldot = lists_f[0], lists_f[1]
         coefs = torch.empty((2,) + tuple(rowdot.shape), dtype=torch.float32, device=dev)
         colrow_sorted = torch.empty_like(colrow)  # the saved lists stay as the forward wrote them (retain_graph safe)
         dD = torch.empty_like(Dc)
         dDw = torch.empty_like(Dwc)
-        tc_engine = engine != "fp32"
-        fold = tc_engine and getattr(ctx, "fold_alpha", False)
         if tc_engine:
             if split:
                 Ahi, Alo, Bhi, Blo = saved[7:11]
@@ -392,11 +393,6 @@ class DescriptorLossFn(torch.autograd.Function):
                  ptr(coefs[1]), stream_of(Dc))
         if fold:
             # bitsR / bitsC already exclude the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
-            key = (dev.index, B, Ncp)
-            if key not in _ones:
-                _ones[key] = torch.ones((B, Ncp), dtype=torch.float32, device=dev)
-            srow = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
-            call("ssp_desc_alpha", ptr(_ones[key]), ptr(g3), ptr(out8), B, Ncp, ptr(srow), st)
             f1.join()
             call("ssp_desc_bits_gemm_tc_pair",
                  ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]), ptr(Bhi), ptr(Blo), ptr(dD),

@@ -150,7 +150,9 @@ class GraphedLossStep(object):
             kw.update(sem_pred=leaves[4], sem=s["sem"], sem_warp_pred=leaves[5], warped_sem=s["warped_sem"])
         out = loss_step(leaves[0], leaves[1], leaves[2], leaves[3], s["labels_2D"], s["warped_labels"], s["mask_2D"],
                         s["mask_warp_2D"], s["mat_H"], **kw)
-        out["loss"].backward()
+        if getattr(self, "_one", None) is None:  # static dL/dloss = 1: no ones_like fill inside the captured step
+            self._one = torch.ones_like(out["loss"])
+        out["loss"].backward(gradient=self._one)
         res = {k: v.detach() for k, v in out.items()}
         res["grads"] = [l.grad for l in leaves]
         return res
