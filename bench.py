@@ -483,12 +483,12 @@ def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, args, images_pe
     Hinv_host = Hinv.repeat(rep, 1, 1, 1).cpu().pin_memory()
     I = I0 * rep
     for s in range(2):
-        pts = S.step.adaptation_step(sets[s][0], Hw, sets[s][1])
+        pts = S.step.adaptation_step(sets[s][0], Hw, sets[s][1], binary_mask=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        pts = S.step.adaptation_step(sets[i % 2][0], Hw, sets[i % 2][1])
+        pts = S.step.adaptation_step(sets[i % 2][0], Hw, sets[i % 2][1], binary_mask=True)
     e1.record()
     barrier()
     ms = sdist.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -502,7 +502,7 @@ def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, args, images_pe
         hw = Hw_host.to(dev, non_blocking=True)
         hinv = Hinv_host.to(dev, non_blocking=True)
         mask = S.compute_valid_mask(shape_t, hinv.reshape(-1, 3, 3), device=dev).reshape(I, N, H_IMG, W_IMG)
-        return S.step.adaptation_step(semi_d, hw, mask)
+        return S.step.adaptation_step(semi_d, hw, mask, binary_mask=True)
     e2e_step(0)
     barrier()
     t0 = time.perf_counter()
@@ -517,14 +517,15 @@ def bench_adaptation(torch, S, dev, rank, world, sdist, barrier, args, images_pe
     # ---- roofline of the dominant kernel (per-entry-point CUDA events over the same steps)
     _lib.profile_begin()
     for i in range(steps):
-        S.step.adaptation_step(sets[i % 2][0], Hw, sets[i % 2][1])
+        S.step.adaptation_step(sets[i % 2][0], Hw, sets[i % 2][1], binary_mask=True)
     prof = _lib.profile_end()
     tot = sum(v[1] for v in prof.values())
     shares = {k: {"calls_per_step": v[0] / steps, "us_per_call": 1e3 * v[1] / v[0], "share": v[1] / tot}
               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     px = H_IMG * W_IMG * 4.0
     algo = {"ssp_combine_heatmap": I * (2 * N + 1) * px, "ssp_combine_heatmap_tiled": I * (2 * N + 1) * px,
-            "ssp_combine_heatmap_bits": I * (2 * N + 1) * px,
+            "ssp_combine_heatmap_bits": I * (2 * N + 1) * px, "ssp_combine_heatmap_signed": I * (N + 1) * px,
+            "ssp_flatten_detection_masked": I * N * (65 * NC * 4.0 + 2 * px),
             "ssp_flatten_detection": I * N * (65 * NC * 4.0 + px), "ssp_nms_fast": I * (px + 12.0 * 600),
             "ssp_mask_pack_bits": I * N * (px + px / 32)}
     top = next(iter(shares))

@@ -73,6 +73,11 @@ int ssp_detector_loss_bwd_pair(const float* semi0, const float* target0, const f
 int ssp_flatten_detection(const float* semi /*[N,65,Hc,Wc]*/, int N, int Hc, int Wc, float* heat /*[N,1,8Hc,8Wc]*/,
                           void* stream);
 
+/* a6 fused with the valid mask of each view (the heat * mask product of export.py:53): heat where mask == 1, -1 where mask == 0;
+ * *flag (device int, zeroed by the caller) is raised by any other mask value.  Input of ssp_combine_heatmap_signed. */
+int ssp_flatten_detection_masked(const float* semi /*[N,65,Hc,Wc]*/, const float* mask /*[N,8Hc,8Wc] 0/1*/, int N, int Hc,
+                                 int Wc, float* heat /*[N,1,8Hc,8Wc]*/, int* flag, void* stream);
+
 /* ---- a7: combine_heatmap (export.py:49-60), batched over I source images ---- */
 int ssp_combine_heatmap(const float* heat /*[I,N,H,W]*/, const float* mask /*[I,N,H,W]*/,
                         const float* Hinv /*[I,N,3,3]*/, int I, int N, int H, int W, const float* xs, const float* ys,
@@ -95,6 +100,11 @@ int ssp_valid_mask_bits(int B, int H, int W, const float* Hinv /*[B,3,3]*/, cons
 int ssp_combine_heatmap_bits(const float* heat /*[I,N,H,W]*/, const uint32_t* mbits /*[I,N,H,ceil(W/32)]*/,
                              const float* Hinv /*[I,N,3,3]*/, int I, int N, int H, int W, const float* xs, const float* ys,
                              const int* flag /*or NULL*/, float* out /*[I,H,W]*/, void* stream);
+/* the same aggregation from the signed heat of ssp_flatten_detection_masked: one gather per tap (bit-identical results for
+ * 0/1 masks; a raised flag turns the output into NaN) */
+int ssp_combine_heatmap_signed(const float* heat_signed /*[I,N,H,W]*/, const float* Hinv /*[I,N,3,3]*/, int I, int N, int H,
+                               int W, const float* xs, const float* ys, const int* flag /*or NULL*/, float* out /*[I,H,W]*/,
+                               void* stream);
 
 /* ---- a8 / a9: getPtsFromHeatmap + nms_fast (utils/utils.py:581-609, 653-712), box_nms (:612-650).
  *      stencil: device (2R+1)^2 bytes, 1 = suppressed offset.  pts: [I,3,capacity] float64 rows x,y,conf,

@@ -25,7 +25,7 @@ pts = torch.rand((76800, 2), device=dev, generator=g) * 2 - 1
 for rep in range(2):
     mask = S.compute_valid_mask(shape_t, Hinv.reshape(-1, 3, 3), device=dev).reshape(I, N, 240, 320)
     mask3 = S.compute_valid_mask(shape_t, Hinv[0], device=dev, erosion_radius=3)
-    out = S.step.adaptation_step(semi, Hw, mask, binary_mask=False)
+    out = S.step.adaptation_step(semi, Hw, mask, binary_mask=True)
     w = S.inv_warp_image_batch(img, Hinv[0], device=dev)
     wn = S.inv_warp_image_batch(img, Hinv[0], device=dev, mode="nearest")
     wg = S.inv_warp_image_batch(img, Hinv[0], device=dev, staged=True)

@@ -487,6 +487,52 @@ flatten_detection_kernel(const float* __restrict__ semi, int N, int Hc, int Wc, 
   }
 }
 
+// flattenDetection fused with the valid mask of the view, for the homography-adaptation aggregation (export.py:49-60 forms
+// heat * mask before warping): out = heat where mask == 1, -1 where mask == 0 (heat is a softmax output, never negative, so the
+// sign carries the mask and the aggregation gathers ONE array instead of two).  Any other mask value raises *flag and the
+// aggregation poisons its result.
+__global__ void __launch_bounds__(128)
+flatten_detection_masked_kernel(const float* __restrict__ semi, const float* __restrict__ mask, int N, int Hc, int Wc,
+                                float* __restrict__ heat, int* __restrict__ flag) {
+  int Nc = Hc * Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= N * Nc) return;
+  int b = cell / Nc, ij = cell % Nc;
+  int k = ij / Wc, l = ij % Wc;
+  float p[NCH];
+  softmax65(semi + (size_t)b * NCH * Nc + ij, Nc, p);
+  int W = Wc * CELL;
+  const size_t off = (size_t)b * Nc * 64 + (size_t)(k * CELL) * W + l * CELL;
+  bool bad = false;
+#pragma unroll
+  for (int dy = 0; dy < CELL; ++dy) {
+    const float4* mr = reinterpret_cast<const float4*>(mask + off + (size_t)dy * W);
+    const float4 m0 = __ldg(mr), m1 = __ldg(mr + 1);
+    const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float v[8];
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) {
+      v[dx] = m[dx] == 1.f ? p[dy * 8 + dx] : -1.f;
+      bad |= !(m[dx] == 1.f || m[dx] == 0.f);
+    }
+    float4* r = reinterpret_cast<float4*>(heat + off + (size_t)dy * W);
+    r[0] = make_float4(v[0], v[1], v[2], v[3]);
+    r[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (bad) *flag = 1;
+}
+
+extern "C" int ssp_flatten_detection_masked(const float* semi, const float* mask, int N, int Hc, int Wc, float* heat, int* flag,
+                                            void* stream) {
+  SSP_REQUIRE(semi && mask && heat && flag, "ssp_flatten_detection_masked: null pointer");
+  SSP_REQUIRE(N > 0 && Hc > 0 && Wc > 0, "ssp_flatten_detection_masked: bad sizes N=%d Hc=%d Wc=%d", N, Hc, Wc);
+  SSP_REQUIRE((((uintptr_t)heat | (uintptr_t)mask) & 15) == 0, "ssp_flatten_detection_masked: mask and output must be 16-byte aligned");
+  int cells = N * Hc * Wc;
+  flatten_detection_masked_kernel<<<ssp_ceil_div(cells, 128), 128, 0, (cudaStream_t)stream>>>(semi, mask, N, Hc, Wc, heat, flag);
+  SSP_CUDA_CHECK_LAUNCH("flatten_detection_masked_kernel");
+  return SSP_OK;
+}
+
 extern "C" int ssp_flatten_detection(const float* semi, int N, int Hc, int Wc, float* heat, void* stream) {
   SSP_REQUIRE(semi && heat, "ssp_flatten_detection: null pointer");
   SSP_REQUIRE(N > 0 && Hc > 0 && Wc > 0, "ssp_flatten_detection: bad sizes N=%d Hc=%d Wc=%d", N, Hc, Wc);

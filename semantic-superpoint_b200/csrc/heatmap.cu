@@ -84,6 +84,80 @@ combine_heatmap_kernel(const float* __restrict__ heat, const float* __restrict__
 }
 
 
+// Signed-heat variant: the input is flatten_detection_masked's array (heat where the view's mask is 1, -1 where it is 0), so a
+// tap is ONE gather and a sign test instead of two gathers.  The gather kernels are bound by L1 wavefronts (ncu: l1tex 89 %,
+// ~6 lines per warp-wide load under rotation), so half the loads is what moves them.  Same arithmetic as the float-mask
+// kernel for m in {0, 1}: bit-identical results.
+__global__ void __launch_bounds__(CH_PIX * CH_GROUPS)
+combine_heatmap_signed_kernel(const float* __restrict__ heat, const float* __restrict__ Hinv, int N, int H, int W,
+                              const float* __restrict__ xs, const float* __restrict__ ys, const int* __restrict__ flag,
+                              float* __restrict__ out) {
+  extern __shared__ __align__(16) float sh[];  // N x 12 floats (homography + pad), then 2*CH_PIX*CH_GROUPS partial sums
+  float4* hs = reinterpret_cast<float4*>(sh);
+  float* part = sh + N * 12;
+  const int plane = H * W;
+  heat += (size_t)blockIdx.y * N * plane;
+  Hinv += (size_t)blockIdx.y * N * 9;
+  out += (size_t)blockIdx.y * plane;
+  for (int i = threadIdx.x; i < N * 12; i += blockDim.x) {
+    const int n = i / 12, k = i - n * 12;
+    sh[i] = k < 9 ? Hinv[n * 9 + k] : 0.f;
+  }
+  __syncthreads();
+  const int lp = threadIdx.x % CH_PIX, g = threadIdx.x / CH_PIX;
+  const int tiles_x = (W + 7) / 8;
+  const int x = (blockIdx.x % tiles_x) * 8 + (lp & 7), y = (blockIdx.x / tiles_x) * 8 + (lp >> 3);
+  const bool inside = x < W && y < H;
+  float sum_h = 0.f, sum_m = 0.f;
+  if (inside) {
+    const float gx = __ldg(xs + x), gy = __ldg(ys + y);
+    const float fW = (float)W, fH = (float)H, sx = (float)(W - 1), sy = (float)(H - 1);
+    const float* hp = heat + (size_t)g * plane;
+    const size_t step = (size_t)CH_GROUPS * plane;
+    for (int n = g; n < N; n += CH_GROUPS, hp += step) {
+      const float4 h0 = hs[3 * n], h1 = hs[3 * n + 1], h2 = hs[3 * n + 2];
+      const float X = fmaf(h0.y, gy, h0.x * gx) + h0.z;
+      const float Y = fmaf(h1.x, gy, h0.w * gx) + h1.y;
+      const float Z = fmaf(h1.w, gy, h1.z * gx) + h2.x;
+      const float ix = ((X / Z + 1.f) / 2.f) * sx;
+      const float iy = ((Y / Z + 1.f) / 2.f) * sy;
+      const float fx = floorf(ix), fy = floorf(iy);
+      if (!(fx >= -1.f && fx < fW && fy >= -1.f && fy < fH)) continue;
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+      const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+      const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
+      const int o = y0 * W + x0;
+      // out-of-image taps read as "masked"
+      const float p00 = (yin0 && xin0) ? __ldg(hp + o) : -1.f;
+      const float p01 = (yin0 && xin1) ? __ldg(hp + o + 1) : -1.f;
+      const float p10 = (yin1 && xin0) ? __ldg(hp + o + W) : -1.f;
+      const float p11 = (yin1 && xin1) ? __ldg(hp + o + W + 1) : -1.f;
+      float ah = 0.f, am = 0.f;
+      if (p00 >= 0.f) { const float w = wx0 * wy0; am += w; ah += p00 * w; }
+      if (p01 >= 0.f) { const float w = wx1 * wy0; am += w; ah += p01 * w; }
+      if (p10 >= 0.f) { const float w = wx0 * wy1; am += w; ah += p10 * w; }
+      if (p11 >= 0.f) { const float w = wx1 * wy1; am += w; ah += p11 * w; }
+      sum_h += ah;
+      sum_m += am;
+    }
+  }
+  part[threadIdx.x] = sum_h;
+  part[CH_PIX * CH_GROUPS + threadIdx.x] = sum_m;
+  __syncthreads();
+  if (g == 0 && inside) {
+    float th = 0.f, tm = 0.f;
+#pragma unroll
+    for (int q = 0; q < CH_GROUPS; ++q) {
+      th += part[q * CH_PIX + lp];
+      tm += part[CH_PIX * CH_GROUPS + q * CH_PIX + lp];
+    }
+    float r = th / tm;  // 0/0 -> NaN exactly like the reference when no view covers the pixel
+    if (flag && *flag) r = __int_as_float(0x7fc00000);  // a mask that was not 0/1: refuse loudly
+    out[y * W + x] = r;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Bit-mask variant (the default of the batched export path).  The valid masks of homography adaptation are 0/1 images
 // (compute_valid_mask, datasets/Coco.py:284-288); as floats they are half of the aggregation's traffic and half of its
@@ -433,6 +507,19 @@ extern "C" int ssp_combine_heatmap(const float* heat, const float* mask, const f
 extern "C" int ssp_combine_heatmap_tiled(const float* heat, const float* mask, const float* Hinv, int I, int N, int H,
                                          int W, const float* xs, const float* ys, float* out, void* stream) {
   return combine_launch(1, heat, mask, Hinv, I, N, H, W, xs, ys, out, stream);
+}
+
+// heat = flatten_detection_masked output [I,N,H,W]; flag = its non-binary-mask flag (device int) or NULL
+extern "C" int ssp_combine_heatmap_signed(const float* heat, const float* Hinv, int I, int N, int H, int W, const float* xs,
+                                          const float* ys, const int* flag, float* out, void* stream) {
+  SSP_REQUIRE(heat && Hinv && xs && ys && out, "ssp_combine_heatmap_signed: null pointer");
+  SSP_REQUIRE(I > 0 && I <= 65535 && N > 0 && H > 0 && W > 0, "ssp_combine_heatmap_signed: bad sizes I=%d N=%d H=%d W=%d", I, N, H, W);
+  size_t smem = ((size_t)N * 12 + 2 * CH_PIX * CH_GROUPS) * sizeof(float);
+  SSP_REQUIRE(smem <= 48 * 1024, "ssp_combine_heatmap_signed: N=%d views exceed the shared-memory table (max ~900)", N);
+  dim3 nblk(ssp_ceil_div(W, 8) * ssp_ceil_div(H, 8), I);
+  combine_heatmap_signed_kernel<<<nblk, CH_PIX * CH_GROUPS, smem, (cudaStream_t)stream>>>(heat, Hinv, N, H, W, xs, ys, flag, out);
+  SSP_CUDA_CHECK_LAUNCH("combine_heatmap_signed_kernel");
+  return SSP_OK;
 }
 
 // ---- bit-mask path ----

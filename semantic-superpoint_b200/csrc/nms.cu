@@ -220,6 +220,128 @@ nms_round_square_kernel(const float* __restrict__ heat, uint8_t* __restrict__ st
   if (left) atomicAdd(remaining, (unsigned int)left);
 }
 
+// Square-window rounds, sliding-window form (R known at compile time).  One 64-bit array carries everything a round needs:
+//   key = 0                suppressed / not a candidate
+//   key = all ones         kept
+//   otherwise              undecided, its priority (order-preserving value bits << 32 | ~linear index)
+// so "a kept point in my window" and "I am the highest undecided point of my window" are the SAME window maximum m:
+// m == all ones -> suppressed, m == own key -> kept.  The (2R+1)^2 maximum is separable, and each thread produces several
+// adjacent outputs of a pass from registers: S outputs need S + 2R inputs and ~(S + 2R) log2(2R+1) max operations
+// (doubling: windows of 1, 2, 4, ... then one overlap step), instead of S (2R+1) shared-memory reads each.
+template <int W, int N>
+__device__ __forceinline__ void sliding_max(unsigned long long (&a)[N]) {
+  int p = 1;
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    if (2 * p <= W) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i + p < N) a[i] = max(a[i], a[i + p]);
+      p *= 2;
+    }
+  }
+  if (p < W) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i + W - p < N) a[i] = max(a[i], a[i + W - p]);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+nms_round_sliding_kernel(const float* __restrict__ heat, uint8_t* __restrict__ state, int H, int W,
+                         unsigned int* __restrict__ remaining) {
+  constexpr int TW = NT + 2 * R;
+  constexpr unsigned long long ONES = ~0ull;
+  __shared__ unsigned long long key[TW][TW + 1];
+  __shared__ unsigned long long rm[TW][NT + 1];  // row maxima of the interior columns, all TW rows
+  const int tid = threadIdx.x;
+  const size_t img = (size_t)blockIdx.z * H * W;
+  heat += img;
+  state += img;
+  const int ty0 = blockIdx.y * NT, tx0 = blockIdx.x * NT;
+  int found = 0;
+  for (int i = tid; i < NT * NT; i += 256) {
+    const int y = ty0 + i / NT, x = tx0 + i % NT;
+    if (y < H && x < W && state[(size_t)y * W + x] == ST_UNDECIDED) found = 1;
+  }
+  if (!__syncthreads_or(found)) return;  // converged tile: one read of its own state
+  for (int i = tid; i < TW * TW; i += 256) {
+    const int ly = i / TW, lx = i - ly * TW;
+    const int y = ty0 - R + ly, x = tx0 - R + lx;
+    unsigned long long k = 0ull;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const uint8_t st = state[(size_t)y * W + x];
+      if (st == ST_KEPT) k = ONES;
+      else if (st == ST_UNDECIDED) k = nms_key(heat[(size_t)y * W + x], (unsigned int)(y * W + x));
+    }
+    key[ly][lx] = k;
+  }
+  __syncthreads();
+  constexpr int SR = 8, SC = 4;  // outputs per thread: row pass (TW rows x 4 segments), column pass (32 columns x 8 segments)
+  for (int it = 0; it < NMS_LOCAL_ITERS; ++it) {
+    if (tid < TW * (NT / SR)) {
+      const int row = tid / (NT / SR), c0 = (tid % (NT / SR)) * SR;
+      unsigned long long a[SR + 2 * R];
+#pragma unroll
+      for (int j = 0; j < SR + 2 * R; ++j) a[j] = key[row][c0 + j];
+      sliding_max<2 * R + 1, SR + 2 * R>(a);
+#pragma unroll
+      for (int j = 0; j < SR; ++j) rm[row][c0 + j] = a[j];
+    }
+    __syncthreads();
+    int changed = 0;
+    {
+      const int col = tid & (NT - 1), r0 = (tid / NT) * SC;
+      unsigned long long a[SC + 2 * R];
+#pragma unroll
+      for (int j = 0; j < SC + 2 * R; ++j) a[j] = rm[r0 + j][col];
+      sliding_max<2 * R + 1, SC + 2 * R>(a);
+#pragma unroll
+      for (int j = 0; j < SC; ++j) {
+        const unsigned long long k = key[r0 + j + R][col + R];
+        if (k != 0ull && k != ONES) {
+          if (a[j] == ONES) { key[r0 + j + R][col + R] = 0ull; changed = 1; }
+          else if (a[j] == k) { key[r0 + j + R][col + R] = ONES; changed = 1; }
+        }
+      }
+    }
+    if (!__syncthreads_or(changed)) break;  // nothing moved: further rounds on this snapshot cannot either
+  }
+  int left = 0;
+  for (int i = tid; i < NT * NT; i += 256) {
+    const int ly = i / NT, lx = i % NT;
+    const int y = ty0 + ly, x = tx0 + lx;
+    if (y < H && x < W) {
+      const unsigned long long k = key[ly + R][lx + R];
+      const uint8_t st = k == 0ull ? ST_NONE : (k == ONES ? ST_KEPT : ST_UNDECIDED);
+      left += st == ST_UNDECIDED;
+      state[(size_t)y * W + x] = st;
+    }
+  }
+  if (left) atomicAdd(remaining, (unsigned int)left);
+}
+
+template <int R>
+static void launch_sliding(dim3 grid, const float* heat, uint8_t* state, int H, int W, unsigned int* remaining, cudaStream_t st) {
+  nms_round_sliding_kernel<R><<<grid, 256, 0, st>>>(heat, state, H, W, remaining);
+}
+
+// true when a compiled sliding-window instance exists for this radius
+static bool nms_launch_sliding(int R, dim3 grid, const float* heat, uint8_t* state, int H, int W, unsigned int* remaining,
+                               cudaStream_t st) {
+  switch (R) {
+    case 1: launch_sliding<1>(grid, heat, state, H, W, remaining, st); return true;
+    case 2: launch_sliding<2>(grid, heat, state, H, W, remaining, st); return true;
+    case 3: launch_sliding<3>(grid, heat, state, H, W, remaining, st); return true;
+    case 4: launch_sliding<4>(grid, heat, state, H, W, remaining, st); return true;
+    case 5: launch_sliding<5>(grid, heat, state, H, W, remaining, st); return true;
+    case 6: launch_sliding<6>(grid, heat, state, H, W, remaining, st); return true;
+    case 8: launch_sliding<8>(grid, heat, state, H, W, remaining, st); return true;
+    default: return false;
+  }
+}
+
 // kept points outside the removed border -> unordered list (value, linear index)
 __global__ void nms_compact_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ state, int H, int W,
                                    int border, int capacity, float* __restrict__ lval, int* __restrict__ lidx,
@@ -339,17 +461,21 @@ static int nms_run_rounds(const float* heat, const NmsWs& w, int I, int H, int W
   }
   int rounds = 0;
   unsigned int remaining = 1;
-  const int batch = 3;  // dense random maps converge in 5-6 rounds: two host checks; converged tiles exit on their first test
+  // dense random maps converge in 7-9 launches (4 local rounds each), real heatmaps in 2-3; a converged tile leaves after one
+  // read of its own state (~4 us per launch for 32 images), a host check costs a stream sync: 8 launches, then 4 at a time
+  int batch = 8;
   while (remaining) {
     for (int k = 0; k < batch; ++k) {
       if (k == batch - 1) SSP_CUDA_CALL(cudaMemsetAsync(w.remaining, 0, 4, st));
-      if (square)
+      if (square && nms_launch_sliding(R, grid, heat, w.state, H, W, w.remaining, st)) {
+      } else if (square)
         nms_round_square_kernel<<<grid, 256, smem, st>>>(heat, w.state, H, W, R, w.remaining);
       else
         nms_round_kernel<<<grid, 256, smem, st>>>(heat, w.state, H, W, R, stencil, w.remaining);
       SSP_CUDA_CHECK_LAUNCH("nms_round_kernel");
       ++rounds;
     }
+    batch = 4;
     SSP_CUDA_CALL(cudaMemcpyAsync(&remaining, w.remaining, 4, cudaMemcpyDeviceToHost, st));
     SSP_CUDA_CALL(cudaStreamSynchronize(st));
     if (rounds > 4 * (H + W) * I + 64) { ssp_set_error("nms: rounds did not converge"); return SSP_EUNSUPPORTED; }

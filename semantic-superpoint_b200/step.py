@@ -69,9 +69,9 @@ def adaptation_step(semi, inv_homographies, mask_2D=None, conf_thresh=0.015, nms
                     mask_homographies=None):
     """semi [I,N,65,Hc,Wc] (or [N,65,Hc,Wc]), inv_homographies [I,N,3,3], mask_2D [I,N,H,W] -> list of [K,3] arrays
     (x, y, prob), K <= top_k, per source image.
-    mask_2D is the stack of valid masks of the warped views; binary_mask=True packs a 0/1 mask to bits for the aggregation
-    (measured slower than the float-mask gather at 240x320 -- the gather is instruction-bound, not wavefront-bound -- so off by
-    default; a non-binary mask then yields NaN heatmaps).
+    mask_2D is the stack of valid masks of the warped views; binary_mask=True promises a 0/1 mask (compute_valid_mask's output,
+    what the export path always passes): the mask is folded into the flattened heatmap as its sign and the aggregation gathers
+    one array instead of two (bit-identical results; a non-binary mask then yields NaN heatmaps).
     mask_2D=None + mask_homographies [I,N,3,3]: the masks are compute_valid_mask(shape, mask_homographies, 0) as in
     datasets/Coco.py:284-288 and are generated as bits on the device."""
     if semi.dim() == 4:
@@ -81,16 +81,13 @@ def adaptation_step(semi, inv_homographies, mask_2D=None, conf_thresh=0.015, nms
         if mask_homographies is not None:
             mask_homographies = mask_homographies.reshape(1, -1, 3, 3)
     I, N, C, Hc, Wc = semi.shape
-    heat = U.flattenDetection(semi.reshape(I * N, C, Hc, Wc)).reshape(I, N, Hc * 8, Wc * 8)
-    agg = U.combine_heatmap_batch(heat, inv_homographies, mask_2D, binary_mask=binary_mask, mask_homographies=mask_homographies)
-    pts = U.heatmap_to_pts_batch(agg, conf_thresh, nms_dist)
-    out = []
-    for p in pts:
-        p = p.transpose()
-        if top_k and p.shape[0] > top_k:
-            p = p[:top_k, :]
-        out.append(p)
-    return out
+    if binary_mask and mask_2D is not None:
+        agg = U.combine_from_logits_batch(semi, inv_homographies, mask_2D)
+    else:
+        heat = U.flattenDetection(semi.reshape(I * N, C, Hc, Wc)).reshape(I, N, Hc * 8, Wc * 8)
+        agg = U.combine_heatmap_batch(heat, inv_homographies, mask_2D, mask_homographies=mask_homographies)
+    pts = U.heatmap_to_pts_batch(agg, conf_thresh, nms_dist, top_k=top_k)
+    return [p.transpose() for p in pts]
 
 
 @torch.no_grad()

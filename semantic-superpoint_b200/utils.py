@@ -386,6 +386,30 @@ def combine_heatmap_batch(heatmap, inv_homographies, mask_2D=None, tiled=False, 
     return out
 
 
+def combine_from_logits_batch(semi, inv_homographies, mask_2D):
+    """flattenDetection + combine_heatmap for the batched export path when the valid masks are 0/1 images (what
+    compute_valid_mask returns): semi [I,N,65,Hc,Wc], inv_homographies [I,N,3,3], mask_2D [I,N,H,W] -> [I,H,W].
+    The mask is folded into the flattened heatmap as its sign (csrc/detector.cu: flatten_detection_masked), so the aggregation
+    gathers one array per tap instead of two: results bit-identical to flattenDetection + combine_heatmap_batch; a mask value
+    other than 0 / 1 turns the output into NaN."""
+    dev = _cuda_device("cuda", semi)
+    x, Hm, m = f32c(semi, dev), f32c(inv_homographies, dev), f32c(mask_2D, dev)
+    I, N, C, Hc, Wc = x.shape
+    if C != 65:
+        raise RuntimeError("combine_from_logits_batch: expected 65 channels, got %d" % C)
+    H, W = Hc * 8, Wc * 8
+    if tuple(m.shape[-2:]) != (H, W) or m.numel() != I * N * H * W:
+        raise RuntimeError("combine_from_logits_batch: mask_2D must be [I,N,%d,%d], got %s" % (H, W, tuple(mask_2D.shape)))
+    st = stream_of(x)
+    heat = torch.empty((I, N, H, W), dtype=torch.float32, device=dev)
+    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    call("ssp_flatten_detection_masked", ptr(x), ptr(m), I * N, Hc, Wc, ptr(heat), ptr(flag), st)
+    out = torch.empty((I, H, W), dtype=torch.float32, device=dev)
+    xs, ys = _linspace_grid(W, dev), _linspace_grid(H, dev)
+    call("ssp_combine_heatmap_signed", ptr(heat), ptr(Hm), I, N, H, W, ptr(xs), ptr(ys), ptr(flag), ptr(out), st)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # a8 / a9  keypoint extraction
 # ------------------------------------------------------------------------------------------------
@@ -424,8 +448,10 @@ def _nms_ws(I, H, W, capacity, dev):
     return torch.empty((nbytes,), dtype=torch.uint8, device=dev), nbytes
 
 
-def heatmap_to_pts_batch(heat, conf_thresh, nms_dist, border_remove=4, capacity=None):
-    """getPtsFromHeatmap for a stack [I,H,W] of CUDA heatmaps in one call.  Returns a list of [3,K] float64 arrays."""
+def heatmap_to_pts_batch(heat, conf_thresh, nms_dist, border_remove=4, capacity=None, top_k=None):
+    """getPtsFromHeatmap for a stack [I,H,W] of CUDA heatmaps in one call.  Returns a list of [3,K] float64 arrays.
+    top_k: only the top_k most confident points of every image are copied back (the list is confidence-descending, so this is
+    what the export's `pts[:top_k]` keeps, export.py:317-323)."""
     dev = _cuda_device("cuda", heat)
     x = f32c(heat, dev)
     I, H, W = x.shape
@@ -437,9 +463,10 @@ def heatmap_to_pts_batch(heat, conf_thresh, nms_dist, border_remove=4, capacity=
     ws, nbytes = _nms_ws(I, H, W, capacity, dev)
     call("ssp_nms_fast", ptr(x), I, H, W, float(conf_thresh), R, ptr(_cheb_stencil(R, dev)), int(border_remove),
          capacity, ptr(pts), counts, ptr(ws), nbytes, stream_of(x))
-    kmax = max(counts) if I else 0
+    cnt = [min(c, top_k) for c in counts] if top_k else list(counts)
+    kmax = max(cnt) if I else 0
     host = pts[:, :, :kmax].cpu().numpy() if kmax else np.zeros((I, 3, 0))
-    return [np.ascontiguousarray(host[i, :, :counts[i]]) for i in range(I)]
+    return [host[i, :, :cnt[i]] for i in range(I)]
 
 
 def getPtsFromHeatmap(heatmap, conf_thresh, nms_dist):

@@ -279,6 +279,26 @@ def test_combine_heatmap_bit_masks():
     assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
 
 
+def test_combine_from_logits_signed_heat():
+    """flatten fused with the 0/1 mask (sign = mask) + one-gather aggregation == flattenDetection + float-mask aggregation, bit for
+    bit, at N = 100; the whole adaptation step returns the same keypoints either way; a soft mask is refused loudly (NaN)."""
+    I, N = 2, 100
+    Hs, Hinv = homographies(I * N, 33, identity_first=True)
+    semi = cu(synth.pseudo_normal((I, N, 65, 30, 40), 12))
+    mask = S.compute_valid_mask(torch.tensor([240, 320]), cu(Hinv), device=DEV).reshape(I, N, 240, 320)
+    Hw = cu(Hs).reshape(I, N, 3, 3)
+    heat = S.flattenDetection(semi.reshape(I * N, 65, 30, 40)).reshape(I, N, 240, 320)
+    ref = S.combine_heatmap_batch(heat, Hw, mask)
+    got = S.utils.combine_from_logits_batch(semi, Hw, mask)
+    assert torch.equal(torch.nan_to_num(ref, nan=-1.0), torch.nan_to_num(got, nan=-1.0))
+    assert torch.isnan(S.utils.combine_from_logits_batch(semi, Hw, mask * 0.5)).all()
+    a = S.step.adaptation_step(semi, Hw, mask)
+    b = S.step.adaptation_step(semi, Hw, mask, binary_mask=True)
+    assert len(a) == len(b) == I
+    for pa, pb in zip(a, b):
+        assert pa.shape == pb.shape and pa.shape[0] <= 600 and np.array_equal(pa, pb)
+
+
 # ------------------------------------------------------------------ a8 / a9
 def test_nms_golden(golden):
     g = golden("nms")
