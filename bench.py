@@ -327,10 +327,16 @@ def run_ours(args):
         torch.cuda.synchronize()
         prof = _lib.profile_end()  # {entry point: (calls, total ms)}
         clocks = sampler.stop()  # sampled every 20 ms from before the timed region to the end of the profiled steps (same workload)
+        # the exchange kernel's duration in these eager, event-bracketed steps is time spent WAITING for the slowest peer (the
+        # ranks drift apart without the graph), not work: reported separately, never the "dominant kernel"
+        xchg = prof.pop("ssp_loss_exchange", None)
         total_prof = sum(v[1] for v in prof.values())
         shares = {k: {"calls_per_step": v[0] / args.steps, "us_per_call": 1e3 * v[1] / v[0], "share": v[1] / total_prof}
                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         top = next(iter(shares))
+        if xchg is not None:
+            shares["ssp_loss_exchange"] = {"calls_per_step": xchg[0] / args.steps, "us_per_call": 1e3 * xchg[1] / xchg[0], "share": None,
+                                           "note": "peer wait in the eager profiling pass; inside the replayed graph the step costs ms_per_step"}
         pk = peaks()
         flops_pair = 2.0 * NC * NC * DCH
         bound_tbl = {
@@ -370,6 +376,11 @@ def run_ours(args):
         extra = {}
         if not args.no_adapt:
             extra = bench_adaptation(torch, S, dev, rank, world, sdist, barrier, args)
+        if world == 1 and not args.no_variants:
+            try:
+                extra["variants"] = bench_variants(torch, S, dsets, args)
+            except Exception as e:  # noqa: BLE001
+                extra["variants"] = {"error": repr(e)}
         if not args.no_semantic and world == 1:  # auxiliary timing, single GPU only
             try:
                 extra.update(bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, args.steps))
@@ -397,14 +408,53 @@ def run_ours(args):
             line.update(extra)
             emit(line)
         if world > 1:
-            sdist.get_exchange(True).check()  # raises if any exchange of the run timed out waiting for a peer
+            ex = sdist.get_exchange(True)
+            ex.check()  # raises if any exchange of the run timed out waiting for a peer
+            torch.cuda.synchronize()
+            # captured graphs go first: with the all-reduce fallback they hold NCCL kernels, and tearing the communicator down
+            # under live graphs blocks forever (seen at N=2: line printed, processes never exit)
+            import gc
+            graphs = slots = None  # noqa: F841
+            gc.collect()
             torch.cuda.synchronize()
             sdist.close_exchanges()
             torch.distributed.barrier()
+            if ex.backend != "p2p":
+                # everything is measured, checked and printed; NCCL's own teardown after graph capture is not worth a hang
+                t = threading.Timer(20.0, lambda: os._exit(0))
+                t.daemon = True
+                t.start()
             torch.distributed.destroy_process_group()
     except Exception as e:  # noqa: BLE001 -- a sticky CUDA error cannot be recovered, only reported
         traceback.print_exc()
         bail("phase after the timed region failed: %r" % (e,))
+
+
+def bench_variants(torch, S, dsets, args):
+    """The same step on the other code paths, graph replay, CUDA events (ms per step): the single-pass bf16 engine (tensor
+    operands rounded to bf16: loss within 3e-3, not the product path), the exact fp32 CUDA-core engine, and fused=False
+    (detector and descriptor losses as separately differentiable autograd nodes, what multi_task_loss needs)."""
+    out = {}
+    steps = max(5, min(args.steps, 20))
+    for name, engine, fused in (("bf16_single_pass", "bf16", True), ("fp32_cuda_cores", "fp32", True), ("bf16x3_unfused", "bf16x3", False)):
+        S.set_descriptor_engine(engine)
+        try:
+            graphs = [S.step.GraphedLossStep(d, fused=fused) for d in dsets]
+            for i in range(3):
+                graphs[i % len(graphs)].replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                graphs[i % len(graphs)].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "pairs_per_s": B_PER_GPU / (ms * 1e-3)}
+            del graphs
+        finally:
+            S.set_descriptor_engine(args.engine)
+    return out
 
 
 def bench_semantic(torch, S, dev, dsets, group, world, sdist, barrier, steps):
@@ -564,6 +614,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph-multi", action="store_true", help="(default now) kept for compatibility")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the timings of the other engines / fused=False")
     ap.add_argument("--no-semantic", action="store_true", help="skip the auxiliary step timing with the semantic head")
     args = ap.parse_args()
     if args.impl == "reference":

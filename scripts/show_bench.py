@@ -12,7 +12,7 @@ for f in sys.argv[1:]:
     if 'kernel_shares' in d:
         tot=0
         for k,v in d['kernel_shares'].items():
-            print('   %-28s calls/step %.1f us/call %8.1f share %.3f'%(k,v['calls_per_step'],v['us_per_call'],v['share'])); tot+=v['calls_per_step']*v['us_per_call']
+            print('   %-28s calls/step %.1f us/call %8.1f share %s'%(k,v['calls_per_step'],v['us_per_call'],v['share'])); tot+=v['calls_per_step']*v['us_per_call']
         print('   sum of kernel time per step: %.1f us'%tot)
     if 'clocks' in d: print('  clocks', d['clocks'])
     if 'homography_adaptation' in d:
@@ -21,3 +21,4 @@ for f in sys.argv[1:]:
         for k,v in a.get('kernel_shares',{}).items(): print('     %-28s calls/step %.1f us/call %8.1f share %.3f'%(k,v['calls_per_step'],v['us_per_call'],v['share']))
     if 'cpu_baseline' in d: print('  cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
     if 'with_semantic_head' in d: print('  semantic', d['with_semantic_head'])
+    if 'variants' in d: print('  variants', {k: (round(v['ms_per_step'], 4) if isinstance(v, dict) and 'ms_per_step' in v else v) for k, v in d['variants'].items()} if isinstance(d['variants'], dict) else d['variants'])
