@@ -435,9 +435,12 @@ constexpr int BG_W_EPI = 8, BG_W_TMA = 16, BG_W_MMA = 17;
 constexpr int BG_NS = 4;                     // ring depth: TMEM holds 2 x 128 accumulator columns + 4 x 64 columns of A
 constexpr int BG_ACOLS = KT / 2;             // TMEM columns of one A stage (two bf16 per column)
 
+constexpr int BG_PF = 4;                     // indicator-word stages in flight per expander set (cp.async groups)
+constexpr int BG_WRING_BYTES = 2 * BG_PF * 4 * BM * 4;  // [set][slot][word of the stage][row of the CTA] = 16 KB
+
 template <int P> struct BgCfg {
   static constexpr int STAGE_BYTES = P * BG_PLANE_BYTES;
-  static constexpr int SMEM = BG_NS * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM = BG_NS * STAGE_BYTES + BAR_BYTES + BG_WRING_BYTES + 1024;
 };
 
 struct BgJob {
@@ -470,6 +473,7 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
   uint64_t* d_full = s_free + NS;   // [2]  each CTA: accumulator complete
   uint64_t* d_empty = d_full + 2;   // [2]  leader: 16 epilogue warps of the pair have drained it
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
+  uint32_t* wring = reinterpret_cast<uint32_t*>(smem + NS * Cfg::STAGE_BYTES + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MP = Nc_pad / (2 * BM), NK = (Nc + KT - 1) / KT, NW = Nc_pad / 32;
@@ -616,14 +620,18 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
       if (lane == 0) tc::mbar_arrive_leader(a_full + s);
       TR(23);
     };
-    // the indicator words run PF of this set's stages ahead of their use over the FLAT stage sequence of all items of this
-    // cluster, so neither the L2 latency inside an item nor the start of a new item is exposed
-    constexpr int PF = 4;
-    uint32_t wq[PF][4];
+    // The indicator words run PF of this set's stages ahead of their use over the FLAT stage sequence of all items of this
+    // cluster, so neither the L2 latency inside an item nor the start of a new item is exposed.  They travel through shared
+    // memory with cp.async (one commit group per stage, every thread copies and later reads only ITS OWN four words, so no
+    // barrier is involved): as register prefetches the loads of different stages shared the warp's six scoreboards, and
+    // waiting for the oldest stage also waited for the one just issued -- ncu showed the expanders stalled on the first use
+    // of a word for a full L2 round trip per stage, which made them, not the tensor pipe, the pace of the kernel.
+    constexpr int PF = BG_PF;
+    uint32_t* myring = wring + (size_t)set * PF * 4 * BM + (q * 32 + lane);  // + (slot * 4 + word) * BM
     int itB = cid, kcB = set;  // fetch cursor (stage `set` of the first item)
     const uint32_t* pB = nullptr;
     bool newitem = true;
-    auto fetch = [&](uint32_t (&w)[4]) {
+    auto fetch = [&](int slot) {
       while (itB < T && kcB >= NK) { kcB -= NK; itB += ncluster; newitem = true; }  // NK may be 1 (tiny inputs)
       if (itB < T) {
         if (newitem) {
@@ -634,27 +642,29 @@ desc_bits_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_c
           newitem = false;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldg(pB + (size_t)(4 * kcB + u) * Nc_pad);
+        for (int u = 0; u < 4; ++u) tc::cp_async4(myring + (slot * 4 + u) * BM, pB + (size_t)(4 * kcB + u) * Nc_pad);
         kcB += 2;
       }
+      tc::cp_async_commit();  // an empty group when the items are exhausted: the group count stays in step with the slots
     };
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) wq[u][v] = 0u;
-      fetch(wq[u]);
-    }
+    for (int u = 0; u < PF; ++u) fetch(u);
     const int nitems = cid < T ? (T - cid + ncluster - 1) / ncluster : 0;
     const int total = nitems * NK;  // global stage count of this cluster; this set owns g = set, set + 2, ...
     for (int g0 = set; g0 < total; g0 += 2 * PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         if (g0 + 2 * u < total) {
-          expand_stage(g0 + 2 * u, wq[u]);
-          fetch(wq[u]);
+          tc::cp_async_wait<PF - 1>();  // the oldest outstanding group = slot u
+          uint32_t w[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) w[v] = myring[(u * 4 + v) * BM];
+          expand_stage(g0 + 2 * u, w);
+          fetch(u);
         }
       }
     }
+    tc::cp_async_wait<0>();
   } else {
     // ------------------------------ epilogue warps 8..15 (both CTAs) ------------------------------
     // two warps per TMEM lane quadrant, each draining two of the four 32-column chunks of the accumulator
