@@ -321,8 +321,13 @@ def run_ours(args):
         e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
 
         # ---- roofline of the dominant kernel: per-entry-point CUDA-event durations over K more steps
+        # Every entry point is bracketed by CUDA events on its launching stream.  Launched eagerly, the GPU would finish each
+        # kernel long before the host issues the next one, and the interval between the two events would then contain the
+        # host's launch latency (tensor-map encoding, ctypes): a spin kernel in front of every step lets the host run ahead,
+        # so the step's kernels execute back to back and the event pairs enclose kernel time only.
         _lib.profile_begin()
         for i in range(args.steps):
+            torch.cuda._sleep(int(3.0e6))  # ~1.5 ms of device spin: longer than the host needs to enqueue one step
             step(dsets[i % NSETS])
         torch.cuda.synchronize()
         prof = _lib.profile_end()  # {entry point: (calls, total ms)}

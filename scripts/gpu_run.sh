@@ -19,6 +19,10 @@ for step in "$@"; do
            timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
              python bench.py --steps 2 --warmup 1 --no-cpu --no-adapt --no-semantic --no-graph > gpurun_out/launches.log 2>&1
            echo "launches rc=$?"; python scripts/launch_table.py gpurun_out/launches.csv | head -40 ;;
+    launches_graph) # the kernels of the REPLAYED graph, caches left warm between kernels as in the real step (still serialised by ncu)
+           timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --graph-profiling node -c 500 --csv --log-file gpurun_out/launches_graph.csv \
+             python bench.py --steps 3 --warmup 3 --no-cpu --no-adapt --no-semantic --no-variants > gpurun_out/launches_graph.log 2>&1
+           echo "launches_graph rc=$?"; python scripts/launch_table.py gpurun_out/launches_graph.csv | head -40 ;;
     launches_adapt) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_adapt.csv \
              python scripts/prof_adapt.py > gpurun_out/launches_adapt.log 2>&1
            echo "launches_adapt rc=$?"; python scripts/launch_table.py gpurun_out/launches_adapt.csv | head -30 ;;
