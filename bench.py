@@ -437,14 +437,17 @@ def run_ours(args):
 
 def bench_variants(torch, S, dsets, args):
     """The same step on the other code paths, graph replay, CUDA events (ms per step): the single-pass bf16 engine (tensor
-    operands rounded to bf16: loss within 3e-3, not the product path), the exact fp32 CUDA-core engine, and fused=False
-    (detector and descriptor losses as separately differentiable autograd nodes, what multi_task_loss needs)."""
+    operands rounded to bf16: loss within 3e-3, not the product path), the exact fp32 CUDA-core engine, fused=False
+    (detector and descriptor losses as separately differentiable autograd nodes) and the reference's multi_task_loss terms
+    (gradient through positive_dist / negative_dist instead of loss_desc, Train_model_heatmap_all.py:355-359)."""
     out = {}
     steps = max(5, min(args.steps, 20))
-    for name, engine, fused in (("bf16_single_pass", "bf16", True), ("fp32_cuda_cores", "fp32", True), ("bf16x3_unfused", "bf16x3", False)):
+    MT = ("loss_det", "loss_det_warp", "positive_dist", "negative_dist")  # the reference's multi_task_loss terms, unit weights
+    for name, engine, fused, keys in (("bf16_single_pass", "bf16", True, None), ("fp32_cuda_cores", "fp32", True, None),
+                                      ("bf16x3_unfused", "bf16x3", False, None), ("bf16x3_multitask_terms", "bf16x3", False, MT)):
         S.set_descriptor_engine(engine)
         try:
-            graphs = [S.step.GraphedLossStep(d, fused=fused) for d in dsets]
+            graphs = [S.step.GraphedLossStep(d, fused=fused, loss_keys=keys) for d in dsets]
             for i in range(3):
                 graphs[i % len(graphs)].replay()
             torch.cuda.synchronize()

@@ -121,8 +121,12 @@ class GraphedLossStep(object):
     IN_KEYS = ("semi", "semi_warp", "desc", "desc_warp", "labels_2D", "warped_labels", "mask_2D", "mask_warp_2D", "mat_H")
     SEM_KEYS = ("sem_pred", "sem_warp_pred", "sem", "warped_sem")  # optional: SSp configuration
 
-    def __init__(self, example, overlap=True, **kw):
+    def __init__(self, example, overlap=True, loss_keys=None, **kw):
+        """loss_keys: the outputs of loss_step whose sum is differentiated (needs fused=False), e.g. the reference's
+        multi-task weighting at unit weights: ("loss_det", "loss_det_warp", "positive_dist", "negative_dist")
+        (Train_model_heatmap_all.py:355-359).  Default: the uniform-weighting total `loss`."""
         self.kw = kw
+        self.loss_keys = loss_keys
         self.semantic = "sem_pred" in example
         if self.semantic:
             self.IN_KEYS = self.IN_KEYS + self.SEM_KEYS
@@ -149,7 +153,10 @@ class GraphedLossStep(object):
                         s["mask_warp_2D"], s["mat_H"], **kw)
         if getattr(self, "_one", None) is None:  # static dL/dloss = 1: no ones_like fill inside the captured step
             self._one = torch.ones_like(out["loss"])
-        out["loss"].backward(gradient=self._one)
+        total = out["loss"]
+        if self.loss_keys:
+            total = sum(out[k] for k in self.loss_keys[1:]) + out[self.loss_keys[0]]
+        total.backward(gradient=self._one)
         res = {k: v.detach() for k, v in out.items()}
         res["grads"] = [l.grad for l in leaves]
         return res
