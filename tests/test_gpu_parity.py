@@ -418,6 +418,34 @@ def test_descriptor_identity_kat(golden, engine):
     close(neg, g["neg"], rtol=rt); close(loss, g["loss"], rtol=rt)
 
 
+@pytest.mark.parametrize("dist", [2.0, 4.0, 6.0, 7.5, 8.0])
+def test_descriptor_dist_values(dist):
+    """descriptor_dist from well below cell/2 up to the supported maximum (= cell): the sparse positive lists come from a tight
+    candidate window, the returned pair mask from the full predicate -- both must agree with the oracle (loss, pos, neg and the
+    gradients through all three), including homographies that shrink (several rows share a partner column)."""
+    B, Hc, Wc = 3, 12, 16
+    D = synth.unit_descriptors(B, 256, Hc, Wc, 131, smooth=0.3)
+    Dw = synth.unit_descriptors(B, 256, Hc, Wc, 132, smooth=0.3)
+    Hs, _ = homographies(B, 41)
+    Hs[1] = np.array([[0.7, 0.0, 0.05], [0.0, 0.7, -0.05], [0.0, 0.0, 1.0]], np.float32)  # shrink: shared partner columns
+    mv = (synth.uniform((B, 1, Hc, Wc), 133) < 0.9).astype(np.float32)
+    g3 = (1.0, 0.5, 0.25)
+    r_loss, r_mask, r_pos, r_neg, r_dD, r_dDw = O.descriptor_loss(D, Dw, Hs, mv, descriptor_dist=dist, grad=g3, return_mask=True)
+    ref = {"loss": r_loss, "mask": r_mask, "pos": r_pos, "neg": r_neg, "dD": r_dD, "dDw": r_dDw}
+    for engine in ("fp32", "bf16x3"):
+        Dt, Dwt = cu(D).requires_grad_(True), cu(Dw).requires_grad_(True)
+        loss, mask, pos, neg = S.descriptor_loss(Dt, Dwt, cu(Hs), mask_valid=cu(mv), device=DEV, descriptor_dist=dist, engine=engine)
+        (g3[0] * loss + g3[1] * pos + g3[2] * neg).backward()
+        m = mask.materialize().reshape(B, Hc * Wc, Hc * Wc).cpu().numpy()
+        assert np.array_equal(m, np.asarray(ref["mask"]).reshape(m.shape)), (engine, dist)
+        assert m.sum() > 0
+        close(loss, ref["loss"], rtol=TOL); close(pos, ref["pos"], rtol=TOL); close(neg, ref["neg"], rtol=TOL)
+        for got, want in ((Dt.grad, ref["dD"]), (Dwt.grad, ref["dDw"])):
+            scale = np.abs(want).max()
+            err = np.abs(got.cpu().numpy() - want).reshape(B, 256, -1).max(axis=1)
+            assert (err > 2e-4 * scale).mean() < 0.02, (engine, dist, float((err > 2e-4 * scale).mean()))  # hinge-kink rows only
+
+
 def test_descriptor_engines_agree_b32():
     """Full BASELINE size (B=32, 240x320): the three engines agree; size-independent properties hold."""
     B = 32
