@@ -323,7 +323,9 @@ class DescriptorLossFn(torch.autograd.Function):
             fork.join()
 
         if step_total is not None:
-            det_out, lam_loss, total = step_total
+            det_out, lam_loss, total = step_total[:3]
+            if len(step_total) > 3 and step_total[3] is not None:
+                step_total[3].join()  # the detector losses ran on a forked stream (LossStepFn)
             call("ssp_desc_finalize", ptr(pos_part), npos, ptr(neg_part), nneg, ptr(mv_part), nmv, B, Hc, Wc, ptr(overflow),
                  ptr(out8), ptr(det_out[0]), ptr(det_out[1]), float(lam_loss), ptr(total), st)
         else:
@@ -444,12 +446,24 @@ class LossStepFn(torch.autograd.Function):
     def forward(ctx, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, desc, desc_w, Hm, lamda_d, dist,
                 lambda_loss, engine, dist_group=None):
         c1 = _Ctx((ctx.needs_input_grad[0], False, False, ctx.needs_input_grad[3], False, False, False, False))
-        l0, l1, cellmask = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
         B, _, Hc, Wc = semi.shape
+        dev = semi.device
+        # The two detector losses (HBM-bound, + their one-block finalize) run on a forked stream next to the first half of
+        # the descriptor chain (geometry -> pack -> positive pairs: a mix of HBM- and latency-bound kernels): nothing there
+        # needs them except the cell mask of the warped valid mask, which one small kernel computes here.  The streams join
+        # in front of desc_finalize, which reads both detector triples for the step total.
+        fork = _Fork(dev)
+        with fork:
+            l0, l1, _cm = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
+        mw = f32c(mask_warp_2D.detach(), dev)
+        if mw.numel() != B * Hc * Wc * 64:
+            raise RuntimeError("loss_step: mask_warp_2D must be [B,1,%d,%d]" % (Hc * 8, Wc * 8))
+        cellmask = torch.empty((B, Hc, Wc), dtype=torch.float32, device=dev)
+        call("ssp_cell_mask", ptr(mw), B, Hc * 8, Wc * 8, ptr(cellmask), stream_of(mw))
         c2 = _Ctx((ctx.needs_input_grad[6], ctx.needs_input_grad[7]) + (False,) * 8)
-        total = torch.empty((1,), dtype=torch.float32, device=semi.device)
+        total = torch.empty((1,), dtype=torch.float32, device=dev)
         ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine,
-                                                       None, None, FOLD_ALPHA, (c1.out, lambda_loss, total))
+                                                       None, None, FOLD_ALPHA, (c1.out, lambda_loss, total, fork))
         if dist_group is not None:
             # multi-GPU: ONE exchange kernel turns the three local results into global-batch values in place (the scalars
             # above are views of c1.out / c2.out8) and rewrites the weighted total; the backward kernels read the global

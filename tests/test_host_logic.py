@@ -155,12 +155,13 @@ def test_orchestration_call_sequences(monkeypatch):
            "ssp_desc_dense_fwd_tc", "ssp_desc_finalize"]
     # one-node fused step: the mask is folded into the indicator words, no pack pass in the backward, both GEMMs in one launch
     bwd_fold = ["ssp_desc_alpha", "ssp_desc_pos_coef", "ssp_desc_bits_gemm_tc_pair"]
-    assert run() == fwd + ["ssp_detector_loss_bwd_pair"] + bwd_fold
+    # (the fused step launches the detector pair on a forked stream and computes the cell mask of the warped valid mask itself)
+    assert run() == fwd[:1] + ["ssp_cell_mask"] + fwd[1:] + ["ssp_detector_loss_bwd_pair"] + bwd_fold
     # separately differentiable components (reference multi_task_loss weighting): general mask path with the pack pass
     bwd_desc = ["ssp_desc_alpha", "ssp_desc_pos_coef", "ssp_desc_pack", "ssp_desc_bits_gemm_tc_pair"]
     unfused = run(fused=False)
     assert unfused[:6] == fwd and sorted(unfused[6:]) == sorted(bwd_desc + ["ssp_detector_loss_bwd_pair"])
-    assert [c for c in run(engine="fp32") if "desc" in c] == [
+    assert [c for c in run(engine="fp32") if "_desc_" in c] == [
         "ssp_desc_geometry", "ssp_desc_pos_fwd", "ssp_desc_dense_fwd_simt", "ssp_desc_finalize", "ssp_desc_alpha",
         "ssp_desc_pos_coef", "ssp_desc_bits_gemm_simt", "ssp_desc_bits_gemm_simt", "ssp_desc_pos_apply"]
     assert "ssp_desc_pos_fwd" in run(engine="bf16") and "ssp_desc_pos_fwd_planes" not in run(engine="bf16")
