@@ -123,8 +123,9 @@ int ssp_box_nms(const float* prob /*[I,H,W]*/, int I, int H, int W, float min_pr
  *      mvbits (optional, [B,Nc_pad/32] u32): mask_valid != 0 per cell in the same bit order, for the "fold" mode of the
  *      tensor-core engine (mask folded into the indicator words; a non-binary mask then poisons the normaliser: NaN) ---- */
 int ssp_desc_geometry_nblocks(int B, int Nc);
-int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/, int B, int Hc, int Wc,
-                      int cell, float* wpts, float* mv_pad, double* mv_part /*[geometry_nblocks]*/,
+int ssp_desc_geometry(const float* H /*[B,3,3]*/, const float* mask_valid /*[B,Nc] or NULL*/,
+                      const float* mask2d /*or NULL; used when mask_valid is NULL: [B,1,8Hc,8Wc], getMasks fused in*/, int B,
+                      int Hc, int Wc, int cell, float* wpts, float* mv_pad, double* mv_part /*[geometry_nblocks]*/,
                       uint32_t* mvbits /*or NULL*/, void* stream);
 int ssp_desc_pos_nblocks(int B, int Nc);
 int ssp_desc_maxp(void); /* DESC_MAXP: list slots per row / column */
@@ -170,11 +171,13 @@ int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)
                    void* stream);
 /* backward coefficients of the positive pairs (and removal of their negative term).  colrow_sorted receives the column
  * lists ordered by row index (deterministic summation order) with their coefficients in colcoef; the forward's lists
- * are left untouched, so a second backward over the same graph sees the same inputs */
+ * are left untouched, so a second backward over the same graph sees the same inputs.
+ * g3: gmode 0 -> {dL/dloss, dL/dpos, dL/dneg}; gmode 1 -> g3[0] = dL/dloss only (fused step); both scaled by gscale.
+ * alpha_out / srow_out (optional, [B,Nc_pad]): what ssp_desc_alpha would write for the same scaled gradients. */
 int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow, const float* coldot,
-                      const uint32_t* bitsR, const float* mv_pad, const float* alpha, const float* g3,
+                      const uint32_t* bitsR, const float* mv_pad, const float* g3, float gscale, int gmode,
                       const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, int* colrow_sorted,
-                      float* colcoef, void* stream);
+                      float* colcoef, float* alpha_out, float* srow_out, void* stream);
 /* dD[b,:,r] += sum_n rowcoef[b,r,n] Dw[b,:,rowcol[b,r,n]];  dDw[b,:,c] += sum_n colcoef[b,c,n] D[b,:,colrow[b,c,n]] */
 int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef, const float* D,
                        const float* Dw, int B, int Dch, int Nc, int which /*0 both, 1 dD, 2 dDw*/, float* dD, float* dDw,

@@ -7,7 +7,10 @@
 // ----------------------------------------------------------------------------------------------
 // geometry: warped cell centres  w = denorm(swap(warp(swap(norm(c)))))   [utils/utils.py:829-851]
 // ----------------------------------------------------------------------------------------------
-__global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* __restrict__ mask_valid, int B,
+// mask_valid [B, Nc] (cell resolution) or, when it is NULL, mask2d [B, 1, 8 Hc, 8 Wc]: the cell mask is then the product of
+// the 64 sub-pixels of every cell, in the order of getMasks / cell_mask_kernel (Train_model_frontend_all.py:373-386).
+__global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* __restrict__ mask_valid,
+                                     const float* __restrict__ mask2d, int B,
                                      int Hc, int Wc, int cell, int Nc_pad, float2* __restrict__ wpts,
                                      float* __restrict__ mv_pad, double* __restrict__ mv_part,
                                      uint32_t* __restrict__ mvbits) {
@@ -30,6 +33,24 @@ __global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* 
     w.x = (ox + 1.f) * Wpx / 2.f;
     w.y = (oy + 1.f) * Hpx / 2.f;
     mv = mask_valid ? mask_valid[(size_t)b * Nc + c] : 1.f;
+    if (!mask_valid && mask2d) {
+      const int W = Wc * 8;
+      const float* img = mask2d + (size_t)b * Nc * 64 + (size_t)((c / Wc) * 8) * W + (c % Wc) * 8;
+      float p = 1.f;
+      bool first = true;
+#pragma unroll
+      for (int dy = 0; dy < 8; ++dy) {
+        const float4* r = reinterpret_cast<const float4*>(img + (size_t)dy * W);
+        const float4 a = __ldg(r), q = __ldg(r + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int dx = 0; dx < 8; ++dx) {
+          p = first ? v[dx] : p * v[dx];
+          first = false;
+        }
+      }
+      mv = p;
+    }
   }
   wpts[(size_t)b * Nc_pad + c] = w;
   mv_pad[(size_t)b * Nc_pad + c] = mv;
@@ -50,13 +71,17 @@ extern "C" int ssp_desc_geometry_nblocks(int B, int Nc) { return B * (desc_nc_pa
 
 // mvbits (optional): [B, Nc_pad/32] words of mask_valid != 0 in DESC_BITPOS order for the "fold" mode of the tensor-core
 // engine; requesting them also makes a non-binary mask poison the normaliser with NaN.
-extern "C" int ssp_desc_geometry(const float* Hm, const float* mask_valid, int B, int Hc, int Wc, int cell,
+// mask2d (optional, used when mask_valid is NULL): the pixel-resolution mask [B,1,8Hc,8Wc] the cell mask is the product of
+// (getMasks fused in; cell must be 8).
+extern "C" int ssp_desc_geometry(const float* Hm, const float* mask_valid, const float* mask2d, int B, int Hc, int Wc, int cell,
                                  float* wpts, float* mv_pad, double* mv_part, uint32_t* mvbits, void* stream) {
   SSP_REQUIRE(Hm && wpts && mv_pad && mv_part, "ssp_desc_geometry: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Hc > 0 && Wc > 0 && cell > 0, "ssp_desc_geometry: bad sizes");
+  SSP_REQUIRE(!mask2d || mask_valid || (cell == 8 && ((uintptr_t)mask2d & 15) == 0),
+              "ssp_desc_geometry: the fused pixel mask needs cell_size 8 and a 16-byte aligned mask");
   int Nc_pad = desc_nc_pad(Hc * Wc);
   dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
-  desc_geometry_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Hm, mask_valid, B, Hc, Wc, cell, Nc_pad,
+  desc_geometry_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Hm, mask_valid, mask2d, B, Hc, Wc, cell, Nc_pad,
                                                                 reinterpret_cast<float2*>(wpts), mv_pad, mv_part, mvbits);
   SSP_CUDA_CHECK_LAUNCH("desc_geometry_kernel");
   return SSP_OK;
@@ -536,38 +561,51 @@ extern "C" int ssp_desc_alpha(const float* mv_pad, const float* g3, const float*
 //   rows: rowcoef[b,r,n] for partner column rowcol[b,r,n]          (dD [b,:,r] += coef * Dw[b,:,c])
 //   cols: entries sorted by row index (deterministic sum order), colcoef (dDw[b,:,c] += coef * D [b,:,r])
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float pos_coef(float dot, float mv, const float* __restrict__ g3, float norm, float lamda,
-                                          float mpos) {
+struct PosG {  // upstream gradients of (loss, pos, neg) and the normaliser, loaded once per thread
+  float gl, gp, gn, norm;
+};
+__device__ __forceinline__ float pos_coef(float dot, float mv, const PosG& G, float lamda, float mpos) {
   float x = mpos - dot;
   float ind = x > 0.f ? 1.f : (x == 0.f ? 0.5f : 0.f);
-  return -lamda * ind * (g3[0] * mv + g3[1]) / norm;
+  return -lamda * ind * (G.gl * mv + G.gp) / G.norm;
 }
+// coefficient of the negative hinge of a column with mask value mv (what desc_alpha_kernel writes)
+__device__ __forceinline__ float neg_alpha(float mv, const PosG& G) { return (G.gl * mv + G.gn) / G.norm; }
 
 // N = number of list slots handled (4: vector loads, the common case; DESC_MAXP: any list).  Lists are filled front to
 // back, so a row list with slot 3 empty / a column count <= 4 is complete within the first 4 slots.
 template <int N>
-__device__ __forceinline__ void pos_coef_rows(const int* __restrict__ rowcol, const float* __restrict__ rowdot, size_t base,
-                                              int b, int cell, int Nc_pad, int NW, const uint32_t* __restrict__ bitsR,
-                                              const float* __restrict__ mv_pad, const float* __restrict__ alpha,
-                                              const float* __restrict__ g3, float norm, float lamda, float mpos,
-                                              float* __restrict__ rowcoef) {
+__device__ __forceinline__ void pos_coef_rows(const int (&c4)[4], const float (&d4)[4], const int* __restrict__ rowcol,
+                                              const float* __restrict__ rowdot, size_t base, int b, int cell, int Nc_pad, int NW,
+                                              const uint32_t* __restrict__ bitsR, const float* __restrict__ mv_pad,
+                                              const PosG& G, float lamda, float mpos, float* __restrict__ rowcoef) {
   int cc[N];
   float dd[N], cf[N];
 #pragma unroll
-  for (int n = 0; n < N; n += 4) {
-    int4 c4 = *reinterpret_cast<const int4*>(rowcol + base + n);
-    float4 d4 = *reinterpret_cast<const float4*>(rowdot + base + n);
-    cc[n] = c4.x; cc[n + 1] = c4.y; cc[n + 2] = c4.z; cc[n + 3] = c4.w;
-    dd[n] = d4.x; dd[n + 1] = d4.y; dd[n + 2] = d4.z; dd[n + 3] = d4.w;
+  for (int n = 0; n < 4; ++n) { cc[n] = c4[n]; dd[n] = d4[n]; }
+#pragma unroll
+  for (int n = 4; n < N; n += 4) {
+    int4 c = *reinterpret_cast<const int4*>(rowcol + base + n);
+    float4 d = *reinterpret_cast<const float4*>(rowdot + base + n);
+    cc[n] = c.x; cc[n + 1] = c.y; cc[n + 2] = c.z; cc[n + 3] = c.w;
+    dd[n] = d.x; dd[n + 1] = d.y; dd[n + 2] = d.z; dd[n + 3] = d.w;
+  }
+  // the dependent gathers (mask value and indicator word of every partner) are issued together, then consumed
+  float mvc[N];
+  uint32_t wc[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const int c = cc[n];
+    mvc[n] = c >= 0 ? __ldg(mv_pad + (size_t)b * Nc_pad + c) : 0.f;
+    wc[n] = c >= 0 ? __ldg(bitsR + ((size_t)b * NW + (c >> 5)) * Nc_pad + cell) : 0u;
   }
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     float coef = 0.f;
-    int c = cc[n];
+    const int c = cc[n];
     if (c >= 0) {
-      coef = pos_coef(dd[n], mv_pad[(size_t)b * Nc_pad + c], g3, norm, lamda, mpos);
-      uint32_t w = bitsR[((size_t)b * NW + (c >> 5)) * Nc_pad + cell];
-      if ((w >> DESC_BITPOS(c & 31)) & 1u) coef -= alpha[(size_t)b * Nc_pad + c];
+      coef = pos_coef(dd[n], mvc[n], G, lamda, mpos);
+      if ((wc[n] >> DESC_BITPOS(c & 31)) & 1u) coef -= neg_alpha(mvc[n], G);
     }
     cf[n] = coef;
   }
@@ -577,18 +615,25 @@ __device__ __forceinline__ void pos_coef_rows(const int* __restrict__ rowcol, co
 }
 
 template <int N>
-__device__ __forceinline__ void pos_coef_cols(int cnt, const int* __restrict__ colrow, const float* __restrict__ coldot, size_t base,
-                                              int b, int cell, int Nc_pad, int NW, const uint32_t* __restrict__ bitsR,
-                                              float mv, float al, const float* __restrict__ g3, float norm, float lamda,
+__device__ __forceinline__ void pos_coef_cols(int cnt, const int (&r4)[4], const float (&d4)[4], const int* __restrict__ colrow,
+                                              const float* __restrict__ coldot, size_t base, int b, int cell, int Nc_pad, int NW,
+                                              const uint32_t* __restrict__ bitsR, float mv, const PosG& G, float lamda,
                                               float mpos, int* __restrict__ colrow_sorted, float* __restrict__ colcoef) {
   int rr[N];
   float dd[N];
 #pragma unroll
   for (int n = 0; n < N; n += 4) {
-    int4 r4 = *reinterpret_cast<const int4*>(colrow + base + n);
-    float4 d4 = *reinterpret_cast<const float4*>(coldot + base + n);
-    int rv[4] = {r4.x, r4.y, r4.z, r4.w};
-    float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+    int rv[4];
+    float dv[4];
+    if (n == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { rv[u] = r4[u]; dv[u] = d4[u]; }
+    } else {
+      int4 r = *reinterpret_cast<const int4*>(colrow + base + n);
+      float4 d = *reinterpret_cast<const float4*>(coldot + base + n);
+      rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+      dv[0] = d.x; dv[1] = d.y; dv[2] = d.z; dv[3] = d.w;
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       rr[n + u] = n + u < cnt ? rv[u] : 0x7fffffff;  // slots past the count were never written
@@ -604,15 +649,18 @@ __device__ __forceinline__ void pos_coef_cols(int cnt, const int* __restrict__ c
         int t = rr[j]; rr[j] = rr[j - 1]; rr[j - 1] = t;
         float u = dd[j]; dd[j] = dd[j - 1]; dd[j - 1] = u;
       }
+  uint32_t wr[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+    wr[n] = n < cnt ? __ldg(bitsR + ((size_t)b * NW + (cell >> 5)) * Nc_pad + rr[n]) : 0u;
+  const float al = neg_alpha(mv, G);
   float cf[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     cf[n] = 0.f;
     if (n < cnt) {
-      int r = rr[n];
-      float coef = pos_coef(dd[n], mv, g3, norm, lamda, mpos);
-      uint32_t w = bitsR[((size_t)b * NW + (cell >> 5)) * Nc_pad + r];
-      if ((w >> DESC_BITPOS(cell & 31)) & 1u) coef -= al;
+      float coef = pos_coef(dd[n], mv, G, lamda, mpos);
+      if ((wr[n] >> DESC_BITPOS(cell & 31)) & 1u) coef -= al;
       cf[n] = coef;
     } else {
       rr[n] = -1;
@@ -628,45 +676,67 @@ __device__ __forceinline__ void pos_coef_cols(int cnt, const int* __restrict__ c
   for (int n = N; n < DESC_MAXP; n += 4) *reinterpret_cast<int4*>(colrow_sorted + base + n) = make_int4(-1, -1, -1, -1);
 }
 
+// blockIdx.z = 0: row lists (+ the alpha / srow vectors of the backward GEMMs, when asked for); 1: column lists.  One thread
+// per cell; the kernel is a chain of dependent gathers, so the first four slots of a list, the column count and the mask
+// value are loaded before anything is looked at, and the second-level gathers of a list are issued together.
+// gmode 0: g3 = {dL/dloss, dL/dpos, dL/dneg};  1: g3[0] = dL/dloss only (the fused step).  Everything is scaled by gscale.
 __global__ void __launch_bounds__(128)
 desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ rowdot,
                      const int* __restrict__ colcnt, const int* __restrict__ colrow,
                      const float* __restrict__ coldot, const uint32_t* __restrict__ bitsR,
-                     const float* __restrict__ mv_pad, const float* __restrict__ alpha,
-                     const float* __restrict__ g3, const float* __restrict__ out8, int Nc_pad,
-                     float lamda, float mpos, float* __restrict__ rowcoef, int* __restrict__ colrow_sorted,
-                     float* __restrict__ colcoef) {
-  int b = blockIdx.y;
-  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+                     const float* __restrict__ mv_pad, const float* __restrict__ g3, float gscale, int gmode,
+                     const float* __restrict__ out8, int Nc_pad, float lamda, float mpos, float* __restrict__ rowcoef,
+                     int* __restrict__ colrow_sorted, float* __restrict__ colcoef, float* __restrict__ alpha_out,
+                     float* __restrict__ srow_out) {
+  const int b = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= Nc_pad) return;
   const int NW = Nc_pad / 32;
-  const float norm = out8[3];
-  size_t base = ((size_t)b * Nc_pad + cell) * DESC_MAXP;
-  // row list of cell = r.  A cell has 0.8 partners on average (descriptor_dist 4 on an 8-pixel grid): the 4-slot path
-  // is the one that runs; longer lists (descriptor_dist close to the cell size, strong minification) take the full one.
-  if (rowcol[base + 3] < 0)
-    pos_coef_rows<4>(rowcol, rowdot, base, b, cell, Nc_pad, NW, bitsR, mv_pad, alpha, g3, norm, lamda, mpos, rowcoef);
-  else
-    pos_coef_rows<DESC_MAXP>(rowcol, rowdot, base, b, cell, Nc_pad, NW, bitsR, mv_pad, alpha, g3, norm, lamda, mpos, rowcoef);
-  // column list of cell = c
-  int cnt = min(colcnt[(size_t)b * Nc_pad + cell], DESC_MAXP);
-  float mv = mv_pad[(size_t)b * Nc_pad + cell], al = alpha[(size_t)b * Nc_pad + cell];
-  if (cnt <= 4)
-    pos_coef_cols<4>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colrow_sorted, colcoef);
-  else
-    pos_coef_cols<DESC_MAXP>(cnt, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, al, g3, norm, lamda, mpos, colrow_sorted, colcoef);
+  const size_t base = ((size_t)b * Nc_pad + cell) * DESC_MAXP;
+  const bool cols = blockIdx.z != 0;
+  // first-level loads, all independent
+  const int4 l4 = *reinterpret_cast<const int4*>((cols ? colrow : rowcol) + base);
+  const float4 f4 = *reinterpret_cast<const float4*>((cols ? coldot : rowdot) + base);
+  const int cnt_raw = cols ? colcnt[(size_t)b * Nc_pad + cell] : 0;
+  const float mv = mv_pad[(size_t)b * Nc_pad + cell];
+  PosG G;
+  G.gl = g3[0] * gscale;
+  G.gp = gmode ? 0.f : g3[1] * gscale;
+  G.gn = gmode ? 0.f : g3[2] * gscale;
+  G.norm = out8[3];
+  const int li[4] = {l4.x, l4.y, l4.z, l4.w};
+  const float lf[4] = {f4.x, f4.y, f4.z, f4.w};
+  if (!cols) {
+    if (alpha_out) alpha_out[(size_t)b * Nc_pad + cell] = neg_alpha(mv, G);
+    if (srow_out) srow_out[(size_t)b * Nc_pad + cell] = neg_alpha(1.f, G);
+    // A cell has 0.8 partners on average (descriptor_dist 4 on an 8-pixel grid): the 4-slot path is the one that runs;
+    // longer lists (descriptor_dist close to the cell size, strong minification) take the full one.
+    if (li[3] < 0)
+      pos_coef_rows<4>(li, lf, rowcol, rowdot, base, b, cell, Nc_pad, NW, bitsR, mv_pad, G, lamda, mpos, rowcoef);
+    else
+      pos_coef_rows<DESC_MAXP>(li, lf, rowcol, rowdot, base, b, cell, Nc_pad, NW, bitsR, mv_pad, G, lamda, mpos, rowcoef);
+  } else {
+    const int cnt = min(cnt_raw, DESC_MAXP);
+    if (cnt <= 4)
+      pos_coef_cols<4>(cnt, li, lf, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, G, lamda, mpos, colrow_sorted, colcoef);
+    else
+      pos_coef_cols<DESC_MAXP>(cnt, li, lf, colrow, coldot, base, b, cell, Nc_pad, NW, bitsR, mv, G, lamda, mpos, colrow_sorted, colcoef);
+  }
 }
 
+// alpha_out / srow_out (optional, [B, Nc_pad]): the vectors ssp_desc_alpha would write for the same (scaled) gradients -- the
+// fused step gets them from this launch and skips that kernel.
 extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow,
-                                 const float* coldot, const uint32_t* bitsR, const float* mv_pad, const float* alpha,
-                                 const float* g3, const float* out8, int B, int Nc_pad, float lamda, float mpos,
-                                 float* rowcoef, int* colrow_sorted, float* colcoef, void* stream) {
-  SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && alpha && g3 && out8 && rowcoef &&
-                  colrow_sorted && colcoef, "ssp_desc_pos_coef: null pointer");
-  SSP_REQUIRE(B > 0 && B <= 65535 && Nc_pad > 0 && Nc_pad % DESC_PAD == 0, "ssp_desc_pos_coef: bad sizes");
-  dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
-  desc_pos_coef_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rowcol, rowdot, colcnt, colrow, coldot, bitsR, mv_pad, alpha,
-                                                               g3, out8, Nc_pad, lamda, mpos, rowcoef, colrow_sorted, colcoef);
+                                 const float* coldot, const uint32_t* bitsR, const float* mv_pad, const float* g3, float gscale,
+                                 int gmode, const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef,
+                                 int* colrow_sorted, float* colcoef, float* alpha_out, float* srow_out, void* stream) {
+  SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && g3 && out8 && rowcoef && colrow_sorted && colcoef,
+              "ssp_desc_pos_coef: null pointer");
+  SSP_REQUIRE(B > 0 && B <= 65535 && Nc_pad > 0 && Nc_pad % DESC_PAD == 0 && (gmode == 0 || gmode == 1), "ssp_desc_pos_coef: bad sizes");
+  dim3 grid(ssp_ceil_div(Nc_pad, 128), B, 2);
+  desc_pos_coef_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rowcol, rowdot, colcnt, colrow, coldot, bitsR, mv_pad, g3, gscale, gmode,
+                                                               out8, Nc_pad, lamda, mpos, rowcoef, colrow_sorted, colcoef, alpha_out,
+                                                               srow_out);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_coef_kernel");
   return SSP_OK;
 }

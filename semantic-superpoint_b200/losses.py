@@ -270,7 +270,10 @@ class DescriptorLossFn(torch.autograd.Function):
         mvbits = torch.empty((B, Ncp // 32), dtype=torch.int32, device=dev) if fold_alpha else None
         nmv = lib.ssp_desc_geometry_nblocks(B, Nc)
         mv_part = torch.empty((nmv,), dtype=torch.float64, device=dev)
-        call("ssp_desc_geometry", ptr(Hm), ptr(mv), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), ptr(mvbits), st)
+        mask2d = None
+        if isinstance(mv, tuple):  # ("2d", mask [B,1,8Hc,8Wc]): LossStepFn -- getMasks is fused into the geometry kernel
+            mask2d, mv = mv[1], None
+        call("ssp_desc_geometry", ptr(Hm), ptr(mv), ptr(mask2d), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), ptr(mvbits), st)
 
         # sparse positive pairs: exact dots, partial sums, pair lists for the backward
         maxp = lib.ssp_desc_maxp()
@@ -357,18 +360,28 @@ class DescriptorLossFn(torch.autograd.Function):
         Nc = Hc * Wc
         Ncp = _nc_pad(Nc)
         st = stream_of(Dc)
-        if g_pos is _SAME:  # fused step: g_loss already is the [g_loss, g_pos, g_neg] device vector
-            g3 = g_loss
+        tc_engine = engine != "fp32"
+        fold = tc_engine and getattr(ctx, "fold_alpha", False)
+        gscale, gmode = 1.0, 0
+        if g_pos is _SAME:  # fused step: g_loss is the upstream gradient of the step total (one element), to be scaled by lambda_loss
+            lam = float(getattr(ctx, "gscale", 1.0))
+            if fold:
+                g3, gscale, gmode = g_loss, lam, 1  # the coefficient kernel applies the scale itself: no torch kernel here
+            else:
+                key = (dev.index, lam)
+                if key not in _lam3:
+                    _lam3[key] = torch.tensor([lam, 0.0, 0.0], dtype=torch.float32, device=dev)
+                g3 = g_loss * _lam3[key]
         else:
             zero = torch.zeros((), dtype=torch.float32, device=dev)
             g3 = torch.stack([(g if g is not None else zero).reshape(()).to(torch.float32) for g in (g_loss, g_pos, g_neg)])
             g3 = g3.contiguous()
-        # alpha[b,c] = (g_loss * mv[c] + g_neg) / norm: coefficient of the negative hinge of column c
-        tc_engine = engine != "fp32"
-        fold = tc_engine and getattr(ctx, "fold_alpha", False)
+        # alpha[b,c] = (g_loss * mv[c] + g_neg) / norm: coefficient of the negative hinge of column c; srow = alpha at mv = 1
+        # (row scale of the folded backward).  Folded: both come out of the coefficient kernel below.
         alpha = torch.empty((B, Ncp), dtype=torch.float32, device=dev)
-        srow = torch.empty((B, Ncp), dtype=torch.float32, device=dev) if fold else None  # folded backward: s = alpha at mv = 1
-        call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), ptr(srow), st)
+        srow = torch.empty((B, Ncp), dtype=torch.float32, device=dev) if fold else None
+        if not fold:
+            call("ssp_desc_alpha", ptr(mv_pad), ptr(g3), ptr(out8), B, Ncp, ptr(alpha), None, st)
         rowcol, colrow, colcnt = lists_i[0], lists_i[1], lists_i[2]
         rowdot, coldot = lists_f[0], lists_f[1]
         coefs = torch.empty((2,) + tuple(rowdot.shape), dtype=torch.float32, device=dev)
@@ -389,18 +402,20 @@ class DescriptorLossFn(torch.autograd.Function):
         # epilogues (dedicated epilogue warps hide the gathers behind the next item's main loop);
         # fp32 engine: one streaming apply kernel after the GEMMs.
         # stream plan:  [pos_coef]  ||  [pack(alpha * Dw), unless folded]  ->  GEMM pair
-        with _Fork(dev) as f1:
-            call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
-                 ptr(mv_pad), ptr(alpha), ptr(g3), ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
-                 ptr(coefs[1]), stream_of(Dc))
         if fold:
             # bitsR / bitsC already exclude the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
-            f1.join()
+            call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
+                 ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
+                 ptr(coefs[1]), ptr(alpha), ptr(srow), st)
             call("ssp_desc_bits_gemm_tc_pair",
                  ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]), ptr(Bhi), ptr(Blo), ptr(dD),
                  ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow_sorted), ptr(coefs[1]), ptr(Ahi), ptr(Alo), ptr(dDw),
                  B, Nc, st)
         elif tc_engine:
+            with _Fork(dev) as f1:
+                call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
+                     ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
+                     ptr(coefs[1]), None, None, stream_of(Dc))
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
             f1.join()
             # positive-pair partners from the packed planes of the forward (Dw for dD, D for dDw)
@@ -409,6 +424,10 @@ class DescriptorLossFn(torch.autograd.Function):
                  ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow_sorted), ptr(coefs[1]), ptr(Ahi), ptr(Alo), ptr(dDw),
                  B, Nc, st)
         else:
+            with _Fork(dev) as f1:
+                call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
+                     ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
+                     ptr(coefs[1]), None, None, stream_of(Dc))
             call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
             call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
             f1.join()
@@ -450,19 +469,17 @@ class LossStepFn(torch.autograd.Function):
         dev = semi.device
         # The two detector losses (HBM-bound, + their one-block finalize) run on a forked stream next to the first half of
         # the descriptor chain (geometry -> pack -> positive pairs: a mix of HBM- and latency-bound kernels): nothing there
-        # needs them except the cell mask of the warped valid mask, which one small kernel computes here.  The streams join
-        # in front of desc_finalize, which reads both detector triples for the step total.
+        # needs them except the cell mask of the warped valid mask, which the geometry kernel computes itself (getMasks fused
+        # in).  The streams join in front of desc_finalize, which reads both detector triples for the step total.
         fork = _Fork(dev)
         with fork:
             l0, l1, _cm = DetectorLossPairFn.forward(c1, semi, labels_2D, mask_2D, semi_w, warped_labels, mask_warp_2D, True)
         mw = f32c(mask_warp_2D.detach(), dev)
         if mw.numel() != B * Hc * Wc * 64:
             raise RuntimeError("loss_step: mask_warp_2D must be [B,1,%d,%d]" % (Hc * 8, Wc * 8))
-        cellmask = torch.empty((B, Hc, Wc), dtype=torch.float32, device=dev)
-        call("ssp_cell_mask", ptr(mw), B, Hc * 8, Wc * 8, ptr(cellmask), stream_of(mw))
         c2 = _Ctx((ctx.needs_input_grad[6], ctx.needs_input_grad[7]) + (False,) * 8)
         total = torch.empty((1,), dtype=torch.float32, device=dev)
-        ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, cellmask.reshape(B, -1), 8, lamda_d, dist, engine,
+        ld, pos, neg, _wpts = DescriptorLossFn.forward(c2, desc, desc_w, Hm, ("2d", mw), 8, lamda_d, dist, engine,
                                                        None, None, FOLD_ALPHA, (c1.out, lambda_loss, total, fork))
         if dist_group is not None:
             # multi-GPU: ONE exchange kernel turns the three local results into global-batch values in place (the scalars
@@ -483,15 +500,13 @@ class LossStepFn(torch.autograd.Function):
         if g is None:
             return (None,) * 14
         dev = g.device
-        key = (dev.index, ctx.lambda_loss)
-        if key not in _lam3:
-            _lam3[key] = torch.tensor([ctx.lambda_loss, 0.0, 0.0], dtype=torch.float32, device=dev)
         g = f32c(g.reshape(1), dev)
         d0 = d1 = dD = dDw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
             d0, _, _, d1 = DetectorLossPairFn.backward(ctx.c1, g, _SAME, None)[:4]
         if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
-            dD, dDw = DescriptorLossFn.backward(ctx.c2, g * _lam3[key], _SAME, None, None)[:2]
+            ctx.c2.gscale = ctx.lambda_loss
+            dD, dDw = DescriptorLossFn.backward(ctx.c2, g, _SAME, None, None)[:2]
         return d0, None, None, d1, None, None, dD, dDw, None, None, None, None, None, None
 
 
