@@ -173,11 +173,12 @@ int ssp_desc_alpha(const float* mv_pad, const float* g3 /*[3] dL/d(loss,pos,neg)
  * lists ordered by row index (deterministic summation order) with their coefficients in colcoef; the forward's lists
  * are left untouched, so a second backward over the same graph sees the same inputs.
  * g3: gmode 0 -> {dL/dloss, dL/dpos, dL/dneg}; gmode 1 -> g3[0] = dL/dloss only (fused step); both scaled by gscale.
- * alpha_out / srow_out (optional, [B,Nc_pad]): what ssp_desc_alpha would write for the same scaled gradients. */
+ * alpha_out / srow_out (optional, [B,Nc_pad]): what ssp_desc_alpha would write for the same scaled gradients.
+ * bitsC_out (optional, then Nc = unpadded cell count): bitsC transposed from bitsR by extra blocks of the same launch. */
 int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow, const float* coldot,
                       const uint32_t* bitsR, const float* mv_pad, const float* g3, float gscale, int gmode,
                       const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, int* colrow_sorted,
-                      float* colcoef, float* alpha_out, float* srow_out, void* stream);
+                      float* colcoef, float* alpha_out, float* srow_out, uint32_t* bitsC_out, int Nc, void* stream);
 /* dD[b,:,r] += sum_n rowcoef[b,r,n] Dw[b,:,rowcol[b,r,n]];  dDw[b,:,c] += sum_n colcoef[b,c,n] D[b,:,colrow[b,c,n]] */
 int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef, const float* D,
                        const float* Dw, int B, int Dch, int Nc, int which /*0 both, 1 dD, 2 dDw*/, float* dD, float* dDw,

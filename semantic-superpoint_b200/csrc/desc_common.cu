@@ -687,11 +687,37 @@ desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ r
                      const float* __restrict__ mv_pad, const float* __restrict__ g3, float gscale, int gmode,
                      const float* __restrict__ out8, int Nc_pad, float lamda, float mpos, float* __restrict__ rowcoef,
                      int* __restrict__ colrow_sorted, float* __restrict__ colcoef, float* __restrict__ alpha_out,
-                     float* __restrict__ srow_out) {
+                     float* __restrict__ srow_out, uint32_t* __restrict__ bitsC_out, int NWv) {
   const int b = blockIdx.y;
+  const int NW = Nc_pad / 32;
+  if (blockIdx.z >= 2) {
+    // ---- blocks of z = 2..5: bitsC = transpose of bitsR (only the backward GEMM reads it, so it is made here, inside a launch
+    // whose other blocks are chains of dependent gathers: the streaming transposes fill the memory pipe they leave idle).
+    //   bitsR[b][cw][r]: bit DESC_BITPOS(j) = indicator(row r, column 32 cw + j);  bitsC[b][rw][c]: bit DESC_BITPOS(i) =
+    //   indicator(row 32 rw + i, column c).  One warp per 32 x 32 tile, lane L holds the word of row 32 rw + inv(L).
+    const int rw = ((int)blockIdx.z - 2) * gridDim.x + blockIdx.x;  // gridDim.x = Nc_pad / 128, four z slices: rw < NW
+    if (rw >= NW) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int rl = ((lane & 15) << 1) | (lane >> 4);
+    for (int cw0 = warp; cw0 < NW; cw0 += 4 * nwarp) {
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cw = cw0 + nwarp * u;
+        // words beyond the valid range were never written by the forward: they transpose to zero
+        w[u] = (cw < NWv && rw < NWv) ? __ldg(bitsR + ((size_t)b * NW + cw) * Nc_pad + rw * 32 + rl) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cw = cw0 + nwarp * u;
+        if (cw >= NW) break;
+        bitsC_out[((size_t)b * NW + rw) * Nc_pad + cw * 32 + rl] = warp_transpose32(w[u], lane);
+      }
+    }
+    return;
+  }
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= Nc_pad) return;
-  const int NW = Nc_pad / 32;
   const size_t base = ((size_t)b * Nc_pad + cell) * DESC_MAXP;
   const bool cols = blockIdx.z != 0;
   // first-level loads, all independent
@@ -726,17 +752,21 @@ desc_pos_coef_kernel(const int* __restrict__ rowcol, const float* __restrict__ r
 
 // alpha_out / srow_out (optional, [B, Nc_pad]): the vectors ssp_desc_alpha would write for the same (scaled) gradients -- the
 // fused step gets them from this launch and skips that kernel.
+// bitsC_out (optional, with Nc = the unpadded cell count): the column-orientation indicator words, transposed from bitsR by
+// extra blocks of the same launch (the tensor-core forward then needs no transpose kernel).
 extern "C" int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow,
                                  const float* coldot, const uint32_t* bitsR, const float* mv_pad, const float* g3, float gscale,
                                  int gmode, const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef,
-                                 int* colrow_sorted, float* colcoef, float* alpha_out, float* srow_out, void* stream) {
+                                 int* colrow_sorted, float* colcoef, float* alpha_out, float* srow_out, uint32_t* bitsC_out,
+                                 int Nc, void* stream) {
   SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && g3 && out8 && rowcoef && colrow_sorted && colcoef,
               "ssp_desc_pos_coef: null pointer");
   SSP_REQUIRE(B > 0 && B <= 65535 && Nc_pad > 0 && Nc_pad % DESC_PAD == 0 && (gmode == 0 || gmode == 1), "ssp_desc_pos_coef: bad sizes");
-  dim3 grid(ssp_ceil_div(Nc_pad, 128), B, 2);
+  SSP_REQUIRE(!bitsC_out || (Nc > 0 && Nc <= Nc_pad), "ssp_desc_pos_coef: bitsC_out needs the cell count Nc");
+  dim3 grid(ssp_ceil_div(Nc_pad, 128), B, bitsC_out ? 6 : 2);
   desc_pos_coef_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rowcol, rowdot, colcnt, colrow, coldot, bitsR, mv_pad, g3, gscale, gmode,
                                                                out8, Nc_pad, lamda, mpos, rowcoef, colrow_sorted, colcoef, alpha_out,
-                                                               srow_out);
+                                                               srow_out, bitsC_out, (Nc + 31) / 32);
   SSP_CUDA_CHECK_LAUNCH("desc_pos_coef_kernel");
   return SSP_OK;
 }

@@ -50,3 +50,23 @@ __device__ __forceinline__ bool pair_positive(float wx, float wy, float cx, floa
   float d2 = __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx));
   return __fsqrt_rn(d2) <= dist;
 }
+
+// 32x32 bit-matrix transpose across a warp (lane r holds row r as a word): five shuffle / mask stages (block-swap
+// recursion).  out[lane c] bit r = in[lane r] bit c.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t a, int lane) {
+  // out[lane c] bit r = in[lane r] bit c
+#define SSP_TSTEP(J, M)                                                \
+  {                                                                    \
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, a, J);             \
+    if (lane & J) a ^= ((o >> J) ^ a) & (M);                            \
+    else          a ^= (((a >> J) ^ o) & (M)) << J;                     \
+  }
+  SSP_TSTEP(16, 0x0000FFFFu)
+  SSP_TSTEP(8, 0x00FF00FFu)
+  SSP_TSTEP(4, 0x0F0F0F0Fu)
+  SSP_TSTEP(2, 0x33333333u)
+  SSP_TSTEP(1, 0x55555555u)
+#undef SSP_TSTEP
+  return a;
+}
+

@@ -382,23 +382,6 @@ desc_dense_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // One warp per 32 x 32 tile: lane L holds the word of row 32 rw + inv(L) (inv = inverse of DESC_BITPOS), the tile is
 // transposed in five shuffle / mask stages (block-swap recursion), and lane L then holds the word of column 32 cw + inv(L).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t a, int lane) {
-  // out[lane c] bit r = in[lane r] bit c
-#define SSP_TSTEP(J, M)                                                \
-  {                                                                    \
-    const uint32_t o = __shfl_xor_sync(0xffffffffu, a, J);             \
-    if (lane & J) a ^= ((o >> J) ^ a) & (M);                            \
-    else          a ^= (((a >> J) ^ o) & (M)) << J;                     \
-  }
-  SSP_TSTEP(16, 0x0000FFFFu)
-  SSP_TSTEP(8, 0x00FF00FFu)
-  SSP_TSTEP(4, 0x0F0F0F0Fu)
-  SSP_TSTEP(2, 0x33333333u)
-  SSP_TSTEP(1, 0x55555555u)
-#undef SSP_TSTEP
-  return a;
-}
-
 __global__ void __launch_bounds__(256)
 desc_bits_transpose_kernel(const uint32_t* __restrict__ bitsR, uint32_t* __restrict__ bitsC, int NW, int NWv, int Nc_pad) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -307,8 +307,10 @@ class DescriptorLossFn(torch.autograd.Function):
             call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
             call("ssp_desc_pos_fwd_planes", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc, cell,
                  dist, lamda, mpos, mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
+            # bitsC (the column-orientation indicator words) is only read by the backward GEMM: it is transposed from bitsR by
+            # extra blocks of the backward's coefficient launch, not here
             call("ssp_desc_dense_fwd_tc", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(mv_pad), ptr(mvbits), B, Hc, Wc, mneg,
-                 ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+                 ptr(neg_part), ptr(bitsR), None, ptr(debug_S), st)
             planes = (Ahi, Alo, Bhi, Blo)
         else:
             # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
@@ -321,7 +323,7 @@ class DescriptorLossFn(torch.autograd.Function):
             else:
                 call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), None, ptr(Bhi), None, st)
                 call("ssp_desc_dense_fwd_tc", ptr(Ahi), None, ptr(Bhi), None, ptr(mv_pad), ptr(mvbits), B, Hc, Wc, mneg,
-                     ptr(neg_part), ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
+                     ptr(neg_part), ptr(bitsR), None, ptr(debug_S), st)
                 planes = (Ahi, None, Bhi, None)
             fork.join()
 
@@ -406,7 +408,7 @@ class DescriptorLossFn(torch.autograd.Function):
             # bitsR / bitsC already exclude the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
             call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
                  ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
-                 ptr(coefs[1]), ptr(alpha), ptr(srow), st)
+                 ptr(coefs[1]), ptr(alpha), ptr(srow), ptr(bitsC), Nc, st)
             call("ssp_desc_bits_gemm_tc_pair",
                  ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]), ptr(Bhi), ptr(Blo), ptr(dD),
                  ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow_sorted), ptr(coefs[1]), ptr(Ahi), ptr(Alo), ptr(dDw),
@@ -415,7 +417,7 @@ class DescriptorLossFn(torch.autograd.Function):
             with _Fork(dev) as f1:
                 call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
                      ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
-                     ptr(coefs[1]), None, None, stream_of(Dc))
+                     ptr(coefs[1]), None, None, ptr(bitsC), Nc, stream_of(Dc))
             call("ssp_desc_pack", ptr(Dwc), ptr(alpha), B, Dch, Nc, ptr(Shi), ptr(Slo), st)
             f1.join()
             # positive-pair partners from the packed planes of the forward (Dw for dD, D for dDw)
@@ -427,7 +429,7 @@ class DescriptorLossFn(torch.autograd.Function):
             with _Fork(dev) as f1:
                 call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
                      ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
-                     ptr(coefs[1]), None, None, stream_of(Dc))
+                     ptr(coefs[1]), None, None, None, 0, stream_of(Dc))
             call("ssp_desc_bits_gemm_simt", ptr(bitsR), ptr(Dwc), ptr(alpha), None, None, None, None, B, Dch, Nc, ptr(dD), st)
             call("ssp_desc_bits_gemm_simt", ptr(bitsC), ptr(Dc), None, ptr(alpha), None, None, None, B, Dch, Nc, ptr(dDw), st)
             f1.join()
