@@ -179,6 +179,16 @@ int ssp_desc_pos_coef(const int* rowcol, const float* rowdot, const int* colcnt,
                       const uint32_t* bitsR, const float* mv_pad, const float* g3, float gscale, int gmode,
                       const float* out8, int B, int Nc_pad, float lamda, float mpos, float* rowcoef, int* colrow_sorted,
                       float* colcoef, float* alpha_out, float* srow_out, uint32_t* bitsC_out, int Nc, void* stream);
+/* Backward prologue of the fused loss step (Train_model_heatmap_all.py:295-365 differentiated through the uniform total):
+ * ssp_detector_loss_bwd_pair (labels / masks at pixel resolution, both images, one upstream gradient) and ssp_desc_pos_coef
+ * (incl. alpha / srow / bitsC outputs) as ONE launch of heterogeneous blocks.  Same results as the two calls. */
+int ssp_step_bwd_prologue(const float* semi0, const float* labels0, const float* mask0, const float* semi1,
+                          const float* labels1, const float* mask1, int B, int Hc, int Wc, const float* fwd0 /*out3*/,
+                          const float* fwd1, const float* gout /*[1]*/, float* dsemi0, float* dsemi1,
+                          const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow, const float* coldot,
+                          const uint32_t* bitsR, const float* mv_pad, const float* g3, float gscale, int gmode,
+                          const float* out8, float lamda, float mpos, float* rowcoef, int* colrow_sorted, float* colcoef,
+                          float* alpha_out, float* srow_out, uint32_t* bitsC_out, void* stream);
 /* dD[b,:,r] += sum_n rowcoef[b,r,n] Dw[b,:,rowcol[b,r,n]];  dDw[b,:,c] += sum_n colcoef[b,c,n] D[b,:,colrow[b,c,n]] */
 int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const int* colrow, const float* colcoef, const float* D,
                        const float* Dw, int B, int Dch, int Nc, int which /*0 both, 1 dD, 2 dDw*/, float* dD, float* dDw,

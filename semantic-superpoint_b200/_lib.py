@@ -64,6 +64,7 @@ SIGNATURES = {
     "ssp_desc_pair_mask": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
     "ssp_desc_alpha": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "ssp_desc_pos_coef": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "ssp_step_bwd_prologue": (_I, [_P] * 6 + [_I] * 3 + [_P] * 5 + [_P] * 8 + [_F, _I, _P, _F, _F] + [_P] * 7),
     "ssp_desc_pos_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "ssp_desc_bits_gemm_simt": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "ssp_desc_bits_gemm_tc_planes": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
@@ -129,7 +130,7 @@ def check(rc, what):
 
 # kernels launched per entry point (memsets / copies not counted); the NMS drivers launch init + >= 2 rounds +
 # compact + rank, counted at their minimum
-KERNELS_PER_CALL = {"ssp_desc_dense_fwd_tc": 2, "ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2,
+KERNELS_PER_CALL = {"ssp_nms_fast": 5, "ssp_box_nms": 4, "ssp_detector_loss_fwd": 2, "ssp_detector_loss_fwd_pair": 2,
                     "ssp_sem_ce_fwd": 2, "ssp_sem_ce_up8": 2}
 kernel_count = 0
 _prof = None

@@ -8,6 +8,7 @@
 // warp reads 32 consecutive cells of one channel = one 128 B line; the 8x8 pixel block of a cell is
 // 8 rows of 32 B, read/written as 2 x float4 per row.  All kernels are HBM-bound.
 #include "common.cuh"
+#include "desc_pos_coef.cuh"
 
 #define CELL 8
 #define NCH 65
@@ -312,20 +313,19 @@ detector_loss_finalize_kernel(const __grid_constant__ DetProblems probs, int nbl
 }
 
 // d semi = gout * mask/den * softmax_bwd( (p - t) / max(p (1-p), 1e-12) )
+// (the body is a device function over the block index so that the fused step's backward prologue can run it as some of the
+// blocks of a launch whose other blocks are the descriptor backward's coefficient / transpose blocks)
 template <int FUSED2D>
-__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
-detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int Hc, int Wc) {
-  const DetProblem& pr = probs.p[blockIdx.y];
+__device__ __forceinline__ void det_bwd_block(const DetProblem& pr, int B, int Hc, int Wc, int bx, DetShared& sh) {
   const float* __restrict__ semi = pr.semi;
   const float* __restrict__ target = pr.target;
   const float* __restrict__ mask = pr.mask;
   const float* __restrict__ fwd_out = pr.fwd_out;
   const float* __restrict__ gout = pr.gout;
   float* __restrict__ dsemi = pr.out;
-  __shared__ DetShared sh;
   int Nc = Hc * Wc;
   int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  int cell = blockIdx.x * DET_CELLS + lane;
+  int cell = bx * DET_CELLS + lane;
   bool valid = cell < B * Nc;
   int b = valid ? cell / Nc : 0, ij = valid ? cell % Nc : 0;
   float v[DET_CPG], e[DET_CPG], t[DET_CPG], vd, ed, td, mk, inv_se, lnse;
@@ -354,6 +354,36 @@ detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
 #pragma unroll
   for (int c = 0; c < DET_CPG; ++c) o[c * Nc] = (e[c] * scale) * (t[c] - dot);
   if (grp == 3) o[DET_CPG * Nc] = (ed * scale) * (gd - dot);
+}
+
+template <int FUSED2D>
+__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
+detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int Hc, int Wc) {
+  __shared__ DetShared sh;
+  det_bwd_block<FUSED2D>(probs.p[blockIdx.y], B, Hc, Wc, blockIdx.x, sh);
+}
+
+// Backward prologue of the fused loss step: ONE launch whose first blocks are the descriptor backward's coefficient /
+// alpha / bit-transpose blocks (chains of dependent gathers and small streaming transposes) and whose remaining blocks are
+// the detector-loss backward of both images (HBM-bound).  As separate kernels they run back to back, each filling the GPU
+// with its own kind of stall; as blocks of one grid they share the SMs.  1-D grid: [pgx * pgy * pgz descriptor blocks |
+// ndet blocks of problem 0 | ndet blocks of problem 1].
+template <int FUSED2D>
+__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
+step_bwd_prologue_kernel(const __grid_constant__ DetProblems probs, const __grid_constant__ PosCoefArgs pc, int B, int Hc, int Wc,
+                         int ndet, int pgx, int pgy, int pgz) {
+  __shared__ DetShared sh;
+  int id = blockIdx.x;
+  const int npc = pgx * pgy * pgz;
+  if (id < npc) {
+    const int bz = id / (pgx * pgy), r = id - bz * (pgx * pgy);
+    const int by = r / pgx, bx = r - by * pgx;
+    desc_pos_coef_block(pc, bx, by, bz, pgx);
+    return;
+  }
+  id -= npc;
+  const int prob = id / ndet;
+  det_bwd_block<FUSED2D>(probs.p[prob], B, Hc, Wc, id - prob * ndet, sh);
 }
 
 extern "C" size_t ssp_detector_loss_ws_bytes(int B, int Hc, int Wc) {
@@ -446,6 +476,43 @@ extern "C" int ssp_detector_loss_bwd(const float* semi, const float* target, con
                                      void* stream) {
   return ssp_detector_loss_bwd_pair(semi, target, mask, nullptr, nullptr, nullptr, B, Hc, Wc, fused2d, fwd_out3, nullptr, gout,
                                     nullptr, dsemi, nullptr, stream);
+}
+
+// Fused-step backward prologue: ssp_detector_loss_bwd_pair (fused2d = 1, both images) and ssp_desc_pos_coef (with alpha / srow
+// / bitsC outputs) as ONE launch.  Arguments = those two calls'.
+extern "C" int ssp_step_bwd_prologue(const float* semi0, const float* labels0, const float* mask0, const float* semi1,
+                                     const float* labels1, const float* mask1, int B, int Hc, int Wc, const float* fwd0,
+                                     const float* fwd1, const float* gout, float* dsemi0, float* dsemi1,
+                                     const int* rowcol, const float* rowdot, const int* colcnt, const int* colrow,
+                                     const float* coldot, const uint32_t* bitsR, const float* mv_pad, const float* g3,
+                                     float gscale, int gmode, const float* out8, float lamda, float mpos, float* rowcoef,
+                                     int* colrow_sorted, float* colcoef, float* alpha_out, float* srow_out,
+                                     uint32_t* bitsC_out, void* stream) {
+  int rc;
+  if ((rc = det_check("ssp_step_bwd_prologue", semi0, labels0, mask0, B, Hc, Wc, 1))) return rc;
+  if ((rc = det_check("ssp_step_bwd_prologue", semi1, labels1, mask1, B, Hc, Wc, 1))) return rc;
+  SSP_REQUIRE(fwd0 && fwd1 && gout && dsemi0 && dsemi1, "ssp_step_bwd_prologue: null pointer (detector side)");
+  SSP_REQUIRE(rowcol && rowdot && colcnt && colrow && coldot && bitsR && mv_pad && g3 && out8 && rowcoef && colrow_sorted && colcoef,
+              "ssp_step_bwd_prologue: null pointer (descriptor side)");
+  SSP_REQUIRE(B <= 65535 && (gmode == 0 || gmode == 1), "ssp_step_bwd_prologue: bad sizes");
+  const int Nc = Hc * Wc, Nc_pad = desc_nc_pad(Nc);
+  DetProblems pb = {};
+  for (int i = 0; i < 2; ++i) {
+    pb.p[i].semi = i ? semi1 : semi0;
+    pb.p[i].target = i ? labels1 : labels0;
+    pb.p[i].mask = i ? mask1 : mask0;
+    pb.p[i].out = i ? dsemi1 : dsemi0;
+    pb.p[i].fwd_out = i ? fwd1 : fwd0;
+    pb.p[i].gout = gout;
+  }
+  PosCoefArgs A = {rowcol, rowdot, colcnt, colrow, coldot, bitsR, mv_pad, g3, gscale, gmode, out8, Nc_pad, lamda, mpos,
+                   rowcoef, colrow_sorted, colcoef, alpha_out, srow_out, bitsC_out, (Nc + 31) / 32};
+  const int ndet = ssp_ceil_div(B * Nc, DET_CELLS), pgx = Nc_pad / 128, pgy = B, pgz = bitsC_out ? 6 : 2;
+  const long long nblk = (long long)pgx * pgy * pgz + 2ll * ndet;
+  SSP_REQUIRE(nblk < 0x7fffffffll, "ssp_step_bwd_prologue: grid too large");
+  step_bwd_prologue_kernel<1><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(pb, A, B, Hc, Wc, ndet, pgx, pgy, pgz);
+  SSP_CUDA_CHECK_LAUNCH("step_bwd_prologue_kernel");
+  return SSP_OK;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -406,9 +406,19 @@ class DescriptorLossFn(torch.autograd.Function):
         # stream plan:  [pos_coef]  ||  [pack(alpha * Dw), unless folded]  ->  GEMM pair
         if fold:
             # bitsR / bitsC already exclude the columns with mask_valid = 0: dD = s * (I' @ Dw) on the forward planes, s = g_loss / norm
-            call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
-                 ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
-                 ptr(coefs[1]), ptr(alpha), ptr(srow), ptr(bitsC), Nc, st)
+            det_job = getattr(ctx, "det_job", None)
+            if det_job is not None:
+                # fused step: the detector-loss backward of both images rides in the same launch (heterogeneous blocks)
+                x0, t0, m0, x1, t1, m1, dout, dg, d0, d1 = det_job
+                call("ssp_step_bwd_prologue", ptr(x0), ptr(t0), ptr(m0), ptr(x1), ptr(t1), ptr(m1), B, Hc, Wc, ptr(dout[0]),
+                     ptr(dout[1]), ptr(dg), ptr(d0), ptr(d1),
+                     ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR), ptr(mv_pad), ptr(g3), gscale,
+                     gmode, ptr(out8), lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted), ptr(coefs[1]), ptr(alpha), ptr(srow),
+                     ptr(bitsC), st)
+            else:
+                call("ssp_desc_pos_coef", ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), ptr(bitsR),
+                     ptr(mv_pad), ptr(g3), gscale, gmode, ptr(out8), B, Ncp, lamda, mpos, ptr(coefs[0]), ptr(colrow_sorted),
+                     ptr(coefs[1]), ptr(alpha), ptr(srow), ptr(bitsC), Nc, st)
             call("ssp_desc_bits_gemm_tc_pair",
                  ptr(bitsR), ptr(Bhi), ptr(Blo), ptr(srow), ptr(rowcol), ptr(coefs[0]), ptr(Bhi), ptr(Blo), ptr(dD),
                  ptr(bitsC), ptr(Ahi), ptr(Alo), ptr(alpha), ptr(colrow_sorted), ptr(coefs[1]), ptr(Ahi), ptr(Alo), ptr(dDw),
@@ -504,11 +514,22 @@ class LossStepFn(torch.autograd.Function):
         dev = g.device
         g = f32c(g.reshape(1), dev)
         d0 = d1 = dD = dDw = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
+        want_det = ctx.needs_input_grad[0] or ctx.needs_input_grad[3]
+        want_desc = ctx.needs_input_grad[6] or ctx.needs_input_grad[7]
+        c2 = ctx.c2
+        c2.det_job = None
+        merged = (want_det and want_desc and getattr(c2, "fold_alpha", False) and c2.meta[8] != "fp32" and ctx.c1.fused2d)
+        if merged:
+            # one launch for the detector backward and the descriptor backward's coefficient / transpose blocks
+            x0, t0, m0, x1, t1, m1 = ctx.c1.saved_tensors
+            d0, d1 = torch.empty_like(x0), torch.empty_like(x1)
+            c2.det_job = (x0, t0, m0, x1, t1, m1, ctx.c1.out, g, d0, d1)
+        elif want_det:
             d0, _, _, d1 = DetectorLossPairFn.backward(ctx.c1, g, _SAME, None)[:4]
-        if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
-            ctx.c2.gscale = ctx.lambda_loss
-            dD, dDw = DescriptorLossFn.backward(ctx.c2, g, _SAME, None, None)[:2]
+        if want_desc:
+            c2.gscale = ctx.lambda_loss
+            dD, dDw = DescriptorLossFn.backward(c2, g, _SAME, None, None)[:2]
+            c2.det_job = None
         return d0, None, None, d1, None, None, dD, dDw, None, None, None, None, None, None
 
 

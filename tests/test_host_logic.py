@@ -154,9 +154,8 @@ def test_orchestration_call_sequences(monkeypatch):
     fwd = ["ssp_detector_loss_fwd_pair", "ssp_desc_geometry", "ssp_desc_pack2", "ssp_desc_pos_fwd_planes",
            "ssp_desc_dense_fwd_tc", "ssp_desc_finalize"]
     # one-node fused step: the mask is folded into the indicator words, no pack pass in the backward, both GEMMs in one launch
-    bwd_fold = ["ssp_desc_pos_coef", "ssp_desc_bits_gemm_tc_pair"]  # alpha / srow come out of the coefficient kernel
-    # (the fused step launches the detector pair on a forked stream; getMasks of the warped valid mask is fused into geometry)
-    assert run() == fwd + ["ssp_detector_loss_bwd_pair"] + bwd_fold
+    # backward of the one-node fused step: detector backward + coefficient / alpha / transpose blocks in ONE launch, then both GEMMs
+    assert run() == fwd + ["ssp_step_bwd_prologue", "ssp_desc_bits_gemm_tc_pair"]
     # separately differentiable components (reference multi_task_loss weighting): general mask path with the pack pass
     bwd_desc = ["ssp_desc_alpha", "ssp_desc_pos_coef", "ssp_desc_pack", "ssp_desc_bits_gemm_tc_pair"]
     unfused = run(fused=False)
