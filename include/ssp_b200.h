@@ -150,6 +150,11 @@ int ssp_desc_pack(const float* src /*[B,Dch,Nc]*/, const float* scale /*[B,Nc_pa
                   void* hi /*bf16 [B,Nc_pad,Dch]*/, void* lo /*or NULL*/, void* stream);
 int ssp_desc_pack2(const float* src0, const float* src1 /*or NULL*/, const float* scale, int B, int Dch, int Nc, void* hi0,
                    void* lo0, void* hi1, void* lo1, void* stream);
+/* ssp_desc_pack2 (both tensors, unscaled) and ssp_desc_geometry as ONE launch: they do not depend on each other */
+int ssp_desc_pack2_geometry(const float* src0, const float* src1, int B, int Dch, int Hc, int Wc, void* hi0, void* lo0 /*or NULL*/,
+                            void* hi1, void* lo1 /*or NULL*/, const float* H /*[B,3,3]*/, const float* mask_valid /*or NULL*/,
+                            const float* mask2d /*or NULL*/, int cell, float* wpts, float* mv_pad, double* mv_part,
+                            uint32_t* mvbits /*or NULL*/, void* stream);
 int ssp_desc_dense_tc_nblocks(int B, int Nc);
 /* tcgen05 forward (CTA-pair MMAs, M=256): negative hinge over all pairs + indicator words; bitsC = transpose of bitsR
  * (second kernel of the same call).  The lo planes must lie above their hi planes in memory (one allocation).

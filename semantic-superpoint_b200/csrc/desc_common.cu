@@ -9,14 +9,20 @@
 // ----------------------------------------------------------------------------------------------
 // mask_valid [B, Nc] (cell resolution) or, when it is NULL, mask2d [B, 1, 8 Hc, 8 Wc]: the cell mask is then the product of
 // the 64 sub-pixels of every cell, in the order of getMasks / cell_mask_kernel (Train_model_frontend_all.py:373-386).
-__global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* __restrict__ mask_valid,
-                                     const float* __restrict__ mask2d, int B,
-                                     int Hc, int Wc, int cell, int Nc_pad, float2* __restrict__ wpts,
-                                     float* __restrict__ mv_pad, double* __restrict__ mv_part,
-                                     uint32_t* __restrict__ mvbits) {
-  __shared__ double shd[32];
-  int b = blockIdx.y;
-  int c = blockIdx.x * blockDim.x + threadIdx.x;  // Nc_pad is a multiple of the block size
+struct GeomArgs {
+  const float* Hm; const float* mask_valid; const float* mask2d; int B, Hc, Wc, cell, Nc_pad;
+  float2* wpts; float* mv_pad; double* mv_part; uint32_t* mvbits;
+};
+#define GEOM_THREADS 256
+// (bx, by) = block coordinates in a (Nc_pad / GEOM_THREADS, B) grid; shd: >= 32 doubles of shared memory
+__device__ __forceinline__ void desc_geometry_block(const GeomArgs& A, int bx, int by, int gridx, double* shd) {
+  const float* __restrict__ Hm = A.Hm; const float* __restrict__ mask_valid = A.mask_valid;
+  const float* __restrict__ mask2d = A.mask2d;
+  const int Hc = A.Hc, Wc = A.Wc, cell = A.cell, Nc_pad = A.Nc_pad;
+  float2* __restrict__ wpts = A.wpts; float* __restrict__ mv_pad = A.mv_pad; double* __restrict__ mv_part = A.mv_part;
+  uint32_t* __restrict__ mvbits = A.mvbits;
+  int b = by;
+  int c = bx * blockDim.x + threadIdx.x;  // Nc_pad is a multiple of the block size
   int Nc = Hc * Wc;
   float2 w = make_float2(SSP_FAR, SSP_FAR);
   float mv = 0.f;
@@ -64,10 +70,15 @@ __global__ void desc_geometry_kernel(const float* __restrict__ Hm, const float* 
   }
   // per-block partial of sum(mask_valid) for the global normaliser (summed in fixed order by finalize)
   double part = block_sum_d(mvs, shd);
-  if (threadIdx.x == 0) mv_part[(size_t)b * gridDim.x + blockIdx.x] = part;
+  if (threadIdx.x == 0) mv_part[(size_t)b * gridx + bx] = part;
 }
 
-extern "C" int ssp_desc_geometry_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / 128); }
+__global__ void __launch_bounds__(GEOM_THREADS) desc_geometry_kernel(const __grid_constant__ GeomArgs A) {
+  __shared__ double shd[32];
+  desc_geometry_block(A, blockIdx.x, blockIdx.y, gridDim.x, shd);
+}
+
+extern "C" int ssp_desc_geometry_nblocks(int B, int Nc) { return B * (desc_nc_pad(Nc) / GEOM_THREADS); }
 
 // mvbits (optional): [B, Nc_pad/32] words of mask_valid != 0 in DESC_BITPOS order for the "fold" mode of the tensor-core
 // engine; requesting them also makes a non-binary mask poison the normaliser with NaN.
@@ -80,9 +91,9 @@ extern "C" int ssp_desc_geometry(const float* Hm, const float* mask_valid, const
   SSP_REQUIRE(!mask2d || mask_valid || (cell == 8 && ((uintptr_t)mask2d & 15) == 0),
               "ssp_desc_geometry: the fused pixel mask needs cell_size 8 and a 16-byte aligned mask");
   int Nc_pad = desc_nc_pad(Hc * Wc);
-  dim3 grid(ssp_ceil_div(Nc_pad, 128), B);
-  desc_geometry_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Hm, mask_valid, mask2d, B, Hc, Wc, cell, Nc_pad,
-                                                                reinterpret_cast<float2*>(wpts), mv_pad, mv_part, mvbits);
+  dim3 grid(Nc_pad / GEOM_THREADS, B);
+  GeomArgs A = {Hm, mask_valid, mask2d, B, Hc, Wc, cell, Nc_pad, reinterpret_cast<float2*>(wpts), mv_pad, mv_part, mvbits};
+  desc_geometry_kernel<<<grid, GEOM_THREADS, 0, (cudaStream_t)stream>>>(A);
   SSP_CUDA_CHECK_LAUNCH("desc_geometry_kernel");
   return SSP_OK;
 }
@@ -648,19 +659,24 @@ extern "C" int ssp_desc_pos_apply(const int* rowcol, const float* rowcoef, const
 // ----------------------------------------------------------------------------------------------
 #define PK_CELLS 64   // cells per block: 256 contiguous bytes of every channel row
 #define PK_CH 128     // channels per block (the grid's z also splits the descriptor): 32 KB tile, 6 blocks per SM
-__global__ void __launch_bounds__(256)
-desc_pack_kernel(const float* __restrict__ src0, const float* __restrict__ src1, const float* __restrict__ scale,
-                 int Dch, int Nc, int Nc_pad, __nv_bfloat16* __restrict__ hi0, __nv_bfloat16* __restrict__ lo0,
-                 __nv_bfloat16* __restrict__ hi1, __nv_bfloat16* __restrict__ lo1) {
-  __shared__ float tile[PK_CH][PK_CELLS + 1];  // [channel][cell]: both phases conflict-free (row stride 65 = 1 mod 32)
+struct PackArgs {
+  const float* src0; const float* src1; const float* scale; int Dch, Nc, Nc_pad;
+  __nv_bfloat16* hi0; __nv_bfloat16* lo0; __nv_bfloat16* hi1; __nv_bfloat16* lo1;
+};
+// (bx, by, bz) = block coordinates in a (Nc_pad / PK_CELLS, B, tensors x channel blocks) grid; tile: PK_CH x (PK_CELLS + 1) floats
+__device__ __forceinline__ void desc_pack_block(const PackArgs& A, int bx, int by, int bz, float (*tile)[PK_CELLS + 1]) {
+  const float* __restrict__ src0 = A.src0; const float* __restrict__ src1 = A.src1; const float* __restrict__ scale = A.scale;
+  const int Dch = A.Dch, Nc = A.Nc, Nc_pad = A.Nc_pad;
+  __nv_bfloat16* __restrict__ hi0 = A.hi0; __nv_bfloat16* __restrict__ lo0 = A.lo0;
+  __nv_bfloat16* __restrict__ hi1 = A.hi1; __nv_bfloat16* __restrict__ lo1 = A.lo1;
   // blockIdx.z = (tensor, channel block)
   const int nchb = (Dch + PK_CH - 1) / PK_CH;
   const int which = blockIdx.z / nchb, d0 = (blockIdx.z - which * nchb) * PK_CH;
   const float* __restrict__ src = which ? src1 : src0;
   __nv_bfloat16* __restrict__ hi = which ? hi1 : hi0;
   __nv_bfloat16* __restrict__ lo = which ? lo1 : lo0;
-  const int b = blockIdx.y;
-  const int c0 = blockIdx.x * PK_CELLS;
+  const int b = by;
+  const int c0 = bx * PK_CELLS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // ---- phase 1: warp = one channel row at a time, lanes = cells (lane, lane + 32); 8 rows = 16 loads in flight per thread
   const int ca = c0 + lane, cb = ca + 32;
@@ -709,6 +725,24 @@ desc_pack_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
   }
 }
 
+__global__ void __launch_bounds__(256) desc_pack_kernel(const __grid_constant__ PackArgs A) {
+  __shared__ float tile[PK_CH][PK_CELLS + 1];
+  desc_pack_block(A, blockIdx.x, blockIdx.y, blockIdx.z, tile);
+}
+
+// Forward prologue of the descriptor loss: the operand pack (z < npack) and the geometry kernel (z == npack; only its first
+// Nc_pad / 256 x-blocks exist) do not depend on each other -- one launch instead of two, the light geometry blocks fill in
+// next to the streaming pack blocks.
+__global__ void __launch_bounds__(256)
+desc_pack_geometry_kernel(const __grid_constant__ PackArgs P, const __grid_constant__ GeomArgs G, int npack, int ggx) {
+  __shared__ __align__(16) float tile[PK_CH][PK_CELLS + 1];
+  if ((int)blockIdx.z < npack) {
+    desc_pack_block(P, blockIdx.x, blockIdx.y, blockIdx.z, tile);
+  } else if ((int)blockIdx.x < ggx) {
+    desc_geometry_block(G, blockIdx.x, blockIdx.y, ggx, reinterpret_cast<double*>(&tile[0][0]));
+  }
+}
+
 // Packs one (src1 == NULL) or two tensors in one launch; `scale` applies to both.
 extern "C" int ssp_desc_pack2(const float* src0, const float* src1, const float* scale, int B, int Dch, int Nc, void* hi0,
                               void* lo0, void* hi1, void* lo1, void* stream) {
@@ -718,9 +752,28 @@ extern "C" int ssp_desc_pack2(const float* src0, const float* src1, const float*
   const int nchb = (Dch + PK_CH - 1) / PK_CH;
   SSP_REQUIRE(2 * nchb <= 65535, "ssp_desc_pack: descriptor dim %d too large", Dch);
   dim3 grid(Nc_pad / PK_CELLS, B, (src1 ? 2 : 1) * nchb);
-  desc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src0, src1, scale, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi0,
-                                                           (__nv_bfloat16*)lo0, (__nv_bfloat16*)hi1, (__nv_bfloat16*)lo1);
+  PackArgs A = {src0, src1, scale, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi0, (__nv_bfloat16*)lo0, (__nv_bfloat16*)hi1, (__nv_bfloat16*)lo1};
+  desc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
   SSP_CUDA_CHECK_LAUNCH("desc_pack_kernel");
+  return SSP_OK;
+}
+
+// ssp_desc_pack2 (both tensors, no scale) and ssp_desc_geometry as ONE launch (arguments = those two calls')
+extern "C" int ssp_desc_pack2_geometry(const float* src0, const float* src1, int B, int Dch, int Hc, int Wc, void* hi0, void* lo0,
+                                       void* hi1, void* lo1, const float* Hm, const float* mask_valid, const float* mask2d,
+                                       int cell, float* wpts, float* mv_pad, double* mv_part, uint32_t* mvbits, void* stream) {
+  SSP_REQUIRE(src0 && src1 && hi0 && hi1 && Hm && wpts && mv_pad && mv_part, "ssp_desc_pack2_geometry: null pointer");
+  SSP_REQUIRE(B > 0 && B <= 65535 && Dch > 0 && Dch % 2 == 0 && Hc > 0 && Wc > 0 && cell > 0, "ssp_desc_pack2_geometry: bad sizes");
+  SSP_REQUIRE(!mask2d || mask_valid || (cell == 8 && ((uintptr_t)mask2d & 15) == 0),
+              "ssp_desc_pack2_geometry: the fused pixel mask needs cell_size 8 and a 16-byte aligned mask");
+  const int Nc = Hc * Wc, Nc_pad = desc_nc_pad(Nc);
+  const int nchb = (Dch + PK_CH - 1) / PK_CH, npack = 2 * nchb;
+  SSP_REQUIRE(npack + 1 <= 65535, "ssp_desc_pack2_geometry: descriptor dim %d too large", Dch);
+  PackArgs P = {src0, src1, nullptr, Dch, Nc, Nc_pad, (__nv_bfloat16*)hi0, (__nv_bfloat16*)lo0, (__nv_bfloat16*)hi1, (__nv_bfloat16*)lo1};
+  GeomArgs G = {Hm, mask_valid, mask2d, B, Hc, Wc, cell, Nc_pad, reinterpret_cast<float2*>(wpts), mv_pad, mv_part, mvbits};
+  dim3 grid(Nc_pad / PK_CELLS, B, npack + 1);
+  desc_pack_geometry_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, G, npack, Nc_pad / GEOM_THREADS);
+  SSP_CUDA_CHECK_LAUNCH("desc_pack_geometry_kernel");
   return SSP_OK;
 }
 

@@ -273,7 +273,10 @@ class DescriptorLossFn(torch.autograd.Function):
         mask2d = None
         if isinstance(mv, tuple):  # ("2d", mask [B,1,8Hc,8Wc]): LossStepFn -- getMasks is fused into the geometry kernel
             mask2d, mv = mv[1], None
-        call("ssp_desc_geometry", ptr(Hm), ptr(mv), ptr(mask2d), B, Hc, Wc, cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), ptr(mvbits), st)
+        geom_args = (ptr(Hm), ptr(mv), ptr(mask2d), cell, ptr(wpts), ptr(mv_pad), ptr(mv_part), ptr(mvbits))
+        if engine == "fp32":
+            call("ssp_desc_geometry", geom_args[0], geom_args[1], geom_args[2], B, Hc, Wc, *geom_args[3:], st)
+        # tensor-core engines: the geometry blocks ride in the operand pack's launch (independent work, one launch instead of two)
 
         # sparse positive pairs: exact dots, partial sums, pair lists for the backward
         maxp = lib.ssp_desc_maxp()
@@ -304,7 +307,7 @@ class DescriptorLossFn(torch.autograd.Function):
         if split:
             # bf16x3: the positive pairs read the packed hi/lo planes (2 x 512 contiguous bytes per cell instead of 256
             # strided channels), so they run right after the pack, in front of the tensor-core kernel
-            call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), st)
+            call("ssp_desc_pack2_geometry", ptr(Dc), ptr(Dwc), B, Dch, Hc, Wc, ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), *geom_args, st)
             call("ssp_desc_pos_fwd_planes", ptr(Ahi), ptr(Alo), ptr(Bhi), ptr(Blo), ptr(wpts), ptr(mv_pad), B, Hc, Wc, cell,
                  dist, lamda, mpos, mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), st)
             # bitsC (the column-orientation indicator words) is only read by the backward GEMM: it is transposed from bitsR by
@@ -314,6 +317,8 @@ class DescriptorLossFn(torch.autograd.Function):
             planes = (Ahi, Alo, Bhi, Blo)
         else:
             # the HBM-bound exact positive-pair kernel overlaps the pack + tensor-core kernels
+            if engine != "fp32":  # single-pass bf16: pack + geometry first (the positive-pair kernel needs the warped points)
+                call("ssp_desc_pack2_geometry", ptr(Dc), ptr(Dwc), B, Dch, Hc, Wc, ptr(Ahi), None, ptr(Bhi), None, *geom_args, st)
             with _Fork(dev) as fork:
                 call("ssp_desc_pos_fwd", ptr(Dc), ptr(Dwc), ptr(wpts), ptr(mv_pad), B, Hc, Wc, Dch, cell, dist, lamda, mpos,
                      mneg, ptr(pos_part), ptr(rowcol), ptr(rowdot), ptr(colcnt), ptr(colrow), ptr(coldot), stream_of(Dc))
@@ -321,7 +326,6 @@ class DescriptorLossFn(torch.autograd.Function):
                 call("ssp_desc_dense_fwd_simt", ptr(Dc), ptr(Dwc), ptr(mv_pad), B, Hc, Wc, Dch, mneg, ptr(neg_part),
                      ptr(bitsR), ptr(bitsC), ptr(debug_S), st)
             else:
-                call("ssp_desc_pack2", ptr(Dc), ptr(Dwc), None, B, Dch, Nc, ptr(Ahi), None, ptr(Bhi), None, st)
                 call("ssp_desc_dense_fwd_tc", ptr(Ahi), None, ptr(Bhi), None, ptr(mv_pad), ptr(mvbits), B, Hc, Wc, mneg,
                      ptr(neg_part), ptr(bitsR), None, ptr(debug_S), st)
                 planes = (Ahi, None, Bhi, None)

@@ -151,7 +151,7 @@ def test_orchestration_call_sequences(monkeypatch):
         out["loss"].backward()
         return list(calls)
 
-    fwd = ["ssp_detector_loss_fwd_pair", "ssp_desc_geometry", "ssp_desc_pack2", "ssp_desc_pos_fwd_planes",
+    fwd = ["ssp_detector_loss_fwd_pair", "ssp_desc_pack2_geometry", "ssp_desc_pos_fwd_planes",
            "ssp_desc_dense_fwd_tc", "ssp_desc_finalize"]
     # one-node fused step: the mask is folded into the indicator words, no pack pass in the backward, both GEMMs in one launch
     # backward of the one-node fused step: detector backward + coefficient / alpha / transpose blocks in ONE launch, then both GEMMs
@@ -159,7 +159,7 @@ def test_orchestration_call_sequences(monkeypatch):
     # separately differentiable components (reference multi_task_loss weighting): general mask path with the pack pass
     bwd_desc = ["ssp_desc_alpha", "ssp_desc_pos_coef", "ssp_desc_pack", "ssp_desc_bits_gemm_tc_pair"]
     unfused = run(fused=False)
-    assert unfused[:6] == fwd and sorted(unfused[6:]) == sorted(bwd_desc + ["ssp_detector_loss_bwd_pair"])
+    assert unfused[:5] == fwd and sorted(unfused[5:]) == sorted(bwd_desc + ["ssp_detector_loss_bwd_pair"])
     assert [c for c in run(engine="fp32") if "_desc_" in c] == [
         "ssp_desc_geometry", "ssp_desc_pos_fwd", "ssp_desc_dense_fwd_simt", "ssp_desc_finalize", "ssp_desc_alpha",
         "ssp_desc_pos_coef", "ssp_desc_bits_gemm_simt", "ssp_desc_bits_gemm_simt", "ssp_desc_pos_apply"]
