@@ -353,7 +353,8 @@ def run_ours(args):
             "ssp_desc_pos_coef": ("hbm", 8.0 * B * NC * 16 * 4),
             "ssp_detector_loss_fwd_pair": ("hbm", 2 * B * (65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
             "ssp_detector_loss_bwd_pair": ("hbm", 2 * B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0)),
-            "ssp_desc_pack2": ("hbm", 2 * B * NC * DCH * 4 * 2.0),
+            "ssp_desc_pack2": ("hbm", 2 * B * NC * DCH * 4 * 2.0), "ssp_desc_pack2_geometry": ("hbm", 2 * B * NC * DCH * 4 * 2.0),
+            "ssp_step_bwd_prologue": ("hbm", 2 * B * (2 * 65 * NC * 4 + 2 * H_IMG * W_IMG * 4.0) + 8.0 * B * NC * 16 * 4),
         }
         bound_tbl["ssp_desc_pos_apply"] = ("hbm", 2.0 * 3.0 * B * NC * DCH * 4)
         # the roofline is reported for the dominant KERNEL of the dense contraction / its data movement

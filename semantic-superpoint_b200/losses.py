@@ -19,7 +19,6 @@ _ENGINES = ("bf16x3", "bf16", "fp32")
 # pack pass (measured: 0.339 -> 0.330 ms per step).  SSP_BG_ALPHA=pack restores the general path (alpha * Dw packed into
 # its own planes), which is also what the reference-signature `descriptor_loss` always uses (its mask may be anything).
 FOLD_ALPHA = os.environ.get("SSP_BG_ALPHA", "fold") != "pack"
-_ones = {}
 _engine = "bf16x3"
 CHECK_LIST_OVERFLOW = False  # tests turn this on (costs a host sync per call)
 
