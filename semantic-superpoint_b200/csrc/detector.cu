@@ -369,7 +369,7 @@ detector_loss_bwd_kernel(const __grid_constant__ DetProblems probs, int B, int H
 // with its own kind of stall; as blocks of one grid they share the SMs.  1-D grid: [pgx * pgy * pgz descriptor blocks |
 // ndet blocks of problem 0 | ndet blocks of problem 1].
 template <int FUSED2D>
-__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS)
+__global__ void __launch_bounds__(DET_CELLS * DET_GROUPS, 8)  // 64 registers: the detector blocks keep their stand-alone occupancy
 step_bwd_prologue_kernel(const __grid_constant__ DetProblems probs, const __grid_constant__ PosCoefArgs pc, int B, int Hc, int Wc,
                          int ndet, int pgx, int pgy, int pgz) {
   __shared__ DetShared sh;
