@@ -368,12 +368,14 @@ def run_ours(args):
         traffic = None
         kern_of = {"ssp_desc_bits_gemm_tc_pair": "desc_bits_gemm_tc_kernel", "ssp_desc_bits_gemm_tc_planes": "desc_bits_gemm_tc_kernel",
                    "ssp_desc_dense_fwd_tc": "desc_dense_fwd_tc_kernel",
-                   "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel"}
-        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+                   "ssp_desc_pack2": "desc_pack_kernel", "ssp_detector_loss_fwd_pair": "detector_loss_fwd_kernel",
+                   "ssp_desc_pack2_geometry": "desc_pack_geometry_kernel", "ssp_step_bwd_prologue": "step_bwd_prologue_kernel",
+                   "ssp_desc_pos_fwd_planes": "desc_pos_fwd_planes_kernel"}
+        tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
         if top in kern_of and os.path.exists(tpath) and args.engine == "bf16x3":
             traffic = json.load(open(tpath)).get(kern_of[top], {}).get("dram_bytes_per_launch")
         roofline = {"kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
+                    "traffic": traffic, "traffic_source": "profiles/r2_ncu_traffic.json (ncu --set full of this command, DRAM read + write bytes per launch)" if traffic else None, "peak_source": pk["src"] + (" burst bf16" if kind == "tensor" else " copy"),
                     "us_per_launch": shares[top]["us_per_call"],
                     "note": "algorithmic 2*Nc^2*256 flop per pair x 32 pairs per launch; bf16x3 issues 3 (fwd) / 2 (bwd) MMAs per "
                             "algorithmic MAC, so its ceiling is 1/3 (1/2) of the bf16 peak"}
